@@ -1,0 +1,130 @@
+/*
+ * rag_b200.h -- C ABI of librag_b200.so: the B200 (sm_100a) stereo hot path of chzhang18/RAG.
+ *
+ * The reference (pure PyTorch) has no FFI for this path; these entry points are what a
+ * binding for it would call.  Each one names the reference lines it replaces (paths
+ * relative to the reference repo root).  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major fp32 unless it says "host";
+ *   - the caller owns every buffer (inputs, outputs, stats); the library never allocates,
+ *     frees or retains device memory; outputs are fully overwritten (no pre-zeroing needed);
+ *   - launches are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream) on the calling thread's current device; no host synchronisation;
+ *   - return value: 0 on success; <0 argument error (RAG_E_*); >0 a cudaError_t.  The text
+ *     of the last error on the calling thread is rag_last_error().  No exceptions cross the ABI;
+ *   - re-entrant and thread-safe: no mutable global state except the thread-local error text.
+ *
+ * Shapes: B batch (stereo pairs), C feature channels (12 in the reference), Hf,Wf = H/3,W/3,
+ * Df = int(maxdisp/3) low-res disparity bins, D = maxdisp full-res bins.
+ */
+#ifndef RAG_B200_H
+#define RAG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RAG_B200_ABI_VERSION 3
+
+#if defined(__GNUC__)
+#define RAG_API __attribute__((visibility("default")))
+#else
+#define RAG_API
+#endif
+
+#define RAG_OK 0
+#define RAG_E_NULL (-1)     /* a required pointer is NULL                      */
+#define RAG_E_SHAPE (-2)    /* a dimension is <= 0 or out of the supported range */
+#define RAG_E_ALIGN (-3)    /* a pointer is not 4-byte (16-byte where stated) aligned */
+#define RAG_E_VARIANT (-4)  /* unknown kernel variant id                        */
+
+RAG_API int rag_abi_version(void);
+RAG_API const char* rag_last_error(void);
+/* Number of kernels this library has launched from the calling process (monotonic counter;
+ * used by bench.py to report `gpu_launches`). */
+RAG_API uint64_t rag_launch_count(void);
+
+/* ---- cost volume -------------------------------------------------------------------------
+ * Replaces src/models/rag_model.py:375-383 (Network.forward), :694-702 (search_forward) and
+ * src/automl/mdenas_basicmodel.py:83-91 (BasicNetwork.forward):
+ *   cost[b,   c, d,h,w] = x[b,c,h,w]   if w >= d else 0
+ *   cost[b, C+c, d,h,w] = y[b,c,h,w-d] if w >= d else 0          d in [0,Df)
+ * x,y [B,C,Hf,Wf]; cost [B,2C,Df,Hf,Wf].  Bit-exact copy. */
+RAG_API int rag_cost_volume_fwd(const float* x, const float* y, float* cost,
+                        int B, int C, int Df, int Hf, int Wf, void* stream);
+
+/* Gradient of the above (replaces the 128 chained CopySlices autograd nodes the reference
+ * loop creates).  gx[b,c,h,w] = sum_d gcost[b,c,d,h,w] (d<=w), gy[b,c,h,w] = sum_d
+ * gcost[b,C+c,d,h,w+d] (w+d<Wf); both summed sequentially in fp32 with d DESCENDING, which is
+ * the order autograd uses, so the result is bit-identical to the reference.  No atomics. */
+RAG_API int rag_cost_volume_bwd(const float* gcost, float* gx, float* gy,
+                        int B, int C, int Df, int Hf, int Wf, void* stream);
+
+/* ---- disparity head ----------------------------------------------------------------------
+ * Replaces src/models/rag_model.py:32-44 (Disp.forward) + :18-29 (DisparityRegression):
+ *   v = trilinear_upsample(cost_lr -> [maxdisp, 3Hl, 3Wl], align_corners=False)
+ *   disp[b,h,w] = sum_k k * softmax_k(-v[b,k,h,w])
+ * cost_lr [B,1,Dl,Hl,Wl] (Dl need not equal maxdisp/3); disp [B,3Hl,3Wl].
+ * stats (nullable) [B,2,3Hl,3Wl]: plane 0 = reference exponent m (log2 domain), plane 1 =
+ * 1/sum_k 2^(z_k-m) with z_k = -log2(e)*v_k -- what the backward needs to rebuild p_k. */
+RAG_API int rag_disp_head_fwd(const float* cost_lr, float* disp, float* stats,
+                      int B, int Dl, int Hl, int Wl, int maxdisp, void* stream);
+
+/* Gradient of the head w.r.t. cost_lr (replaces autograd through interpolate/softmin/mul/sum;
+ * PyTorch's CUDA trilinear backward uses atomicAdd -- this is a deterministic gather).
+ * gdisp, disp [B,3Hl,3Wl]; stats [B,2,3Hl,3Wl] from the forward; gcost_lr [B,1,Dl,Hl,Wl]. */
+RAG_API int rag_disp_head_bwd(const float* cost_lr, const float* gdisp, const float* disp,
+                      const float* stats, float* gcost_lr,
+                      int B, int Dl, int Hl, int Wl, int maxdisp, void* stream);
+
+/* DisparityRegression alone (src/models/rag_model.py:18-29): p [B,D,H,W] -> out [B,H,W],
+ * out = sum_k k*p[b,k,h,w]. */
+RAG_API int rag_disparity_regression_fwd(const float* p, float* out, int B, int D, int H, int W, void* stream);
+/* Its gradient: gp[b,k,h,w] = k * gout[b,h,w]. */
+RAG_API int rag_disparity_regression_bwd(const float* gout, float* gp, int B, int D, int H, int W, void* stream);
+
+/* Debug/validation: the upsample alone (F.interpolate at rag_model.py:40), out [B,maxdisp,3Hl,3Wl].
+ * fma_index != 0 evaluates the source index with a fused multiply-add (what PyTorch's CUDA
+ * kernel compiles to); 0 uses separate multiply and subtract. */
+RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int Dl, int Hl, int Wl,
+                           int maxdisp, int fma_index, void* stream);
+
+/* ---- variants (tuning / A-B measurement only; the functions above pick the default) -------- */
+RAG_API int rag_cost_volume_fwd_v(const float* x, const float* y, float* cost,
+                          int B, int C, int Df, int Hf, int Wf, int variant, void* stream);
+RAG_API int rag_cost_volume_bwd_v(const float* gcost, float* gx, float* gy,
+                          int B, int C, int Df, int Hf, int Wf, int variant, void* stream);
+RAG_API int rag_disp_head_fwd_v(const float* cost_lr, float* disp, float* stats,
+                        int B, int Dl, int Hl, int Wl, int maxdisp, int variant, void* stream);
+RAG_API int rag_disp_head_bwd_v(const float* cost_lr, const float* gdisp, const float* disp,
+                        const float* stats, float* gcost_lr,
+                        int B, int Dl, int Hl, int Wl, int maxdisp, int variant, void* stream);
+
+/* ---- adjacent rows -------------------------------------------------
+ * Masked loss + metrics on the disparity map, one fused reduction.  Replaces
+ * src/approaches/rag.py:418-430 + src/utilstool/metrics.py:22-65 (about 10*B tiny kernels and
+ * 6+ .item() syncs per batch).  est, gt [B,H,W]; sums: DOUBLE [B,8] per image:
+ *   0 n_mask (0<gt<maxdisp)  1 n_pos (gt>0)  2 sum smooth_l1  3 sum |gt-est|
+ *   4 n_d1 (E>3 && E/|gt|>0.05)  5 n_E>1  6 n_E>2  7 n_E>3
+ * Deterministic (fixed-order reduction, no float atomics).  scratch: DOUBLE [B, rag_loss_metrics_scratch(H,W)]. */
+RAG_API int rag_loss_metrics_scratch(int H, int W);
+RAG_API int rag_loss_metrics_sums(const float* est, const float* gt, double* sums, double* scratch,
+                          int B, int H, int W, float maxdisp, void* stream);
+/* gradient of mean masked smooth-L1 (beta=1) w.r.t. est: gest = gloss * dsl1(est-gt) / n_mask_total
+ * where mask true, else 0.  n_mask_total read from device `sums` rows (sum over b of sums[b][0]). */
+RAG_API int rag_smooth_l1_bwd(const float* est, const float* gt, const double* sums, const float* gloss,
+                      float* gest, int B, int H, int W, float maxdisp, void* stream);
+
+/* Eval-time input staging: uint8 HWC image -> ImageNet-normalised fp32 CHW, zero-padded on the
+ * top and right.  Replaces src/dataloaders/data_io.py:6-13 + stereo_dataset.py:88-102.
+ * img [B,H,W,3] uint8; out [B,3,H+top_pad,W+right_pad] fp32. */
+RAG_API int rag_normalize_pad(const uint8_t* img, float* out, int B, int H, int W,
+                      int top_pad, int right_pad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAG_B200_H */

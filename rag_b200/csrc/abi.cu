@@ -1,0 +1,85 @@
+// extern "C" surface of librag_b200.so -- see include/rag_b200.h for the contract.
+#include "common.cuh"
+
+namespace rag {
+thread_local char g_last_error[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int cost_volume_fwd(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int cost_volume_bwd(const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
+int upsample_trilinear(const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int disp_head_fwd(const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
+int disp_head_bwd(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int disparity_regression_fwd(const float*, float*, int, int, int, int, cudaStream_t);
+int disparity_regression_bwd(const float*, float*, int, int, int, int, cudaStream_t);
+int loss_metrics_scratch(int, int);
+int loss_metrics_sums(const float*, const float*, double*, double*, int, int, int, float, cudaStream_t);
+int smooth_l1_bwd(const float*, const float*, const double*, const float*, float*, int, int, int, float, cudaStream_t);
+int normalize_pad(const uint8_t*, float*, int, int, int, int, int, cudaStream_t);
+}  // namespace rag
+
+using namespace rag;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+// default variants (picked from the measurements in profiles/)
+static constexpr int kCvFwdDefault = 0;
+static constexpr int kCvBwdDefault = 0;
+static constexpr int kHeadFwdDefault = -1;  // -1 = x3 kernel when maxdisp == 3*Dl, generic otherwise
+static constexpr int kHeadBwdDefault = -1;
+
+extern "C" {
+
+RAG_API int rag_abi_version(void) { return RAG_B200_ABI_VERSION; }
+RAG_API const char* rag_last_error(void) { return g_last_error; }
+RAG_API uint64_t rag_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+RAG_API int rag_cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf, void* stream) {
+    return cost_volume_fwd(x, y, cost, B, C, Df, Hf, Wf, kCvFwdDefault, ST(stream));
+}
+RAG_API int rag_cost_volume_bwd(const float* gcost, float* gx, float* gy, int B, int C, int Df, int Hf, int Wf, void* stream) {
+    return cost_volume_bwd(gcost, gx, gy, B, C, Df, Hf, Wf, kCvBwdDefault, ST(stream));
+}
+RAG_API int rag_disp_head_fwd(const float* cost_lr, float* disp, float* stats, int B, int Dl, int Hl, int Wl, int maxdisp, void* stream) {
+    return disp_head_fwd(cost_lr, disp, stats, B, Dl, Hl, Wl, maxdisp, kHeadFwdDefault, ST(stream));
+}
+RAG_API int rag_disp_head_bwd(const float* cost_lr, const float* gdisp, const float* disp, const float* stats, float* gcost_lr,
+                      int B, int Dl, int Hl, int Wl, int maxdisp, void* stream) {
+    return disp_head_bwd(cost_lr, gdisp, disp, stats, gcost_lr, B, Dl, Hl, Wl, maxdisp, kHeadBwdDefault, ST(stream));
+}
+RAG_API int rag_disparity_regression_fwd(const float* p, float* out, int B, int D, int H, int W, void* stream) {
+    return disparity_regression_fwd(p, out, B, D, H, W, ST(stream));
+}
+RAG_API int rag_disparity_regression_bwd(const float* gout, float* gp, int B, int D, int H, int W, void* stream) {
+    return disparity_regression_bwd(gout, gp, B, D, H, W, ST(stream));
+}
+RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int Dl, int Hl, int Wl, int maxdisp, int fma_index, void* stream) {
+    return upsample_trilinear(cost_lr, out, B, Dl, Hl, Wl, maxdisp, fma_index, ST(stream));
+}
+
+RAG_API int rag_cost_volume_fwd_v(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf, int variant, void* stream) {
+    return cost_volume_fwd(x, y, cost, B, C, Df, Hf, Wf, variant, ST(stream));
+}
+RAG_API int rag_cost_volume_bwd_v(const float* gcost, float* gx, float* gy, int B, int C, int Df, int Hf, int Wf, int variant, void* stream) {
+    return cost_volume_bwd(gcost, gx, gy, B, C, Df, Hf, Wf, variant, ST(stream));
+}
+RAG_API int rag_disp_head_fwd_v(const float* cost_lr, float* disp, float* stats, int B, int Dl, int Hl, int Wl, int maxdisp, int variant, void* stream) {
+    return disp_head_fwd(cost_lr, disp, stats, B, Dl, Hl, Wl, maxdisp, variant, ST(stream));
+}
+RAG_API int rag_disp_head_bwd_v(const float* cost_lr, const float* gdisp, const float* disp, const float* stats, float* gcost_lr,
+                        int B, int Dl, int Hl, int Wl, int maxdisp, int variant, void* stream) {
+    return disp_head_bwd(cost_lr, gdisp, disp, stats, gcost_lr, B, Dl, Hl, Wl, maxdisp, variant, ST(stream));
+}
+
+RAG_API int rag_loss_metrics_scratch(int H, int W) { return loss_metrics_scratch(H, W); }
+RAG_API int rag_loss_metrics_sums(const float* est, const float* gt, double* sums, double* scratch, int B, int H, int W, float maxdisp, void* stream) {
+    return loss_metrics_sums(est, gt, sums, scratch, B, H, W, maxdisp, ST(stream));
+}
+RAG_API int rag_smooth_l1_bwd(const float* est, const float* gt, const double* sums, const float* gloss, float* gest,
+                      int B, int H, int W, float maxdisp, void* stream) {
+    return smooth_l1_bwd(est, gt, sums, gloss, gest, B, H, W, maxdisp, ST(stream));
+}
+RAG_API int rag_normalize_pad(const uint8_t* img, float* out, int B, int H, int W, int top_pad, int right_pad, void* stream) {
+    return normalize_pad(img, out, B, H, W, top_pad, right_pad, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,284 @@
+// Concatenation cost volume, forward and backward, for sm_100a.
+//
+// Reference semantics: src/models/rag_model.py:375-383 (and its two verbatim copies):
+//   cost[b,   c, d,h,w] = x[b,c,h,w]   (w >= d) else 0
+//   cost[b, C+c, d,h,w] = y[b,c,h,w-d] (w >= d) else 0
+// The reference does this with one zero-fill + 2*Df strided slice copies (129 launches, the
+// volume written twice) and its autograd replays 2*Df CopySlices nodes that each clone the full
+// gradient volume.  Here: one launch per direction, every byte of the volume touched once.
+//
+// Forward  (HBM store stream): a CTA stages R feature rows of one (b,c) -- the left row once and
+//   the right row as V copies pre-shifted by 0..V-1 elements -- in shared memory, so that for every
+//   disparity d = V*q + s the shifted right row is an ALIGNED 16-byte shared-memory read of copy s
+//   at vector offset -q, and every global store is a full, aligned, coalesced 128-bit store.
+//   Each input row is read from HBM/L2 once per disparity sweep (d-chunk), not once per disparity.
+// Backward (HBM load stream): one thread owns V adjacent w of one (b,c,h) row and walks d from
+//   Df-1 down to 0 accumulating in fp32 -- exactly the order in which autograd accumulates the
+//   CopySlices gradients -- so the result is bit-identical to the reference; loads are 128-bit,
+//   coalesced, and issued U disparities ahead of the dependent adds.  No atomics, no reduction tree.
+#include "common.cuh"
+
+namespace rag {
+
+template <int V> struct Vec;
+template <> struct Vec<4> { using T = float4; };
+template <> struct Vec<2> { using T = float2; };
+template <> struct Vec<1> { using T = float; };
+
+__device__ __forceinline__ float get(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+__device__ __forceinline__ float get(const float2& v, int i) { return i == 0 ? v.x : v.y; }
+__device__ __forceinline__ float get(const float& v, int) { return v; }
+__device__ __forceinline__ void set(float4& v, int i, float a) { if (i == 0) v.x = a; else if (i == 1) v.y = a; else if (i == 2) v.z = a; else v.w = a; }
+__device__ __forceinline__ void set(float2& v, int i, float a) { if (i == 0) v.x = a; else v.y = a; }
+__device__ __forceinline__ void set(float& v, int, float a) { v = a; }
+template <typename T> __device__ __forceinline__ T zero_vec();
+template <> __device__ __forceinline__ float4 zero_vec<float4>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <> __device__ __forceinline__ float2 zero_vec<float2>() { return make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ float zero_vec<float>() { return 0.f; }
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+// grid: x = h-tile * n_dchunks + d-chunk, y = c, z = b.   smem: [V+1][R*Wf] floats + u16 table[R*Wv]
+template <int V, int NT>
+__global__ void __launch_bounds__(NT)
+cv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ cost,
+              int C, int Df, int Hf, int Wf, int R, int dchunk, int n_dchunks) {
+    using VT = typename Vec<V>::T;
+    extern __shared__ __align__(16) float smem[];
+    const int Wv = Wf / V;
+    const int tile = blockIdx.x / n_dchunks;
+    const int dci = blockIdx.x - tile * n_dchunks;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const int h0 = tile * R;
+    const int rows = min(R, Hf - h0);
+    const int d0 = dci * dchunk;                 // multiple of V by construction
+    const int nd = min(dchunk, Df - d0);
+    const int P = rows * Wv;                     // vectors in the tile
+    const int tile_elems = R * Wf;
+
+    float* sx = smem;                            // left rows
+    float* sy = smem + tile_elems;               // V shifted copies of the right rows
+    unsigned short* wvtab = reinterpret_cast<unsigned short*>(smem + (V + 1) * tile_elems);
+
+    // ---- stage the rows (each input element read once per CTA) ----
+    const size_t in_off = ((size_t)(b * C + c) * Hf + h0) * Wf;
+    const VT* xg = reinterpret_cast<const VT*>(x + in_off);
+    const VT* yg = reinterpret_cast<const VT*>(y + in_off);
+    for (int p = threadIdx.x; p < P; p += NT) {
+        const int r = p / Wv;
+        const int wv = p - r * Wv;
+        wvtab[p] = (unsigned short)wv;
+        reinterpret_cast<VT*>(sx)[p] = __ldg(xg + p);
+        const VT yv = __ldg(yg + p);
+        const int w0 = wv * V;
+#pragma unroll
+        for (int s = 0; s < V; ++s) {
+            float* row = sy + s * tile_elems + r * Wf;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int i = w0 + k + s;        // copy_s[i] = y[i - s]
+                if (i < Wf) row[i] = get(yv, k);
+            }
+            if (wv == 0) {
+#pragma unroll
+                for (int k = 0; k < V; ++k)
+                    if (k < s) row[k] = 0.f;     // copy_s[i < s] = 0
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- stream the volume: items = (d_local, p), consecutive threads -> consecutive vectors ----
+    const size_t plane = (size_t)Hf * Wf;
+    float* left = cost + (((size_t)(b * 2 * C + c) * Df + d0) * Hf + h0) * Wf;
+    float* right = left + (size_t)C * Df * plane;
+    const VT* sxv = reinterpret_cast<const VT*>(sx);
+
+    int p = threadIdx.x, dl = 0;
+    while (p >= P) { p -= P; ++dl; }
+    while (dl < nd) {
+        const int d = d0 + dl;
+        const int wv = wvtab[p];
+        const int w0 = wv * V;
+        const size_t off = (size_t)dl * plane + (size_t)p * V;
+        // left half: x masked by w >= d
+        VT xv = sxv[p];
+        if (w0 < d) {
+#pragma unroll
+            for (int k = 0; k < V; ++k)
+                if (w0 + k < d) set(xv, k, 0.f);
+        }
+        st_stream(reinterpret_cast<VT*>(left + off), xv);
+        // right half: y shifted by d = V*q + s  ->  copy s, vector (wv - q)
+        const int q = d / V, s = d - q * V;
+        VT yv = zero_vec<VT>();
+        if (wv >= q) yv = reinterpret_cast<const VT*>(sy + s * tile_elems)[p - q];
+        st_stream(reinterpret_cast<VT*>(right + off), yv);
+        p += NT;
+        while (p >= P) { p -= P; ++dl; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+// Vector path (Wf % 4 == 0).  grid: x over Hf*Wv vectors, y = c, z = b.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+cv_bwd_v4_kernel(const float* __restrict__ g, float* __restrict__ gx, float* __restrict__ gy,
+                 int C, int Df, int Hf, int Wf) {
+    const int Wv = Wf >> 2;
+    const int PV = Hf * Wv;
+    const int p = blockIdx.x * NT + threadIdx.x;
+    if (p >= PV) return;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const int wv = p % Wv;
+    const int w0 = wv << 2;
+    const size_t planeV = (size_t)PV;
+    const float4* gl = reinterpret_cast<const float4*>(g) + (size_t)(b * 2 * C + c) * Df * planeV + p;
+    const float4* gr = gl + (size_t)C * Df * planeV;
+
+    float4 ax = make_float4(0.f, 0.f, 0.f, 0.f), ay = ax;
+    constexpr int U = 4;
+    // d runs from the first multiple-of-4 boundary above Df-1 down to 0 so that s = d & 3 = 3-u is
+    // a compile-time constant inside the unrolled body
+    for (int dq = ((Df + 3) & ~3) - 1; dq >= 0; dq -= U) {
+        float4 tl[U], ta[U], tb[U];
+        const int q = dq >> 2;                      // same q for the 4 disparities of this block
+        const bool inA = (wv + q) < Wv;
+        const bool inB = (wv + q + 1) < Wv;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int d = dq - u;
+            const bool dv = d < Df;
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            tl[u] = (dv && (w0 + 3 >= d)) ? ld_stream(gl + (size_t)d * planeV) : z;
+            ta[u] = (dv && inA) ? __ldg(gr + (size_t)d * planeV + q) : z;
+            tb[u] = (dv && inB && (3 - u) > 0) ? __ldg(gr + (size_t)d * planeV + q + 1) : z;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int d = dq - u;
+            if (d < Df) {
+                // gx[w] += g[d][w] for w >= d
+                if (w0 + 0 >= d) ax.x = ax.x + tl[u].x;
+                if (w0 + 1 >= d) ax.y = ax.y + tl[u].y;
+                if (w0 + 2 >= d) ax.z = ax.z + tl[u].z;
+                if (w0 + 3 >= d) ax.w = ax.w + tl[u].w;
+                // gy[w'] += g[d][w'+d], elements s..s+3 of the 8-float window (A,B), s = 3-u
+                if (inA) {
+                    const int s = 3 - u;
+                    const float e0 = s == 0 ? ta[u].x : s == 1 ? ta[u].y : s == 2 ? ta[u].z : ta[u].w;
+                    const float e1 = s == 0 ? ta[u].y : s == 1 ? ta[u].z : s == 2 ? ta[u].w : tb[u].x;
+                    const float e2 = s == 0 ? ta[u].z : s == 1 ? ta[u].w : s == 2 ? tb[u].x : tb[u].y;
+                    const float e3 = s == 0 ? ta[u].w : s == 1 ? tb[u].x : s == 2 ? tb[u].y : tb[u].z;
+                    // validity: w'+d < Wf  <=>  element index (s+k) stays inside A, or B exists
+                    ay.x = ay.x + e0;                                   // s+0 <= 3: always inside A
+                    if (s + 1 <= 3 || inB) ay.y = ay.y + e1;
+                    if (s + 2 <= 3 || inB) ay.z = ay.z + e2;
+                    if (s + 3 <= 3 || inB) ay.w = ay.w + e3;
+                }
+            }
+        }
+    }
+    const size_t o = (size_t)(b * C + c) * planeV + p;
+    reinterpret_cast<float4*>(gx)[o] = ax;
+    reinterpret_cast<float4*>(gy)[o] = ay;
+}
+
+// Scalar path (any Wf).  grid: x over Hf*Wf elements, y = c, z = b.
+template <int NT>
+__global__ void __launch_bounds__(NT)
+cv_bwd_scalar_kernel(const float* __restrict__ g, float* __restrict__ gx, float* __restrict__ gy,
+                     int C, int Df, int Hf, int Wf) {
+    const int PE = Hf * Wf;
+    const int p = blockIdx.x * NT + threadIdx.x;
+    if (p >= PE) return;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const int w = p % Wf;
+    const float* gl = g + (size_t)(b * 2 * C + c) * Df * PE + p;
+    const float* gr = gl + (size_t)C * Df * PE;
+    float ax = 0.f, ay = 0.f;
+    for (int d = Df - 1; d >= 0; --d) {
+        if (w >= d) ax = ax + ld_stream(gl + (size_t)d * PE);
+        if (w + d < Wf) ay = ay + ld_stream(gr + (size_t)d * PE + d);
+    }
+    const size_t o = (size_t)(b * C + c) * PE + p;
+    gx[o] = ax;
+    gy[o] = ay;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static int check_cv_args(const void* a, const void* b_, const void* c, int B, int C, int Df, int Hf, int Wf) {
+    if (!a || !b_ || !c) return fail(RAG_E_NULL, "cost_volume: null pointer");
+    if (B <= 0 || C <= 0 || Df <= 0 || Hf <= 0 || Wf <= 0)
+        return fail(RAG_E_SHAPE, "cost_volume: non-positive dimension B=%d C=%d Df=%d Hf=%d Wf=%d", B, C, Df, Hf, Wf);
+    if (B > 65535 || C > 65535) return fail(RAG_E_SHAPE, "cost_volume: B and C must be <= 65535");
+    if ((size_t)Df * Hf * Wf >= ((size_t)1 << 31) || Wf > 65535)
+        return fail(RAG_E_SHAPE, "cost_volume: Df*Hf*Wf must be < 2^31 and Wf <= 65535");
+    if (!aligned(a, 4) || !aligned(b_, 4) || !aligned(c, 4)) return fail(RAG_E_ALIGN, "cost_volume: pointers must be 4-byte aligned");
+    return RAG_OK;
+}
+
+template <int V>
+static int launch_cv_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
+                         int variant, cudaStream_t st) {
+    constexpr int NT = 256;
+    // variant: 0 -> 16-disparity chunks, 36 KB tiles; 1 -> 32-disparity chunks; 2 -> whole sweep per CTA;
+    //          3 -> 16-disparity chunks, 72 KB tiles
+    int dchunk = variant == 1 ? 32 : variant == 2 ? Df : 16;
+    dchunk = ((dchunk + V - 1) / V) * V;
+    const int n_dchunks = (Df + dchunk - 1) / dchunk;
+    const size_t budget = variant == 3 ? 72 * 1024 : 36 * 1024;
+    int R = (int)(budget / ((size_t)(V + 1) * 4 * Wf + (size_t)2 * (Wf / V)));
+    R = R < 1 ? 1 : (R > Hf ? Hf : R);
+    // prefer an R that divides Hf (no ragged last tile) when one is close
+    for (int r = R; r >= (R * 3) / 4 && r >= 1; --r)
+        if (Hf % r == 0) { R = r; break; }
+    const size_t smem = (size_t)(V + 1) * R * Wf * 4 + (size_t)R * (Wf / V) * 2;
+    if (smem > 200 * 1024) return fail(RAG_E_SHAPE, "cost_volume_fwd: Wf=%d too wide for one shared-memory row tile", Wf);
+    auto kern = cv_fwd_kernel<V, NT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail((int)e, "cost_volume_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    const int n_tiles = (Hf + R - 1) / R;
+    dim3 grid(n_tiles * n_dchunks, C, B);
+    kern<<<grid, NT, smem, st>>>(x, y, cost, C, Df, Hf, Wf, R, dchunk, n_dchunks);
+    return check_launch("cost_volume_fwd");
+}
+
+int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
+                    int variant, cudaStream_t st) {
+    if (int e = check_cv_args(x, y, cost, B, C, Df, Hf, Wf)) return e;
+    if (variant < 0 || variant > 3) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
+    const bool a16 = aligned(x, 16) && aligned(y, 16) && aligned(cost, 16);
+    const bool a8 = aligned(x, 8) && aligned(y, 8) && aligned(cost, 8);
+    if (Wf % 4 == 0 && a16) return launch_cv_fwd<4>(x, y, cost, B, C, Df, Hf, Wf, variant, st);
+    if (Wf % 2 == 0 && a8) return launch_cv_fwd<2>(x, y, cost, B, C, Df, Hf, Wf, variant, st);
+    return launch_cv_fwd<1>(x, y, cost, B, C, Df, Hf, Wf, variant, st);
+}
+
+int cost_volume_bwd(const float* g, float* gx, float* gy, int B, int C, int Df, int Hf, int Wf,
+                    int variant, cudaStream_t st) {
+    if (int e = check_cv_args(g, gx, gy, B, C, Df, Hf, Wf)) return e;
+    if (variant < 0 || variant > 1) return fail(RAG_E_VARIANT, "cost_volume_bwd: unknown variant %d", variant);
+    const bool a16 = aligned(g, 16) && aligned(gx, 16) && aligned(gy, 16);
+    if (variant == 0 && Wf % 4 == 0 && a16) {
+        constexpr int NT = 128;
+        const int PV = Hf * (Wf / 4);
+        dim3 grid((PV + NT - 1) / NT, C, B);
+        cv_bwd_v4_kernel<NT><<<grid, NT, 0, st>>>(g, gx, gy, C, Df, Hf, Wf);
+    } else {
+        constexpr int NT = 256;
+        const int PE = Hf * Wf;
+        dim3 grid((PE + NT - 1) / NT, C, B);
+        cv_bwd_scalar_kernel<NT><<<grid, NT, 0, st>>>(g, gx, gy, C, Df, Hf, Wf);
+    }
+    return check_launch("cost_volume_bwd");
+}
+
+}  // namespace rag

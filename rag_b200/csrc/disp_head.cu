@@ -1,0 +1,428 @@
+// Disparity head: trilinear x3 upsample -> softmin over D -> soft-argmin, fused, fwd + bwd (sm_100a).
+//
+// Reference semantics: src/models/rag_model.py:32-44 (Disp.forward) + :18-29 (DisparityRegression):
+//   v = F.interpolate(cost_lr, [maxdisp, 3Hl, 3Wl], 'trilinear', align_corners=False)
+//   disp = sum_k k * softmax_k(-v)
+// The reference materialises the [B,maxdisp,H,W] volume about nine times (~1.1 GB/pair at 288x576);
+// here the full-resolution volume never exists: the forward reads cost_lr once and writes disp (+2
+// stats planes for the backward), the backward re-derives p_k from cost_lr and the stats.
+//
+// The upsample arithmetic replicates PyTorch's fp32 source-index / lambda computation
+// (ATen/native/cuda/UpSample.cuh:115-130; nesting W -> H -> D as in UpSampleTrilinear3d.cu), because
+// "ideal" 1/3, 2/3 weights are off by up to 1.3e-6 and move ~5% of pixels by more than 1e-4 px.
+//
+// Softmax numerics: exponents are taken in the log2 domain, z_k = -log2(e) * v_k, relative to a
+// per-pixel reference exponent m that is only moved when the running maximum exceeds it by more
+// than kTau (lazy rescaling, exact); sums are kept in short fp32 group accumulators that are
+// folded into fp64 totals every 8 low-res bins, and the regression is centred (disp = kc +
+// sum e_k (k-kc) / sum e_k), which keeps the kernel's own error ~1e-5 px -- an order of magnitude
+// below the reference's fp32 noise floor.
+//
+// Bound: NOT HBM. Per output pixel the head needs maxdisp exp2 on the SFU (16 lanes/clk/SM): 192
+// MUFU.EX2 per pixel = 8 SMSP-clk per pixel-bin, which is the floor of this kernel (~7 us per
+// 288x576 pair); the x3 kernel is organised so that everything else (blend, sums) fits under it.
+#include "common.cuh"
+
+namespace rag {
+
+constexpr float kNegLog2e = -1.4426950408889634f;
+constexpr float kTau = 24.0f;  // lazy-rescale threshold (log2 units): e_k <= 2^24 between rescales
+
+// ---------------------------------------------------------------------------------------------
+// debug: the upsample alone
+// ---------------------------------------------------------------------------------------------
+template <bool FMA>
+__global__ void upsample_kernel(const float* __restrict__ cost, float* __restrict__ out,
+                                int Dl, int Hl, int Wl, int D, float sd, float sh, float sw) {
+    const int H = 3 * Hl, W = 3 * Wl;
+    const size_t n = (size_t)D * H * W;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int b = blockIdx.y;
+    const int w = idx % W, h = (idx / W) % H, k = idx / ((size_t)W * H);
+    int t0, t1, h0, h1, w0, w1;
+    float tl0, tl1, hl0, hl1, wl0, wl1;
+    src_index<FMA>(sd, k, Dl, t0, t1, tl0, tl1);
+    src_index<FMA>(sh, h, Hl, h0, h1, hl0, hl1);
+    src_index<FMA>(sw, w, Wl, w0, w1, wl0, wl1);
+    const float* s = cost + (size_t)b * Dl * Hl * Wl;
+    auto at = [&](int t, int y, int x) { return s[((size_t)t * Hl + y) * Wl + x]; };
+    const float v = tl0 * (hl0 * (wl0 * at(t0, h0, w0) + wl1 * at(t0, h0, w1)) + hl1 * (wl0 * at(t0, h1, w0) + wl1 * at(t0, h1, w1))) +
+                    tl1 * (hl0 * (wl0 * at(t1, h0, w0) + wl1 * at(t1, h0, w1)) + hl1 * (wl0 * at(t1, h1, w0) + wl1 * at(t1, h1, w1)));
+    out[(size_t)b * n + idx] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic forward: any (Dl, maxdisp); one thread per output pixel.  Slow path / cross-check.
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT)
+head_fwd_generic_kernel(const float* __restrict__ cost, float* __restrict__ disp, float* __restrict__ stats,
+                        int Dl, int Hl, int Wl, int D, float sd, float sh, float sw) {
+    const int H = 3 * Hl, W = 3 * Wl;
+    const int idx = blockIdx.x * NT + threadIdx.x;
+    if (idx >= H * W) return;
+    const int b = blockIdx.y;
+    const int h = idx / W, w = idx - h * W;
+    int h0, h1, w0, w1;
+    float hl0, hl1, wl0, wl1;
+    src_index<true>(sh, h, Hl, h0, h1, hl0, hl1);
+    src_index<true>(sw, w, Wl, w0, w1, wl0, wl1);
+    const float* base = cost + (size_t)b * Dl * Hl * Wl;
+    const int o00 = h0 * Wl + w0, o01 = h0 * Wl + w1, o10 = h1 * Wl + w0, o11 = h1 * Wl + w1;
+    auto blend = [&](int j) {
+        const float* s = base + (size_t)j * Hl * Wl;
+        return hl0 * (wl0 * __ldg(s + o00) + wl1 * __ldg(s + o01)) + hl1 * (wl0 * __ldg(s + o10) + wl1 * __ldg(s + o11));
+    };
+    int cur = -1;
+    float a0 = 0.f, a1 = 0.f;
+    float m = -INFINITY;
+    double den = 0.0, num = 0.0;
+    for (int k = 0; k < D; ++k) {
+        int t0, t1;
+        float l0, l1;
+        src_index<true>(sd, k, Dl, t0, t1, l0, l1);
+        if (t0 != cur) {
+            a0 = blend(t0);
+            a1 = (t1 == t0) ? a0 : blend(t1);
+            cur = t0;
+        }
+        const float v = l0 * a0 + l1 * a1;
+        const float z = v * kNegLog2e;
+        if (z > m) {
+            const double f = (double)exp2f(m - z);  // m = -inf on the first bin -> 0
+            den *= f;
+            num *= f;
+            m = z;
+        }
+        const float e = exp2f(z - m);
+        den += (double)e;
+        num += (double)e * (double)k;
+    }
+    const size_t o = (size_t)b * H * W + idx;
+    disp[o] = (float)(num / den);
+    if (stats) {
+        stats[(size_t)b * 2 * H * W + idx] = m;
+        stats[(size_t)b * 2 * H * W + (size_t)H * W + idx] = (float)(1.0 / den);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// x3 forward (maxdisp == 3*Dl): one thread per 3x3 output-pixel block.
+// ---------------------------------------------------------------------------------------------
+// Block (r,c), r in [-1,Hl-1], c in [-1,Wl-1], owns output rows 3r+1..3r+3 and cols 3c+1..3c+3.
+// All nine pixels interpolate between low-res rows {max(r,0), min(max(r,0)+1,Hl-1)} and the
+// matching two columns, so per low-res bin j a thread loads 4 values and forms the 9 bilinear
+// blends with 30 FP ops (3.3 per pixel instead of 10), then walks the 3 full-res bins k=3j+1..3j+3
+// that interpolate between bins j and j+1 (k=0 rides along with j=0).
+// grid: x = ceil((Wl+1)/32), y = ceil((Hl+1)/WARPS), z = B.  A warp = 32 consecutive c of one r.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+head_fwd_x3_kernel(const float* __restrict__ cost, float* __restrict__ disp, float* __restrict__ stats,
+                   int Dl, int Hl, int Wl, float scale) {
+    extern __shared__ float2 dlam[];  // [D] (lambda0, lambda1) of full-res bin k
+    const int D = 3 * Dl, H = 3 * Hl, W = 3 * Wl;
+    for (int k = threadIdx.x; k < D; k += WARPS * 32) {
+        int t0, t1;
+        float l0, l1;
+        src_index<true>(scale, k, Dl, t0, t1, l0, l1);
+        dlam[k] = make_float2(l0, l1);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane - 1;
+    const int r = blockIdx.y * WARPS + warp - 1;
+    const int b = blockIdx.z;
+    if (c > Wl - 1 || r > Hl - 1) return;
+
+    // per-axis tables for the block's 3 rows / 3 cols
+    float hs0[3], hs1[3], wl0[3], wl1[3];
+    bool hv[3], wv[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int i0, i1;
+        float l0, l1;
+        const int h = 3 * r + 1 + i;
+        hv[i] = h >= 0 && h < H;
+        src_index<true>(scale, max(h, 0), Hl, i0, i1, l0, l1);
+        hs0[i] = l0 * kNegLog2e;  // fold -log2(e): blends come out directly as exponents z
+        hs1[i] = l1 * kNegLog2e;
+        const int w = 3 * c + 1 + i;
+        wv[i] = w >= 0 && w < W;
+        src_index<true>(scale, max(w, 0), Wl, i0, i1, l0, l1);
+        wl0[i] = l0;
+        wl1[i] = l1;
+    }
+    const int rl0 = max(r, 0), rl1 = min(rl0 + 1, Hl - 1);
+    const int cl0 = max(c, 0), cl1 = min(cl0 + 1, Wl - 1);
+    const size_t plane = (size_t)Hl * Wl;
+    const float* base = cost + (size_t)b * Dl * plane;
+    const int o00 = rl0 * Wl + cl0, o01 = rl0 * Wl + cl1, o10 = rl1 * Wl + cl0, o11 = rl1 * Wl + cl1;
+
+    float cur[9], nxt[9], m[9], dg[9], ng[9];
+    double dend[9], numd[9];
+    float ld[4];
+
+    auto load4 = [&](int j) {
+        const float* s = base + (size_t)j * plane;
+        ld[0] = __ldg(s + o00); ld[1] = __ldg(s + o01); ld[2] = __ldg(s + o10); ld[3] = __ldg(s + o11);
+    };
+    auto blend9 = [&](float* za) {
+        float x0[3], x1[3];
+#pragma unroll
+        for (int pw = 0; pw < 3; ++pw) {
+            x0[pw] = __fmaf_rn(wl0[pw], ld[0], wl1[pw] * ld[1]);
+            x1[pw] = __fmaf_rn(wl0[pw], ld[2], wl1[pw] * ld[3]);
+        }
+#pragma unroll
+        for (int ph = 0; ph < 3; ++ph)
+#pragma unroll
+            for (int pw = 0; pw < 3; ++pw) za[ph * 3 + pw] = __fmaf_rn(hs0[ph], x0[pw], hs1[ph] * x1[pw]);
+    };
+
+    load4(0);
+    blend9(cur);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { m[i] = cur[i]; dg[i] = 0.f; ng[i] = 0.f; dend[i] = 0.0; numd[i] = 0.0; }
+    load4(min(1, Dl - 1));
+    const float kc = 0.5f * (float)D;
+
+    for (int j = 0; j < Dl; ++j) {
+        blend9(nxt);                       // z-blend of low-res bin min(j+1, Dl-1) (loaded last iteration)
+        load4(min(j + 2, Dl - 1));         // prefetch for the next iteration
+        const int k1 = 3 * j + 1;
+        const float2 L1 = dlam[k1];
+        const float2 L2 = dlam[min(k1 + 1, D - 1)];
+        const float2 L3 = dlam[min(k1 + 2, D - 1)];
+        const bool has3 = (k1 + 2) < D;    // false only for j = Dl-1
+        const float kf = (float)k1 - kc;   // centred bin index of k1
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            // lazy rescale: only when the new low-res exponent exceeds the reference by > kTau
+            if (nxt[i] > m[i] + kTau) {
+                const float f = ex2_approx(m[i] - nxt[i]);
+                dg[i] *= f; ng[i] *= f;
+                dend[i] *= (double)f; numd[i] *= (double)f;
+                m[i] = nxt[i];
+            }
+            const float a = cur[i] - m[i];
+            const float dlt = nxt[i] - cur[i];
+            if (j == 0) {                  // full-res bin 0 (lambda1 == 0): exponent of low-res bin 0
+                const float e0 = ex2_approx(a);
+                dg[i] += e0;
+                ng[i] = __fmaf_rn(e0, -kc, ng[i]);
+            }
+            const float e1 = ex2_approx(__fmaf_rn(L1.y, dlt, a));
+            const float e2 = ex2_approx(__fmaf_rn(L2.y, dlt, a));
+            float e3 = ex2_approx(__fmaf_rn(L3.y, dlt, a));
+            e3 = has3 ? e3 : 0.f;
+            dg[i] += e1; ng[i] = __fmaf_rn(e1, kf, ng[i]);
+            dg[i] += e2; ng[i] = __fmaf_rn(e2, kf + 1.f, ng[i]);
+            dg[i] += e3; ng[i] = __fmaf_rn(e3, kf + 2.f, ng[i]);
+            cur[i] = nxt[i];
+        }
+        if ((j & 7) == 7 || j == Dl - 1) {  // fold the short fp32 group sums into the fp64 totals
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                dend[i] += (double)dg[i]; numd[i] += (double)ng[i];
+                dg[i] = 0.f; ng[i] = 0.f;
+            }
+        }
+    }
+    const size_t img = (size_t)H * W;
+#pragma unroll
+    for (int ph = 0; ph < 3; ++ph) {
+        if (!hv[ph]) continue;
+        const int h = 3 * r + 1 + ph;
+#pragma unroll
+        for (int pw = 0; pw < 3; ++pw) {
+            if (!wv[pw]) continue;
+            const int w = 3 * c + 1 + pw;
+            const int i = ph * 3 + pw;
+            const size_t o = (size_t)h * W + w;
+            disp[(size_t)b * img + o] = kc + (float)(numd[i] / dend[i]);
+            if (stats) {
+                stats[(size_t)b * 2 * img + o] = m[i];
+                stats[(size_t)b * 2 * img + img + o] = (float)(1.0 / dend[i]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic backward: deterministic gather, one thread per low-res voxel.  Slow path / cross-check.
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT)
+head_bwd_generic_kernel(const float* __restrict__ cost, const float* __restrict__ gdisp,
+                        const float* __restrict__ disp, const float* __restrict__ stats,
+                        float* __restrict__ gcost, int Dl, int Hl, int Wl, int D, float sd, float sh, float sw) {
+    const int H = 3 * Hl, W = 3 * Wl;
+    const size_t nvox = (size_t)Dl * Hl * Wl;
+    const size_t idx = (size_t)blockIdx.x * NT + threadIdx.x;
+    if (idx >= nvox) return;
+    const int b = blockIdx.y;
+    const int c = idx % Wl, r = (idx / Wl) % Hl, j = idx / ((size_t)Wl * Hl);
+    const float* base = cost + (size_t)b * nvox;
+    const size_t img = (size_t)H * W;
+    const float* gd = gdisp + (size_t)b * img;
+    const float* dp = disp + (size_t)b * img;
+    const float* sm = stats + (size_t)b * 2 * img;
+    const float* sinv = sm + img;
+
+    // candidate full-res ranges (conservative), each candidate is tested against the tables
+    const float inv_sd = 1.f / sd;
+    const int klo = max(0, (int)floorf(((float)j - 0.5f) * inv_sd - 0.5f) - 2);
+    const int khi = min(D - 1, (int)ceilf(((float)j + 1.5f) * inv_sd - 0.5f) + 2);
+    const int hlo = max(0, 3 * r - 3), hhi = min(H - 1, 3 * r + 4);
+    const int wlo = max(0, 3 * c - 3), whi = min(W - 1, 3 * c + 4);
+
+    double acc = 0.0;
+    for (int h = hlo; h <= hhi; ++h) {
+        int h0, h1;
+        float hl0, hl1;
+        src_index<true>(sh, h, Hl, h0, h1, hl0, hl1);
+        const float wh = (h0 == r ? hl0 : 0.f) + (h1 == r ? hl1 : 0.f);
+        if (h0 != r && h1 != r) continue;
+        for (int w = wlo; w <= whi; ++w) {
+            int w0, w1;
+            float wl0, wl1;
+            src_index<true>(sw, w, Wl, w0, w1, wl0, wl1);
+            if (w0 != c && w1 != c) continue;
+            const float ww = (w0 == c ? wl0 : 0.f) + (w1 == c ? wl1 : 0.f);
+            const size_t o = (size_t)h * W + w;
+            const float g = __ldg(gd + o);
+            if (g == 0.f) continue;
+            const float dsp = __ldg(dp + o), m = __ldg(sm + o), inv = __ldg(sinv + o);
+            const int o00 = h0 * Wl + w0, o01 = h0 * Wl + w1, o10 = h1 * Wl + w0, o11 = h1 * Wl + w1;
+            auto blend = [&](int t) {
+                const float* s = base + (size_t)t * Hl * Wl;
+                return hl0 * (wl0 * __ldg(s + o00) + wl1 * __ldg(s + o01)) + hl1 * (wl0 * __ldg(s + o10) + wl1 * __ldg(s + o11));
+            };
+            double pix = 0.0;
+            for (int k = klo; k <= khi; ++k) {
+                int t0, t1;
+                float l0, l1;
+                src_index<true>(sd, k, Dl, t0, t1, l0, l1);
+                if (t0 != j && t1 != j) continue;
+                const float wd = (t0 == j ? l0 : 0.f) + (t1 == j ? l1 : 0.f);
+                const float v = l0 * blend(t0) + l1 * blend(t1);
+                const float p = exp2f(v * kNegLog2e - m) * inv;
+                pix += (double)wd * (double)(-p * ((float)k - dsp));
+            }
+            acc += (double)(wh * ww) * (double)g * pix;
+        }
+    }
+    gcost[(size_t)b * nvox + idx] = (float)acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DisparityRegression alone (rag_model.py:18-29) and its gradient
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT)
+regression_fwd_kernel(const float* __restrict__ p, float* __restrict__ out, int D, int HW) {
+    const int idx = blockIdx.x * NT + threadIdx.x;
+    if (idx >= HW) return;
+    const int b = blockIdx.y;
+    const float* s = p + (size_t)b * D * HW + idx;
+    double acc = 0.0;
+    int k = 0;
+    for (; k + 4 <= D; k += 4) {
+        const float v0 = ld_stream(s + (size_t)(k + 0) * HW), v1 = ld_stream(s + (size_t)(k + 1) * HW);
+        const float v2 = ld_stream(s + (size_t)(k + 2) * HW), v3 = ld_stream(s + (size_t)(k + 3) * HW);
+        acc += (double)v0 * k + (double)v1 * (k + 1) + (double)v2 * (k + 2) + (double)v3 * (k + 3);
+    }
+    for (; k < D; ++k) acc += (double)ld_stream(s + (size_t)k * HW) * k;
+    out[(size_t)b * HW + idx] = (float)acc;
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT)
+regression_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gp, int D, int HW) {
+    const int idx = blockIdx.x * NT + threadIdx.x;
+    if (idx >= HW) return;
+    const int b = blockIdx.y;
+    const float g = __ldg(gout + (size_t)b * HW + idx);
+    float* d = gp + (size_t)b * D * HW + idx;
+    for (int k = 0; k < D; ++k) st_stream(d + (size_t)k * HW, g * (float)k);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+static int check_head_args(int B, int Dl, int Hl, int Wl, int D) {
+    if (B <= 0 || Dl <= 0 || Hl <= 0 || Wl <= 0 || D <= 0)
+        return fail(RAG_E_SHAPE, "disp_head: non-positive dimension B=%d Dl=%d Hl=%d Wl=%d maxdisp=%d", B, Dl, Hl, Wl, D);
+    if (B > 65535) return fail(RAG_E_SHAPE, "disp_head: B must be <= 65535");
+    if ((size_t)9 * Hl * Wl >= ((size_t)1 << 31) || (size_t)Dl * Hl * Wl >= ((size_t)1 << 31) || D > 4096)
+        return fail(RAG_E_SHAPE, "disp_head: image or volume too large (9*Hl*Wl, Dl*Hl*Wl < 2^31, maxdisp <= 4096)");
+    return RAG_OK;
+}
+
+int upsample_trilinear(const float* cost, float* out, int B, int Dl, int Hl, int Wl, int D, int fma, cudaStream_t st) {
+    if (!cost || !out) return fail(RAG_E_NULL, "upsample_trilinear: null pointer");
+    if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
+    const size_t n = (size_t)D * 9 * Hl * Wl;
+    const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
+    dim3 grid((unsigned)((n + 255) / 256), B);
+    if (fma) upsample_kernel<true><<<grid, 256, 0, st>>>(cost, out, Dl, Hl, Wl, D, sd, sh, sw);
+    else upsample_kernel<false><<<grid, 256, 0, st>>>(cost, out, Dl, Hl, Wl, D, sd, sh, sw);
+    return check_launch("upsample_trilinear");
+}
+
+int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, int Hl, int Wl, int D,
+                  int variant, cudaStream_t st) {
+    if (!cost || !disp) return fail(RAG_E_NULL, "disp_head_fwd: null pointer");
+    if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
+    if (variant < -1 || variant > 1) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
+    const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
+    const bool x3 = (D == 3 * Dl);
+    if (variant == 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_fwd: variant 1 needs maxdisp == 3*Dl");
+    if (variant == -1) variant = x3 ? 1 : 0;
+    if (variant == 1) {
+        constexpr int WARPS = 4;
+        dim3 grid((Wl + 1 + 31) / 32, (Hl + 1 + WARPS - 1) / WARPS, B);
+        head_fwd_x3_kernel<WARPS><<<grid, WARPS * 32, (size_t)D * sizeof(float2), st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+    } else {
+        constexpr int NT = 128;
+        dim3 grid((9 * Hl * Wl + NT - 1) / NT, B);
+        head_fwd_generic_kernel<NT><<<grid, NT, 0, st>>>(cost, disp, stats, Dl, Hl, Wl, D, sd, sh, sw);
+    }
+    return check_launch("disp_head_fwd");
+}
+
+int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, const float* stats, float* gcost,
+                  int B, int Dl, int Hl, int Wl, int D, int variant, cudaStream_t st) {
+    if (!cost || !gdisp || !disp || !stats || !gcost) return fail(RAG_E_NULL, "disp_head_bwd: null pointer");
+    if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
+    if (variant < -1 || variant > 0) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
+    const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
+    constexpr int NT = 128;
+    const size_t nvox = (size_t)Dl * Hl * Wl;
+    dim3 grid((unsigned)((nvox + NT - 1) / NT), B);
+    head_bwd_generic_kernel<NT><<<grid, NT, 0, st>>>(cost, gdisp, disp, stats, gcost, Dl, Hl, Wl, D, sd, sh, sw);
+    return check_launch("disp_head_bwd");
+}
+
+int disparity_regression_fwd(const float* p, float* out, int B, int D, int H, int W, cudaStream_t st) {
+    if (!p || !out) return fail(RAG_E_NULL, "disparity_regression_fwd: null pointer");
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || B > 65535 || (size_t)H * W >= ((size_t)1 << 31))
+        return fail(RAG_E_SHAPE, "disparity_regression_fwd: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+    constexpr int NT = 256;
+    dim3 grid((H * W + NT - 1) / NT, B);
+    regression_fwd_kernel<NT><<<grid, NT, 0, st>>>(p, out, D, H * W);
+    return check_launch("disparity_regression_fwd");
+}
+
+int disparity_regression_bwd(const float* gout, float* gp, int B, int D, int H, int W, cudaStream_t st) {
+    if (!gout || !gp) return fail(RAG_E_NULL, "disparity_regression_bwd: null pointer");
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || B > 65535 || (size_t)H * W >= ((size_t)1 << 31))
+        return fail(RAG_E_SHAPE, "disparity_regression_bwd: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+    constexpr int NT = 256;
+    dim3 grid((H * W + NT - 1) / NT, B);
+    regression_bwd_kernel<NT><<<grid, NT, 0, st>>>(gout, gp, D, H * W);
+    return check_launch("disparity_regression_bwd");
+}
+
+}  // namespace rag
