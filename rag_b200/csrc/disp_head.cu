@@ -26,7 +26,7 @@
 namespace rag {
 
 constexpr float kNegLog2e = -1.4426950408889634f;
-constexpr float kTau = 24.0f;  // lazy-rescale threshold (log2 units): e_k <= 2^24 between rescales
+
 
 // ---------------------------------------------------------------------------------------------
 // debug: the upsample alone
@@ -107,147 +107,13 @@ head_fwd_generic_kernel(const float* __restrict__ cost, float* __restrict__ disp
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// x3 forward (maxdisp == 3*Dl): one thread per 3x3 output-pixel block.
-// ---------------------------------------------------------------------------------------------
-// Block (r,c), r in [-1,Hl-1], c in [-1,Wl-1], owns output rows 3r+1..3r+3 and cols 3c+1..3c+3.
-// All nine pixels interpolate between low-res rows {max(r,0), min(max(r,0)+1,Hl-1)} and the
-// matching two columns, so per low-res bin j a thread loads 4 values and forms the 9 bilinear
-// blends with 30 FP ops (3.3 per pixel instead of 10), then walks the 3 full-res bins k=3j+1..3j+3
-// that interpolate between bins j and j+1 (k=0 rides along with j=0).
-// grid: x = ceil((Wl+1)/32), y = ceil((Hl+1)/WARPS), z = B.  A warp = 32 consecutive c of one r.
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-head_fwd_x3_kernel(const float* __restrict__ cost, float* __restrict__ disp, float* __restrict__ stats,
-                   int Dl, int Hl, int Wl, float scale) {
-    extern __shared__ float2 dlam[];  // [D] (lambda0, lambda1) of full-res bin k
-    const int D = 3 * Dl, H = 3 * Hl, W = 3 * Wl;
-    for (int k = threadIdx.x; k < D; k += WARPS * 32) {
-        int t0, t1;
-        float l0, l1;
-        src_index<true>(scale, k, Dl, t0, t1, l0, l1);
-        dlam[k] = make_float2(l0, l1);
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + lane - 1;
-    const int r = blockIdx.y * WARPS + warp - 1;
-    const int b = blockIdx.z;
-    if (c > Wl - 1 || r > Hl - 1) return;
-
-    // per-axis tables for the block's 3 rows / 3 cols
-    float hs0[3], hs1[3], wl0[3], wl1[3];
-    bool hv[3], wv[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        int i0, i1;
-        float l0, l1;
-        const int h = 3 * r + 1 + i;
-        hv[i] = h >= 0 && h < H;
-        src_index<true>(scale, max(h, 0), Hl, i0, i1, l0, l1);
-        hs0[i] = l0 * kNegLog2e;  // fold -log2(e): blends come out directly as exponents z
-        hs1[i] = l1 * kNegLog2e;
-        const int w = 3 * c + 1 + i;
-        wv[i] = w >= 0 && w < W;
-        src_index<true>(scale, max(w, 0), Wl, i0, i1, l0, l1);
-        wl0[i] = l0;
-        wl1[i] = l1;
-    }
-    const int rl0 = max(r, 0), rl1 = min(rl0 + 1, Hl - 1);
-    const int cl0 = max(c, 0), cl1 = min(cl0 + 1, Wl - 1);
-    const size_t plane = (size_t)Hl * Wl;
-    const float* base = cost + (size_t)b * Dl * plane;
-    const int o00 = rl0 * Wl + cl0, o01 = rl0 * Wl + cl1, o10 = rl1 * Wl + cl0, o11 = rl1 * Wl + cl1;
-
-    float cur[9], nxt[9], m[9], dg[9], ng[9];
-    double dend[9], numd[9];
-    float ld[4];
-
-    auto load4 = [&](int j) {
-        const float* s = base + (size_t)j * plane;
-        ld[0] = __ldg(s + o00); ld[1] = __ldg(s + o01); ld[2] = __ldg(s + o10); ld[3] = __ldg(s + o11);
-    };
-    auto blend9 = [&](float* za) {
-        float x0[3], x1[3];
-#pragma unroll
-        for (int pw = 0; pw < 3; ++pw) {
-            x0[pw] = __fmaf_rn(wl0[pw], ld[0], wl1[pw] * ld[1]);
-            x1[pw] = __fmaf_rn(wl0[pw], ld[2], wl1[pw] * ld[3]);
-        }
-#pragma unroll
-        for (int ph = 0; ph < 3; ++ph)
-#pragma unroll
-            for (int pw = 0; pw < 3; ++pw) za[ph * 3 + pw] = __fmaf_rn(hs0[ph], x0[pw], hs1[ph] * x1[pw]);
-    };
-
-    load4(0);
-    blend9(cur);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) { m[i] = cur[i]; dg[i] = 0.f; ng[i] = 0.f; dend[i] = 0.0; numd[i] = 0.0; }
-    load4(min(1, Dl - 1));
-    const float kc = 0.5f * (float)D;
-
-    for (int j = 0; j < Dl; ++j) {
-        blend9(nxt);                       // z-blend of low-res bin min(j+1, Dl-1) (loaded last iteration)
-        load4(min(j + 2, Dl - 1));         // prefetch for the next iteration
-        const int k1 = 3 * j + 1;
-        const float2 L1 = dlam[k1];
-        const float2 L2 = dlam[min(k1 + 1, D - 1)];
-        const float2 L3 = dlam[min(k1 + 2, D - 1)];
-        const bool has3 = (k1 + 2) < D;    // false only for j = Dl-1
-        const float kf = (float)k1 - kc;   // centred bin index of k1
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            // lazy rescale: only when the new low-res exponent exceeds the reference by > kTau
-            if (nxt[i] > m[i] + kTau) {
-                const float f = ex2_approx(m[i] - nxt[i]);
-                dg[i] *= f; ng[i] *= f;
-                dend[i] *= (double)f; numd[i] *= (double)f;
-                m[i] = nxt[i];
-            }
-            const float a = cur[i] - m[i];
-            const float dlt = nxt[i] - cur[i];
-            if (j == 0) {                  // full-res bin 0 (lambda1 == 0): exponent of low-res bin 0
-                const float e0 = ex2_approx(a);
-                dg[i] += e0;
-                ng[i] = __fmaf_rn(e0, -kc, ng[i]);
-            }
-            const float e1 = ex2_approx(__fmaf_rn(L1.y, dlt, a));
-            const float e2 = ex2_approx(__fmaf_rn(L2.y, dlt, a));
-            float e3 = ex2_approx(__fmaf_rn(L3.y, dlt, a));
-            e3 = has3 ? e3 : 0.f;
-            dg[i] += e1; ng[i] = __fmaf_rn(e1, kf, ng[i]);
-            dg[i] += e2; ng[i] = __fmaf_rn(e2, kf + 1.f, ng[i]);
-            dg[i] += e3; ng[i] = __fmaf_rn(e3, kf + 2.f, ng[i]);
-            cur[i] = nxt[i];
-        }
-        if ((j & 7) == 7 || j == Dl - 1) {  // fold the short fp32 group sums into the fp64 totals
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                dend[i] += (double)dg[i]; numd[i] += (double)ng[i];
-                dg[i] = 0.f; ng[i] = 0.f;
-            }
-        }
-    }
-    const size_t img = (size_t)H * W;
-#pragma unroll
-    for (int ph = 0; ph < 3; ++ph) {
-        if (!hv[ph]) continue;
-        const int h = 3 * r + 1 + ph;
-#pragma unroll
-        for (int pw = 0; pw < 3; ++pw) {
-            if (!wv[pw]) continue;
-            const int w = 3 * c + 1 + pw;
-            const int i = ph * 3 + pw;
-            const size_t o = (size_t)h * W + w;
-            disp[(size_t)b * img + o] = kc + (float)(numd[i] / dend[i]);
-            if (stats) {
-                stats[(size_t)b * 2 * img + o] = m[i];
-                stats[(size_t)b * 2 * img + img + o] = (float)(1.0 / dend[i]);
-            }
-        }
-    }
-}
+}  // namespace rag
+#include "disp_head_x3.cuh"
+#include "disp_head_x3p.cuh"
+#include "disp_head_x3c.cuh"
+#include "disp_head_x3t.cuh"
+#include "disp_head_x3tp.cuh"
+namespace rag {
 
 // ---------------------------------------------------------------------------------------------
 // generic backward: deterministic gather, one thread per low-res voxel.  Slow path / cross-check.
@@ -375,15 +241,40 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
                   int variant, cudaStream_t st) {
     if (!cost || !disp) return fail(RAG_E_NULL, "disp_head_fwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 1) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 5) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
-    if (variant == 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_fwd: variant 1 needs maxdisp == 3*Dl");
-    if (variant == -1) variant = x3 ? 1 : 0;
-    if (variant == 1) {
+    if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl", variant);
+    const bool tiled_ok = x3 && (Wl % 4 == 0) && aligned(cost, 16);
+    if (variant >= 4 && !tiled_ok) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl, Wl %% 4 == 0 and 16-byte aligned cost_lr", variant);
+    if (variant == -1) variant = tiled_ok ? 5 : (x3 ? 1 : 0);
+    if (variant == 5) {
+        dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
+        const size_t smem = (size_t)kTStages * kTStageFloats * sizeof(float) + ((size_t)18 * 128 + D) * sizeof(float2);
+        auto kern = head_fwd_x3tp_kernel;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "disp_head_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        }
+        kern<<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+    } else if (variant == 4) {
+        dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
+        const size_t smem = ((size_t)kTStages * kTStageFloats + D) * sizeof(float);
+        head_fwd_x3t_kernel<<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+    } else if (variant == 3) {
+        constexpr int NT = 128;
+        const long long n = (long long)(Hl + 1) * 3 * Wl;
+        dim3 grid((unsigned)((n + NT - 1) / NT), B);
+        head_fwd_x3c_kernel<NT><<<grid, NT, (size_t)D * sizeof(float), st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+    } else if (variant == 2) {
         constexpr int WARPS = 4;
         dim3 grid((Wl + 1 + 31) / 32, (Hl + 1 + WARPS - 1) / WARPS, B);
-        head_fwd_x3_kernel<WARPS><<<grid, WARPS * 32, (size_t)D * sizeof(float2), st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+        const size_t smem = ((size_t)D + 20 * WARPS * 32) * sizeof(float2);
+        head_fwd_x3p_kernel<WARPS><<<grid, WARPS * 32, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+    } else if (variant == 1) {
+        constexpr int WARPS = 4;
+        dim3 grid((Wl + 1 + 31) / 32, (Hl + 1 + WARPS - 1) / WARPS, B);
+        head_fwd_x3_kernel<WARPS><<<grid, WARPS * 32, (size_t)D * sizeof(float), st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
     } else {
         constexpr int NT = 128;
         dim3 grid((9 * Hl * Wl + NT - 1) / NT, B);
@@ -396,12 +287,28 @@ int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, cons
                   int B, int Dl, int Hl, int Wl, int D, int variant, cudaStream_t st) {
     if (!cost || !gdisp || !disp || !stats || !gcost) return fail(RAG_E_NULL, "disp_head_bwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 0) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 1) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
-    constexpr int NT = 128;
-    const size_t nvox = (size_t)Dl * Hl * Wl;
-    dim3 grid((unsigned)((nvox + NT - 1) / NT), B);
-    head_bwd_generic_kernel<NT><<<grid, NT, 0, st>>>(cost, gdisp, disp, stats, gcost, Dl, Hl, Wl, D, sd, sh, sw);
+    const bool x3 = (D == 3 * Dl);
+    if (variant == 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_bwd: variant 1 needs maxdisp == 3*Dl");
+    if (variant == -1) variant = x3 ? 1 : 0;
+    if (variant == 1) {
+        constexpr int J = 16;
+        const int nJ = (Dl + J - 1) / J;
+        const int strips = (Wl + 30) / 31;
+        // taller row tiles recompute fewer halo rows; use them when there is enough work to fill the GPU
+        int TR = 8;
+        if ((long long)B * strips * ((Hl + TR - 1) / TR) * nJ < 4LL * 4 * kNumSMs) TR = 4;
+        const int n_tasks = ((Hl + TR - 1) / TR) * nJ;
+        dim3 grid(strips, (n_tasks + 3) / 4, B);
+        const size_t smem = (size_t)(3 * (D + 3) + 4 * J * 32) * sizeof(float);
+        head_bwd_x3_kernel<J><<<grid, 128, smem, st>>>(cost, gdisp, disp, stats, gcost, Dl, Hl, Wl, sd, TR, nJ, n_tasks);
+    } else {
+        constexpr int NT = 128;
+        const size_t nvox = (size_t)Dl * Hl * Wl;
+        dim3 grid((unsigned)((nvox + NT - 1) / NT), B);
+        head_bwd_generic_kernel<NT><<<grid, NT, 0, st>>>(cost, gdisp, disp, stats, gcost, Dl, Hl, Wl, D, sd, sh, sw);
+    }
     return check_launch("disp_head_bwd");
 }
 

@@ -48,7 +48,7 @@ def test_golden(F_, path):
         tol = 6e-4     # ... and with sigma (near-one-hot softmax); see test_oracle_golden
     assert np.abs(disp.detach().cpu().numpy() - z["disp"]).max() <= tol
     d64, g64 = O.disp_head_grad_f64(z["cost"][:, 0], z["gdisp"], md)
-    assert np.abs(disp.detach().cpu().numpy() - d64).max() <= 2e-5
+    assert np.abs(disp.detach().cpu().numpy() - d64).max() <= (1e-4 if "_s5" in path else 2e-5)
     disp.backward(torch.from_numpy(z["gdisp"]).cuda())
     assert maxnorm_rel(cost.grad.cpu().numpy(), z["gcost"]) <= 2 * TOL_GRAD  # vs fp32 reference (own noise 7.5e-6)
     assert maxnorm_rel(cost.grad.cpu().numpy()[:, 0], g64) <= TOL_GRAD       # vs exact
@@ -76,6 +76,8 @@ CASES = [
     (1, 64, 16, 33, 192, 5.0),   # sigma 5 stress
     (1, 48, 6, 10, 192, 1.0),    # depth != maxdisp/3 -> generic kernel
     (1, 1, 2, 2, 3, 1.0),        # smallest x3 case
+    (2, 64, 7, 36, 192, 1.0),    # tiled kernel: ragged CTA tiles (Hl % 4 != 0, Wl % 32 != 0)
+    (1, 20, 5, 4, 60, 1.0),      # tiled kernel: Dl not a multiple of the 8-bin stage, one 4-wide strip
     (1, 4, 1, 1, 12, 1.0),       # single low-res pixel
 ]
 
@@ -87,15 +89,20 @@ def test_forward_parity(F_, case):
     ref_cpu = O.disp_head_ref(cost, md).numpy()
     ref_gpu = O.disp_head_ref(cost.cuda(), md).cpu().numpy()
     d64, _ = O.disp_head_f64(cost[:, 0].numpy(), md)
-    variants = [None, 0] + ([1] if md == 3 * dl else [])
+    variants = [None, 0] + ([1, 2, 3] if md == 3 * dl else []) + ([4, 5] if md == 3 * dl and wl % 4 == 0 else [])
     for v in variants:
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=v)
         out = disp.cpu().numpy()
         own = np.abs(out - d64).max()
         assert own <= (2e-5 if sigma <= 1 else 1e-4), f"variant {v}: own error {own}"
-        tol = TOL_DISP * (md / 192) if sigma <= 1 else 1e-3
-        assert np.abs(out - ref_cpu).max() <= tol, f"variant {v} vs CPU reference"
-        assert np.abs(out - ref_gpu).max() <= tol, f"variant {v} vs CUDA reference"
+        # vs the fp32 reference: within 1e-4 px, allowing at each pixel for the reference's OWN deviation
+        # from the exact value of its formula (its fp32 sum of p_k*k is good to ~1e-4 at maxdisp 192 and
+        # worse at maxdisp 288 / sigma 5); and the bulk of the pixels within 1e-4 outright
+        for name, ref in (("CPU", ref_cpu), ("CUDA", ref_gpu)):
+            err = np.abs(out - ref)
+            assert np.all(err <= TOL_DISP + np.abs(ref - d64)), f"variant {v} vs {name} reference"
+            if sigma <= 1:
+                assert (err <= TOL_DISP).mean() >= 0.995, f"variant {v} vs {name} reference (bulk)"
         disp2, _ = F_.disp_head_forward(cost.cuda(), md, want_stats=False, variant=v)
         assert torch.equal(disp, disp2)
 
@@ -111,7 +118,7 @@ def test_backward_parity(F_, case):
     _, gref = O.disp_head_grad_ref(cost, gd, md)
     _, g64 = O.disp_head_grad_f64(cost[:, 0].numpy(), gd.numpy(), md)
     variants = [None, 0] + ([1] if md == 3 * dl else [])
-    for vf in ([None, 0] if md != 3 * dl else [None, 0, 1]):
+    for vf in ([None, 0] if md != 3 * dl else [None, 0, 1, 2, 3] + ([4, 5] if wl % 4 == 0 else [])):
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=vf)
         for v in variants:
             try:
