@@ -113,6 +113,8 @@ head_fwd_generic_kernel(const float* __restrict__ cost, float* __restrict__ disp
 #include "disp_head_x3c.cuh"
 #include "disp_head_x3t.cuh"
 #include "disp_head_x3tp.cuh"
+#include "disp_head_x3u.cuh"
+#include "disp_head_x3v.cuh"
 namespace rag {
 
 // ---------------------------------------------------------------------------------------------
@@ -241,14 +243,24 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
                   int variant, cudaStream_t st) {
     if (!cost || !disp) return fail(RAG_E_NULL, "disp_head_fwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 5) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 9) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
     if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl", variant);
     const bool tiled_ok = x3 && (Wl % 4 == 0) && aligned(cost, 16);
     if (variant >= 4 && !tiled_ok) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl, Wl %% 4 == 0 and 16-byte aligned cost_lr", variant);
-    if (variant == -1) variant = tiled_ok ? 5 : (x3 ? 1 : 0);
-    if (variant == 5) {
+    if (variant == -1) variant = tiled_ok ? 7 : (x3 ? 1 : 0);
+    if (variant >= 7) {
+        dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
+        const size_t smem = (size_t)kTStages * kTStageFloats * sizeof(float) + ((size_t)18 * 128 + 4 * Dl) * sizeof(float2);
+        if (variant == 7) head_fwd_x3v_kernel<4><<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+        if (variant == 8) head_fwd_x3v_kernel<5><<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+        if (variant == 9) head_fwd_x3v_kernel<6><<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+    } else if (variant == 6) {
+        dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
+        const size_t smem = (size_t)kTStages * kTStageFloats * sizeof(float) + (size_t)Dl * sizeof(float4);
+        head_fwd_x3u_kernel<<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+    } else if (variant == 5) {
         dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
         const size_t smem = (size_t)kTStages * kTStageFloats * sizeof(float) + ((size_t)18 * 128 + D) * sizeof(float2);
         auto kern = head_fwd_x3tp_kernel;

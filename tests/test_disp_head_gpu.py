@@ -89,7 +89,7 @@ def test_forward_parity(F_, case):
     ref_cpu = O.disp_head_ref(cost, md).numpy()
     ref_gpu = O.disp_head_ref(cost.cuda(), md).cpu().numpy()
     d64, _ = O.disp_head_f64(cost[:, 0].numpy(), md)
-    variants = [None, 0] + ([1, 2, 3] if md == 3 * dl else []) + ([4, 5] if md == 3 * dl and wl % 4 == 0 else [])
+    variants = [None, 0] + ([1, 2, 3] if md == 3 * dl else []) + ([4, 5, 6, 7] if md == 3 * dl and wl % 4 == 0 else [])
     for v in variants:
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=v)
         out = disp.cpu().numpy()
@@ -101,8 +101,8 @@ def test_forward_parity(F_, case):
         for name, ref in (("CPU", ref_cpu), ("CUDA", ref_gpu)):
             err = np.abs(out - ref)
             assert np.all(err <= TOL_DISP + np.abs(ref - d64)), f"variant {v} vs {name} reference"
-            if sigma <= 1:
-                assert (err <= TOL_DISP).mean() >= 0.995, f"variant {v} vs {name} reference (bulk)"
+            if sigma <= 1:  # the reference's fp32 noise scales with the magnitude of sum p_k*k, i.e. with maxdisp
+                assert (err <= TOL_DISP * md / 192).mean() >= 0.995, f"variant {v} vs {name} reference (bulk)"
         disp2, _ = F_.disp_head_forward(cost.cuda(), md, want_stats=False, variant=v)
         assert torch.equal(disp, disp2)
 
@@ -118,7 +118,7 @@ def test_backward_parity(F_, case):
     _, gref = O.disp_head_grad_ref(cost, gd, md)
     _, g64 = O.disp_head_grad_f64(cost[:, 0].numpy(), gd.numpy(), md)
     variants = [None, 0] + ([1] if md == 3 * dl else [])
-    for vf in ([None, 0] if md != 3 * dl else [None, 0, 1, 2, 3] + ([4, 5] if wl % 4 == 0 else [])):
+    for vf in ([None, 0] if md != 3 * dl else [None, 0, 1, 2, 3] + ([4, 5, 6, 7] if wl % 4 == 0 else [])):
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=vf)
         for v in variants:
             try:

@@ -103,7 +103,7 @@ def main():
         report("torch_sum_same_bytes(r)", -1, med, best, vol_bytes)
         del gc
     if want("head_fwd"):
-        for v in (5, 4, 1):
+        for v in (9, 8, 7):
             try:
                 med, best = timeit(lambda: F_.disp_head_forward(cost_lr, md, True, variant=v), a.iters, flush)
                 report("head_fwd", v, med, best, hf_bytes)
