@@ -1,0 +1,106 @@
+"""Drop-in boundary for the reference's stereo networks.
+
+The reference builds the cost volume inline in three ``forward`` methods and owns its ``Disp`` head:
+
+* ``Network.forward(left, right, t, task_arch=None, path=None)``      src/models/rag_model.py:369-387
+* ``Network.search_forward(left, right, t, selected_ops)``            src/models/rag_model.py:688-706
+* ``BasicNetwork.forward(left, right, fea_ops, mat_ops)``             src/automl/mdenas_basicmodel.py:76-97
+
+The functions below are those three methods with the nine inline cost-volume lines replaced by one
+call to the CUDA kernel and ``self.disp`` routed through the fused head.  ``install()`` binds them
+onto the reference's classes (and swaps its ``Disp`` / ``DisparityRegression``), so the growth loop
+(``expand`` / ``select``), the NAS search and ``approaches/rag.py`` call the B200 path unchanged.
+Everything else in the reference (2-D / 3-D convolutions, growth logic) is untouched.
+
+``PathRouter`` is the dispatch the paper calls the Scene Router: the reference selects the grown
+path with the oracle task id (``self.archis[t]``, approaches/rag.py:208,416); the router groups a
+batch by a per-sample scene id and runs each group through its ``task_arch``.
+"""
+from __future__ import annotations
+
+import torch
+
+from .functional import cost_volume, disp_head
+from .modules import CostVolume, Disp, DisparityRegression  # noqa: F401  (re-exported)
+
+
+def _head(self, cost):
+    # use the module if it is already ours (keeps hooks working), else the functional form
+    d = getattr(self, "disp", None)
+    if isinstance(d, Disp):
+        return d(cost)
+    return disp_head(cost, self.maxdisp)
+
+
+def network_forward(self, left, right, t, task_arch=None, path=None):
+    """Replacement for Network.forward (rag_model.py:369-387)."""
+    x = self.feature(left, task_arch, path)
+    y = self.feature(right, task_arch, path)
+    cost = cost_volume(x, y, self.maxdisp)          # rag_model.py:375-383
+    cost = self.matching(cost, task_arch, path)
+    return _head(self, cost)                        # rag_model.py:386
+
+
+def network_search_forward(self, left, right, t, selected_ops):
+    """Replacement for Network.search_forward (rag_model.py:688-706)."""
+    x = self.search_feature(left, selected_ops)
+    y = self.search_feature(right, selected_ops)
+    cost = cost_volume(x, y, self.maxdisp)          # rag_model.py:694-702
+    cost = self.search_matching(cost, selected_ops, t)
+    return _head(self, cost)
+
+
+def basic_network_forward(self, left, right, fea_ops, mat_ops):
+    """Replacement for BasicNetwork.forward (mdenas_basicmodel.py:76-97)."""
+    x = self.feature(left, fea_ops)
+    y = self.feature(right, fea_ops)
+    cost = cost_volume(x, y, self.maxdisp)          # mdenas_basicmodel.py:83-91
+    cost = self.matching(cost, mat_ops)
+    return _head(self, cost)
+
+
+def install(rag_model=None, mdenas_basicmodel=None) -> dict:
+    """Bind the B200 hot path onto the reference's modules (pass the imported module objects
+    ``models.rag_model`` and/or ``automl.mdenas_basicmodel``).  Returns what was patched.
+    New networks constructed afterwards get ``rag_b200.Disp``; existing instances keep working
+    because the patched ``forward`` methods bypass ``self.disp`` when it is the reference's."""
+    done = {}
+    if rag_model is not None:
+        rag_model.Network.forward = network_forward
+        rag_model.Network.search_forward = network_search_forward
+        rag_model.Disp = Disp
+        rag_model.DisparityRegression = DisparityRegression
+        done["rag_model"] = ["Network.forward", "Network.search_forward", "Disp", "DisparityRegression"]
+    if mdenas_basicmodel is not None:
+        mdenas_basicmodel.BasicNetwork.forward = basic_network_forward
+        mdenas_basicmodel.Disp = Disp
+        mdenas_basicmodel.DisparityRegression = DisparityRegression
+        done["mdenas_basicmodel"] = ["BasicNetwork.forward", "Disp", "DisparityRegression"]
+    return done
+
+
+class PathRouter:
+    """Scene-router dispatch over grown paths (BASELINE config 4): ``archis[u]`` is the ``task_arch``
+    of scene u (what ``Network.select`` returned for task u, approaches/rag.py:101-102).  ``route``
+    runs each scene's sub-batch through its path and scatters the results back in input order.
+    The hot-path modules are parameter-free and shared by every path."""
+
+    def __init__(self, model, archis):
+        self.model = model
+        self.archis = list(archis)
+
+    @torch.no_grad()
+    def route(self, left: torch.Tensor, right: torch.Tensor, scene_ids) -> torch.Tensor:
+        scene_ids = torch.as_tensor(scene_ids)
+        if scene_ids.numel() != left.shape[0]:
+            raise ValueError("one scene id per stereo pair")
+        out = None
+        for u in sorted(set(int(s) for s in scene_ids.tolist())):
+            if not 0 <= u < len(self.archis):
+                raise IndexError(f"scene id {u} has no grown path (have {len(self.archis)})")
+            idx = torch.nonzero(scene_ids == u).flatten().to(left.device)
+            d = self.model.forward(left.index_select(0, idx).contiguous(), right.index_select(0, idx).contiguous(), u, self.archis[u])
+            if out is None:
+                out = torch.empty((left.shape[0],) + tuple(d.shape[1:]), dtype=d.dtype, device=d.device)
+            out.index_copy_(0, idx, d)
+        return out
