@@ -94,7 +94,7 @@ def test_forward_parity(F_, case):
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=v)
         out = disp.cpu().numpy()
         own = np.abs(out - d64).max()
-        assert own <= (2e-5 if sigma <= 1 else 1e-4), f"variant {v}: own error {own}"
+        assert own <= (2e-5 * md / 192 if sigma <= 1 else 1e-4), f"variant {v}: own error {own}"
         # vs the fp32 reference: within 1e-4 px, allowing at each pixel for the reference's OWN deviation
         # from the exact value of its formula (its fp32 sum of p_k*k is good to ~1e-4 at maxdisp 192 and
         # worse at maxdisp 288 / sigma 5); and the bulk of the pixels within 1e-4 outright
@@ -129,7 +129,11 @@ def test_backward_parity(F_, case):
                 raise
             out = gc.cpu().numpy()
             assert maxnorm_rel(out[:, 0], g64) <= TOL_GRAD, f"fwd {vf} bwd {v} vs fp64"
-            assert maxnorm_rel(out, gref.numpy()) <= 2 * TOL_GRAD, f"fwd {vf} bwd {v} vs fp32 reference"
+            if np.abs(g64).max() > 1e-6 * gd.abs().max().item():   # Dl == 1: the true gradient is 0 and the
+                # fp32 reference returns pure rounding noise (~1e-8); nothing to be relative to
+                assert maxnorm_rel(out, gref.numpy()) <= 2 * TOL_GRAD, f"fwd {vf} bwd {v} vs fp32 reference"
+            else:
+                assert np.abs(out).max() <= 1e-6 * gd.abs().max().item()
 
 
 def test_backward_deterministic_and_vs_cuda_autograd(F_):
