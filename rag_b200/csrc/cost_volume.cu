@@ -223,10 +223,9 @@ static int check_cv_args(const void* a, const void* b_, const void* c, int B, in
     return RAG_OK;
 }
 
-template <int V>
+template <int V, int NT>
 static int launch_cv_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
-                         int variant, cudaStream_t st) {
-    constexpr int NT = 256;
+                         int variant, size_t smem_floor, cudaStream_t st) {
     // variant: 0 -> 16-disparity chunks, 36 KB tiles; 1 -> 32-disparity chunks; 2 -> whole sweep per CTA;
     //          3 -> 16-disparity chunks, 72 KB tiles
     int dchunk = variant == 1 ? 32 : variant == 2 ? Df : 16;
@@ -238,7 +237,8 @@ static int launch_cv_fwd(const float* x, const float* y, float* cost, int B, int
     // prefer an R that divides Hf (no ragged last tile) when one is close
     for (int r = R; r >= (R * 3) / 4 && r >= 1; --r)
         if (Hf % r == 0) { R = r; break; }
-    const size_t smem = (size_t)(V + 1) * R * Wf * 4 + (size_t)R * (Wf / V) * 2;
+    size_t smem = (size_t)(V + 1) * R * Wf * 4 + (size_t)R * (Wf / V) * 2;
+    if (smem < smem_floor) smem = smem_floor;   // occupancy experiments only
     if (smem > 200 * 1024) return fail(RAG_E_SHAPE, "cost_volume_fwd: Wf=%d too wide for one shared-memory row tile", Wf);
     auto kern = cv_fwd_kernel<V, NT>;
     if (smem > 48 * 1024) {
@@ -254,12 +254,17 @@ static int launch_cv_fwd(const float* x, const float* y, float* cost, int B, int
 int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
                     int variant, cudaStream_t st) {
     if (int e = check_cv_args(x, y, cost, B, C, Df, Hf, Wf)) return e;
-    if (variant < 0 || variant > 3) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
+    if (variant < 0 || variant > 7) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
     const bool a16 = aligned(x, 16) && aligned(y, 16) && aligned(cost, 16);
     const bool a8 = aligned(x, 8) && aligned(y, 8) && aligned(cost, 8);
-    if (Wf % 4 == 0 && a16) return launch_cv_fwd<4>(x, y, cost, B, C, Df, Hf, Wf, variant, st);
-    if (Wf % 2 == 0 && a8) return launch_cv_fwd<2>(x, y, cost, B, C, Df, Hf, Wf, variant, st);
-    return launch_cv_fwd<1>(x, y, cost, B, C, Df, Hf, Wf, variant, st);
+    if (variant >= 4) {   // occupancy experiments: 128-thread CTAs, 4: unconstrained, 5: <=4, 6: <=2, 7: 1 CTA per SM
+        if (!(Wf % 4 == 0 && a16)) return fail(RAG_E_VARIANT, "cost_volume_fwd: variants 4-7 need Wf %% 4 == 0");
+        const size_t floor_b = variant == 5 ? 50 * 1024 : variant == 6 ? 100 * 1024 : variant == 7 ? 190 * 1024 : 0;
+        return launch_cv_fwd<4, 128>(x, y, cost, B, C, Df, Hf, Wf, 0, floor_b, st);
+    }
+    if (Wf % 4 == 0 && a16) return launch_cv_fwd<4, 256>(x, y, cost, B, C, Df, Hf, Wf, variant, 0, st);
+    if (Wf % 2 == 0 && a8) return launch_cv_fwd<2, 256>(x, y, cost, B, C, Df, Hf, Wf, variant, 0, st);
+    return launch_cv_fwd<1, 256>(x, y, cost, B, C, Df, Hf, Wf, variant, 0, st);
 }
 
 int cost_volume_bwd(const float* g, float* gx, float* gy, int B, int C, int Df, int Hf, int Wf,

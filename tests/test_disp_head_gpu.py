@@ -136,6 +136,37 @@ def test_backward_parity(F_, case):
                 assert np.abs(out).max() <= 1e-6 * gd.abs().max().item()
 
 
+@pytest.mark.parametrize("sigma", [30.0, 8000.0])
+def test_large_magnitude_costs_exercise_the_rescale_path(F_, sigma):
+    """An untrained Matching Net emits costs with sigma ~ 8000: the running maximum
+    jumps by far more than the lazy-rescale threshold, the softmax is one-hot.  Every variant must stay
+    finite and agree with the fp64 evaluation wherever that is well conditioned (a clear winner bin)."""
+    g = gen(int(sigma))
+    b, dl, hl, wl, md = 1, 64, 6, 36, 192
+    cost = randn((b, 1, dl, hl, wl), g, sigma)
+    # monotone ramps force repeated upward moves of the reference exponent
+    cost[0, 0, :, 0, :] = -torch.arange(dl, dtype=torch.float32)[:, None] * sigma
+    cost[0, 0, :, 1, :] = torch.arange(dl, dtype=torch.float32)[:, None] * sigma
+    d64, p64 = O.disp_head_f64(cost[:, 0].numpy(), md)
+    gd = sparse_grad((b, 3 * hl, 3 * wl), g, keep=1.0)
+    _, g64 = O.disp_head_grad_f64(cost[:, 0].numpy(), gd.numpy(), md)
+    # well conditioned = a 1-ulp change of the logits cannot move the result by more than ~1e-4
+    top2 = np.sort(p64, axis=1)[:, -2:]
+    clear = (top2[:, 1] > 0.999) | (sigma <= 30.0)
+    for v in (None, 0, 1, 2, 3, 4, 5, 6, 7):
+        disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=v)
+        out = disp.cpu().numpy()
+        assert np.isfinite(out).all() and out.min() >= 0 and out.max() <= md - 1, f"variant {v}"
+        tol = 2e-3 if sigma <= 30.0 else 1e-2
+        assert np.abs(out - d64)[clear].max() <= tol, f"variant {v}: {np.abs(out - d64)[clear].max()}"
+        assert torch.isfinite(stats).all()
+        for vb in (0, 1):
+            gc = F_.disp_head_backward(cost.cuda(), gd.cuda(), disp, stats, md, variant=vb).cpu().numpy()
+            assert np.isfinite(gc).all(), f"fwd {v} bwd {vb}"
+            if sigma <= 30.0:
+                assert maxnorm_rel(gc[:, 0], g64) <= 5e-3, f"fwd {v} bwd {vb}"
+
+
 def test_backward_deterministic_and_vs_cuda_autograd(F_):
     g = gen(21)
     cost = randn((2, 1, 64, 8, 24), g).cuda().requires_grad_(True)
