@@ -39,17 +39,14 @@ template <> __device__ __forceinline__ float zero_vec<float>() { return 0.f; }
 // ---------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------
-// grid: x = h-tile * n_dchunks + d-chunk, y = c, z = b.   smem: [V+1][R*Wf] floats + u16 table[R*Wv]
+// One work unit = R rows of one (b,c) x one sweep of `dchunk` disparities.
+// smem: [V+1][R*Wf] floats + u16 table[R*Wv]
 template <int V, int NT>
-__global__ void __launch_bounds__(NT)
-cv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ cost,
-              int C, int Df, int Hf, int Wf, int R, int dchunk, int n_dchunks) {
+__device__ __forceinline__ void
+cv_fwd_unit(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ cost,
+            int C, int Df, int Hf, int Wf, int R, int dchunk, int tile, int dci, int c, int b, float* smem) {
     using VT = typename Vec<V>::T;
-    extern __shared__ __align__(16) float smem[];
     const int Wv = Wf / V;
-    const int tile = blockIdx.x / n_dchunks;
-    const int dci = blockIdx.x - tile * n_dchunks;
-    const int c = blockIdx.y, b = blockIdx.z;
     const int h0 = tile * R;
     const int rows = min(R, Hf - h0);
     const int d0 = dci * dchunk;                 // multiple of V by construction
@@ -117,6 +114,35 @@ cv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* _
         st_stream(reinterpret_cast<VT*>(right + off), yv);
         p += NT;
         while (p >= P) { p -= P; ++dl; }
+    }
+}
+
+// grid: x = h-tile * n_dchunks + d-chunk, y = c, z = b.
+template <int V, int NT>
+__global__ void __launch_bounds__(NT)
+cv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ cost,
+              int C, int Df, int Hf, int Wf, int R, int dchunk, int n_dchunks) {
+    extern __shared__ __align__(16) float smem[];
+    const int tile = blockIdx.x / n_dchunks;
+    cv_fwd_unit<V, NT>(x, y, cost, C, Df, Hf, Wf, R, dchunk, tile, blockIdx.x - tile * n_dchunks, blockIdx.y, blockIdx.z, smem);
+}
+
+// Persistent form: a fixed number of CTAs (a multiple of the SM count) walks the work units.  Used when the
+// kernel has to SHARE every SM with the disparity-head kernel on a second stream (rag_b200.pipeline): a
+// resident footprint of exactly k CTAs per SM leaves the rest of the register file / shared memory free.
+template <int V, int NT>
+__global__ void __launch_bounds__(NT)
+cv_fwd_persistent_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ cost,
+                         int B, int C, int Df, int Hf, int Wf, int R, int dchunk, int n_dchunks, int n_tiles) {
+    extern __shared__ __align__(16) float smem[];
+    const int per_bc = n_tiles * n_dchunks;
+    const long long total = (long long)B * C * per_bc;
+    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
+        const int bc = (int)(u / per_bc);
+        const int rem = (int)(u - (long long)bc * per_bc);
+        const int tile = rem / n_dchunks;
+        cv_fwd_unit<V, NT>(x, y, cost, C, Df, Hf, Wf, R, dchunk, tile, rem - tile * n_dchunks, bc % C, bc / C, smem);
+        __syncthreads();   // the staging buffers are reused by the next unit
     }
 }
 
@@ -254,7 +280,23 @@ static int launch_cv_fwd(const float* x, const float* y, float* cost, int B, int
 int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
                     int variant, cudaStream_t st) {
     if (int e = check_cv_args(x, y, cost, B, C, Df, Hf, Wf)) return e;
-    if (variant < 0 || variant > 7) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
+    if (variant < 0 || variant > 10) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
+    if (variant >= 8) {   // persistent: exactly 3 (variant 8), 4 (9) or 2 (10) 128-thread CTAs per SM, ~20 KB tiles
+        if (!(Wf % 4 == 0 && aligned(x, 16) && aligned(y, 16) && aligned(cost, 16)))
+            return fail(RAG_E_VARIANT, "cost_volume_fwd: persistent variants need Wf %% 4 == 0 and 16-byte aligned pointers");
+        constexpr int V = 4, NT = 128;
+        const int per_sm = variant == 8 ? 3 : variant == 9 ? 4 : 2;
+        const int dchunk = 16, n_dchunks = (Df + dchunk - 1) / dchunk;
+        int R = (int)((20 * 1024) / ((size_t)(V + 1) * 4 * Wf + (size_t)2 * (Wf / V)));
+        R = R < 1 ? 1 : (R > Hf ? Hf : R);
+        for (int r = R; r >= (R * 3) / 4 && r >= 1; --r)
+            if (Hf % r == 0) { R = r; break; }
+        const size_t smem = (size_t)(V + 1) * R * Wf * 4 + (size_t)R * (Wf / V) * 2;
+        if (smem > 48 * 1024) return fail(RAG_E_SHAPE, "cost_volume_fwd: Wf=%d too wide for the persistent variant", Wf);
+        const int n_tiles = (Hf + R - 1) / R;
+        cv_fwd_persistent_kernel<V, NT><<<kNumSMs * per_sm, NT, smem, st>>>(x, y, cost, B, C, Df, Hf, Wf, R, dchunk, n_dchunks, n_tiles);
+        return check_launch("cost_volume_fwd(persistent)");
+    }
     const bool a16 = aligned(x, 16) && aligned(y, 16) && aligned(cost, 16);
     const bool a8 = aligned(x, 8) && aligned(y, 8) && aligned(cost, 8);
     if (variant >= 4) {   // occupancy experiments: 128-thread CTAs, 4: unconstrained, 5: <=4, 6: <=2, 7: 1 CTA per SM

@@ -53,7 +53,7 @@ def test_forward_bit_exact(F_, shape):
     g = gen(hash(shape) % 1000)
     x, y = randn((b, c, hf, wf), g), randn((b, c, hf, wf), g)
     ref = O.cost_volume_ref(x, y, md)
-    for variant in (None, 0, 1, 2, 3):
+    for variant in (None, 0, 1, 2, 3) + ((4, 8, 9, 10) if wf % 4 == 0 else ()):
         out = F_.cost_volume_forward(x.cuda(), y.cuda(), int(md / 3), variant=variant)
         assert torch.equal(out.cpu(), ref), f"variant {variant}"
 

@@ -81,7 +81,7 @@ def main():
         return not a.only or k in a.only.split(",")
 
     if want("cv_fwd"):
-        for v in (0, 3, 4, 5, 6, 7):
+        for v in (0, 8, 9, 10):
             med, best = timeit(lambda: F_.cost_volume_forward(x, y, df, variant=v), a.iters, flush)
             report("cv_fwd", v, med, best, vol_bytes)
         # torch baseline for scale: a plain device copy of the same number of bytes
