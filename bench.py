@@ -33,6 +33,11 @@ WORKLOADS = {
     # name: (B per GPU, C, Hf, Wf, Df, maxdisp, backward?, description)
     "infer": (8, 12, 160, 320, 64, 192, False, "inference batch 8/GPU at 400x880 padded to 480x960 (reference eval pad), maxdisp 192"),
     "train": (4, 12, 96, 192, 64, 192, True, "training step fwd+bwd batch 4/GPU at 288x576 crop, maxdisp 192"),
+    # configs[3]: 32 pairs routed over 4 grown scene paths = 4 sub-batches of 8 per step (the hot path is path-independent)
+    "router": (32, 12, 160, 320, 64, 192, False, "scene-router inference, 32 pairs/GPU at 480x960 as 4 path sub-batches of 8, maxdisp 192"),
+    # configs[4]: resolution / disparity sweep
+    "sweep192": (4, 12, 128, 416, 64, 192, False, "inference batch 4/GPU at 384x1248, maxdisp 192"),
+    "sweep288": (4, 12, 128, 416, 96, 288, False, "inference batch 4/GPU at 384x1248, maxdisp 288"),
 }
 
 
@@ -223,12 +228,14 @@ def run_gpu(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     marks = [[ev() for _ in range(5)] for _ in range(K)]
 
+    sub = 8 if args.workload == "router" else b   # router: one call per scene path
+
     def step(mk=None):
         if mk: mk[0].record()
         if not bwd:
-            cost = F_.cost_volume_forward(x, y, df)
+            cost = [F_.cost_volume_forward(x[i:i + sub], y[i:i + sub], df) for i in range(0, b, sub)]
             if mk: mk[1].record()
-            disp, _ = F_.disp_head_forward(cl, md, want_stats=False)
+            disp = [F_.disp_head_forward(cl[i:i + sub], md, want_stats=False)[0] for i in range(0, b, sub)]
             if mk: mk[2].record()
             return cost, disp
         cost = F_.cost_volume_forward(x, y, df)
@@ -270,12 +277,13 @@ def run_gpu(args):
     seg_ms = [sum(marks[k][i].elapsed_time(marks[k][i + 1]) for k in range(K)) / K for i in range(n_seg)]
     cvb, hfb, hbb = alg_bytes(c, hf, wf, df)
     peak, peak_src = measured_peak()
-    cv_ms = seg_ms[0]
-    achieved = cvb * b / (cv_ms * 1e-3) / 1e9
+    n_sub = b // sub
+    cv_ms = seg_ms[0] / n_sub                       # average duration of ONE cost-volume launch
+    achieved = cvb * sub / (cv_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "cv_fwd_kernel<4,256> (cost-volume forward)", "achieved": round(achieved, 1), "peak": peak,
         "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic("cv_fwd_kernel"),
-        "peak_source": peak_src, "alg_bytes_per_launch": cvb * b, "avg_launch_ms": round(cv_ms, 5),
+        "peak_source": peak_src, "alg_bytes_per_launch": cvb * sub, "avg_launch_ms": round(cv_ms, 5),
     }
     path_bytes = (cvb + hfb + ((cvb + hbb) if bwd else 0)) * b
     kernels = {"cv_fwd_ms": seg_ms[0], "head_fwd_ms": seg_ms[1]}

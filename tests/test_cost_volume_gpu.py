@@ -109,6 +109,25 @@ def test_full_size_properties(F_):
     assert torch.equal(gx, cnt_x.expand_as(gx)) and torch.equal(gy, cnt_y.expand_as(gy))
 
 
+def test_empty_and_maximum_sizes(F_):
+    """Empty batch (the reference's zero-fill of an empty tensor) and BASELINE config 4's size:
+    32 pairs at 480x960 -> a 10 GB volume; config 5's largest: 384x1248 at maxdisp 288."""
+    e = F_.cost_volume_forward(torch.zeros(0, 12, 4, 8, device="cuda"), torch.zeros(0, 12, 4, 8, device="cuda"), 64)
+    assert e.shape == (0, 24, 64, 4, 8)
+    gx, gy = F_.cost_volume_backward(torch.zeros(0, 24, 64, 4, 8, device="cuda"), 12)
+    assert gx.shape == (0, 12, 4, 8) and gy.shape == (0, 12, 4, 8)
+    for (b, c, hf, wf, df) in ((32, 12, 160, 320, 64), (4, 12, 128, 416, 96)):
+        g = gen(b)
+        x, y = randn((b, c, hf, wf), g).cuda(), randn((b, c, hf, wf), g).cuda()
+        cost = F_.cost_volume_forward(x, y, df)
+        for d in (0, 7, df - 1):
+            assert torch.equal(cost[:, :c, d, :, d:], x[..., d:]) and torch.equal(cost[:, c:, d, :, d:], y[..., : wf - d])
+            assert not cost[:, :, d, :, :d].any()
+        assert torch.equal(cost[b - 1, c + 3, 5, hf - 1, 5:], y[b - 1, 3, hf - 1, : wf - 5])
+        del cost
+        torch.cuda.empty_cache()
+
+
 def test_autograd_module_and_hygiene(F_):
     import copy
     import pickle
