@@ -109,6 +109,45 @@ def cpu_reference(workload, budget_s=12.0, min_reps=2):
     }, times
 
 
+def torch_cuda_reference(workload, dev, reps=5):
+    """The reference's own op sequence (oracle port) run by PyTorch eager ON THE SAME GPU: the honest GPU
+    baseline.  One pair per call (its temporaries are ~1.8 GB/pair at 480x960)."""
+    import torch
+
+    from oracle import rag_oracle as O
+
+    b, c, hf, wf, df, md, bwd, _ = WORKLOADS[workload]
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(1, c, hf, wf, generator=g).to(dev)
+    y = torch.randn(1, c, hf, wf, generator=g).to(dev)
+    cl = torch.randn(1, 1, df, hf, wf, generator=g).to(dev)
+
+    def step():
+        if not bwd:
+            with torch.no_grad():
+                O.cost_volume_ref(x, y, md)
+                O.disp_head_ref(cl, md)
+        else:
+            xr, yr, cr = x.clone().requires_grad_(True), y.clone().requires_grad_(True), cl.clone().requires_grad_(True)
+            cost = O.cost_volume_ref(xr, yr, md)
+            cost.backward(torch.ones_like(cost))
+            d = O.disp_head_ref(cr, md)
+            d.backward(torch.ones_like(d))
+
+    step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    torch.cuda.empty_cache()
+    return {"value": 1e3 / ms, "unit": "pairs/s", "ms_per_pair": ms,
+            "what": "reference op sequence (rag_model.py:375-383,18-44) through PyTorch eager CUDA kernels on this GPU, 1 pair per call"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -325,8 +364,10 @@ def run_gpu(args):
            "mean_disp": checksum}
 
     cpu = None
+    torch_gpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_reference(args.workload, budget_s=12.0)
+        torch_gpu = torch_cuda_reference(args.workload, dev)
 
     if rank == 0:
         line = {
@@ -337,7 +378,7 @@ def run_gpu(args):
                        "volume": [b, 2 * c, df, hf, wf], "head_in": [b, 1, df, hf, wf], "maxdisp": md,
                        "l2": "no explicit flush: every step streams %.2f GB (>> 126 MB L2) through HBM" % (path_bytes / 1e9),
                        "sharding": "stereo pairs across ranks, no data-path collective"},
-            "roofline": roofline, "path": path, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "path": path, "cpu_baseline": cpu, "torch_cuda_reference": torch_gpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
