@@ -299,6 +299,20 @@ head_bwd_x3_kernel(const float* __restrict__ cost, const float* __restrict__ gdi
                 dsp[i] = __ldg(dp + o);
                 gneg[i] = ok ? -__ldg(gd + o) * __ldg(sm + img + o) : 0.f;
             }
+        // Ground-truth masks are sparse and spatially coherent (no LiDAR returns in the sky, occlusions): if no
+        // pixel of the warp's 32 blocks carries an upstream gradient, the whole block row contributes zeros --
+        // skip its exp2 work but keep the carries and the stores going.
+        float gabs = 0.f;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) gabs = fmaxf(gabs, fabsf(gneg[i]));
+        if (!__any_sync(0xffffffffu, gabs != 0.f)) {
+            for (int jb = max(jb0, j0); jb < j1; ++jb) {
+                const int jj = jb - j0;
+                if (rb >= r0 && lane >= 1 && lane_on) gout[(size_t)jb * plane + (size_t)rb * Wl + c] = carry[jj * 32];
+                carry[jj * 32] = 0.f;
+            }
+            continue;
+        }
         X3Loader ld;
         ld.init(base, Wl, plane, Dl, jb0, ah.lo0, ah.lo1, aw.lo0, aw.lo1);
         x3_blend9_rel(ld.v, aw.l0, aw.l1, hs0, hs1, m, a);

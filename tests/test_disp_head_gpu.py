@@ -167,6 +167,24 @@ def test_large_magnitude_costs_exercise_the_rescale_path(F_, sigma):
                 assert maxnorm_rel(gc[:, 0], g64) <= 5e-3, f"fwd {v} bwd {vb}"
 
 
+def test_backward_with_spatially_coherent_zero_gradient(F_):
+    """Sparse ground truth: whole regions with no upstream gradient take the warp-level skip path."""
+    g = gen(77)
+    b, dl, hl, wl, md = 2, 64, 24, 70, 192
+    cost = randn((b, 1, dl, hl, wl), g)
+    gd = sparse_grad((b, 3 * hl, 3 * wl), g)
+    gd[:, : 3 * hl // 2] = 0          # "sky": no returns in the top half
+    gd[1, :, 100:] = 0                # and a blank right part in the second image
+    _, g64 = O.disp_head_grad_f64(cost[:, 0].numpy(), gd.numpy(), md)
+    disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True)
+    out1 = F_.disp_head_backward(cost.cuda(), gd.cuda(), disp, stats, md, variant=1)
+    out0 = F_.disp_head_backward(cost.cuda(), gd.cuda(), disp, stats, md, variant=0)
+    assert maxnorm_rel(out1.cpu().numpy()[:, 0], g64) <= TOL_GRAD
+    assert maxnorm_rel(out1.cpu().numpy(), out0.cpu().numpy()) <= TOL_GRAD
+    zero = F_.disp_head_backward(cost.cuda(), torch.zeros_like(gd).cuda(), disp, stats, md, variant=1)
+    assert not zero.any()
+
+
 def test_backward_deterministic_and_vs_cuda_autograd(F_):
     g = gen(21)
     cost = randn((2, 1, 64, 8, 24), g).cuda().requires_grad_(True)
