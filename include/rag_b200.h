@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RAG_B200_ABI_VERSION 3
+#define RAG_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
@@ -75,9 +75,11 @@ RAG_API int rag_disp_head_fwd(const float* cost_lr, float* disp, float* stats,
 
 /* Gradient of the head w.r.t. cost_lr (replaces autograd through interpolate/softmin/mul/sum;
  * PyTorch's CUDA trilinear backward uses atomicAdd -- this is a deterministic gather).
- * gdisp, disp [B,3Hl,3Wl]; stats [B,2,3Hl,3Wl] from the forward; gcost_lr [B,1,Dl,Hl,Wl]. */
+ * gdisp, disp [B,3Hl,3Wl]; stats [B,2,3Hl,3Wl] from the forward; gcost_lr [B,1,Dl,Hl,Wl].
+ * scratch: nullable caller-owned work buffer of the same size as gcost_lr ([B,1,Dl,Hl,Wl], contents
+ * undefined on return); when given (and maxdisp == 3*Dl) the faster two-buffer kernel is used. */
 RAG_API int rag_disp_head_bwd(const float* cost_lr, const float* gdisp, const float* disp,
-                      const float* stats, float* gcost_lr,
+                      const float* stats, float* gcost_lr, float* scratch,
                       int B, int Dl, int Hl, int Wl, int maxdisp, void* stream);
 
 /* DisparityRegression alone (src/models/rag_model.py:18-29): p [B,D,H,W] -> out [B,H,W],
@@ -100,7 +102,7 @@ RAG_API int rag_cost_volume_bwd_v(const float* gcost, float* gx, float* gy,
 RAG_API int rag_disp_head_fwd_v(const float* cost_lr, float* disp, float* stats,
                         int B, int Dl, int Hl, int Wl, int maxdisp, int variant, void* stream);
 RAG_API int rag_disp_head_bwd_v(const float* cost_lr, const float* gdisp, const float* disp,
-                        const float* stats, float* gcost_lr,
+                        const float* stats, float* gcost_lr, float* scratch,
                         int B, int Dl, int Hl, int Wl, int maxdisp, int variant, void* stream);
 
 /* ---- adjacent rows -------------------------------------------------

@@ -9,7 +9,7 @@ int cost_volume_fwd(const float*, const float*, float*, int, int, int, int, int,
 int cost_volume_bwd(const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
 int upsample_trilinear(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int disp_head_fwd(const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
-int disp_head_bwd(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int disp_head_bwd(const float*, const float*, const float*, const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
 int disparity_regression_fwd(const float*, float*, int, int, int, int, cudaStream_t);
 int disparity_regression_bwd(const float*, float*, int, int, int, int, cudaStream_t);
 int loss_metrics_scratch(int, int);
@@ -43,8 +43,8 @@ RAG_API int rag_disp_head_fwd(const float* cost_lr, float* disp, float* stats, i
     return disp_head_fwd(cost_lr, disp, stats, B, Dl, Hl, Wl, maxdisp, kHeadFwdDefault, ST(stream));
 }
 RAG_API int rag_disp_head_bwd(const float* cost_lr, const float* gdisp, const float* disp, const float* stats, float* gcost_lr,
-                      int B, int Dl, int Hl, int Wl, int maxdisp, void* stream) {
-    return disp_head_bwd(cost_lr, gdisp, disp, stats, gcost_lr, B, Dl, Hl, Wl, maxdisp, kHeadBwdDefault, ST(stream));
+                      float* scratch, int B, int Dl, int Hl, int Wl, int maxdisp, void* stream) {
+    return disp_head_bwd(cost_lr, gdisp, disp, stats, gcost_lr, scratch, B, Dl, Hl, Wl, maxdisp, kHeadBwdDefault, ST(stream));
 }
 RAG_API int rag_disparity_regression_fwd(const float* p, float* out, int B, int D, int H, int W, void* stream) {
     return disparity_regression_fwd(p, out, B, D, H, W, ST(stream));
@@ -66,8 +66,8 @@ RAG_API int rag_disp_head_fwd_v(const float* cost_lr, float* disp, float* stats,
     return disp_head_fwd(cost_lr, disp, stats, B, Dl, Hl, Wl, maxdisp, variant, ST(stream));
 }
 RAG_API int rag_disp_head_bwd_v(const float* cost_lr, const float* gdisp, const float* disp, const float* stats, float* gcost_lr,
-                        int B, int Dl, int Hl, int Wl, int maxdisp, int variant, void* stream) {
-    return disp_head_bwd(cost_lr, gdisp, disp, stats, gcost_lr, B, Dl, Hl, Wl, maxdisp, variant, ST(stream));
+                        float* scratch, int B, int Dl, int Hl, int Wl, int maxdisp, int variant, void* stream) {
+    return disp_head_bwd(cost_lr, gdisp, disp, stats, gcost_lr, scratch, B, Dl, Hl, Wl, maxdisp, variant, ST(stream));
 }
 
 RAG_API int rag_loss_metrics_scratch(int H, int W) { return loss_metrics_scratch(H, W); }

@@ -115,6 +115,7 @@ head_fwd_generic_kernel(const float* __restrict__ cost, float* __restrict__ disp
 #include "disp_head_x3tp.cuh"
 #include "disp_head_x3u.cuh"
 #include "disp_head_x3v.cuh"
+#include "disp_head_x3w.cuh"
 namespace rag {
 
 // ---------------------------------------------------------------------------------------------
@@ -295,15 +296,35 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
     return check_launch("disp_head_fwd");
 }
 
-int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, const float* stats, float* gcost,
+int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, const float* stats, float* gcost, float* scratch,
                   int B, int Dl, int Hl, int Wl, int D, int variant, cudaStream_t st) {
     if (!cost || !gdisp || !disp || !stats || !gcost) return fail(RAG_E_NULL, "disp_head_bwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 1) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 2) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
-    if (variant == 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_bwd: variant 1 needs maxdisp == 3*Dl");
-    if (variant == -1) variant = x3 ? 1 : 0;
+    if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_bwd: variant %d needs maxdisp == 3*Dl", variant);
+    if (variant == 2 && !scratch) return fail(RAG_E_NULL, "disp_head_bwd: variant 2 needs a scratch buffer");
+    if (variant == -1) variant = x3 ? (scratch ? 2 : 1) : 0;
+    if (variant == 2) {
+        const int nJ = (Dl + kBwJ - 1) / kBwJ;
+        const int strips = (Wl + 30) / 31;
+        const int n_tasks = (Hl + 1) * nJ;
+        dim3 grid(strips, (n_tasks + 3) / 4, B);
+        const size_t smem = (size_t)3 * (D + 3) * sizeof(float2) + (size_t)4 * kBwWin * sizeof(float);
+        auto kern = head_bwd_x3w_kernel;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "disp_head_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        }
+        kern<<<grid, 128, smem, st>>>(cost, gdisp, disp, stats, gcost, scratch, Dl, Hl, Wl, sd, nJ, n_tasks);
+        if (int e = check_launch("disp_head_bwd(main)")) return e;
+        const size_t n = (size_t)B * Dl * Hl * Wl;
+        const size_t n4 = (aligned(gcost, 16) && aligned(scratch, 16)) ? n / 4 : 0;
+        const size_t work = n4 > 0 ? n4 : 1;
+        head_bwd_combine_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(gcost, scratch, n4, n);
+        return check_launch("disp_head_bwd(combine)");
+    }
     if (variant == 1) {
         constexpr int J = 16;
         const int nJ = (Dl + J - 1) / J;

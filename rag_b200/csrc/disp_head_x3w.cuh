@@ -1,0 +1,267 @@
+// x3 disparity-head backward, second generation (default when a scratch buffer is supplied).
+//
+// Same maths as head_bwd_x3_kernel (disp_head_x3.cuh): deterministic, atomics-free transpose of the
+// upsample applied to -g p_k (k - disp), p_k rebuilt from cost_lr and the forward's stats.  What the
+// profile of the first kernel showed (profiles/r1_train_bwd_kernels_ncu.md): 111 M warp instructions
+// for a batch the forward does in 26 M -- issue bound at 69 %, 1.5 waves of long tasks, 25 % of the work
+// recomputed halo rows.  So here
+//   * a task is ONE block row (no halo rows): its "A" part (cell row rb) goes to gcost, its "B" part
+//     (cell row rb+1) to a scratch buffer of the same shape, and a trivial second kernel adds the two in a
+//     fixed order (still deterministic) -- 5x more, 5x shorter tasks and no recomputation;
+//   * the warp's 2 x 34 x (J+2) low-res window is staged in shared memory with cp.async, so the k-block
+//     loop reads it at compile-time offsets;
+//   * the per-bin arithmetic runs on packed FP32 (FFMA2/FMUL2) with the pixel pairing of the forward
+//     (P0=(p00,p01) P1=(p10,p11) P2=(p20,p21) P3=(p02,p12) S=p22).
+// grid: x = ceil(Wl/31) strips, y = ceil((Hl+1)*nJ / 4), z = B; 128 threads (4 independent warp tasks).
+#pragma once
+#include <cuda_pipeline.h>
+
+#include "disp_head_x3p.cuh"
+
+namespace rag {
+
+constexpr int kBwJ = 16;                 // low-res bins (cells) per task
+constexpr int kBwBins = kBwJ + 2;        // low-res bins a task reads
+constexpr int kBwCols = 34;              // window width: 32 block columns + 1 + pad
+constexpr int kBwWin = kBwBins * 2 * kBwCols;
+
+__global__ void __launch_bounds__(128)
+head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gdisp, const float* __restrict__ disp,
+                    const float* __restrict__ stats, float* __restrict__ gcost, float* __restrict__ scratch,
+                    int Dl, int Hl, int Wl, float scale, int nJ, int n_tasks) {
+    extern __shared__ __align__(16) float x3w_smem[];
+    const int D = 3 * Dl, H = 3 * Hl, W = 3 * Wl;
+    float2* lzb = reinterpret_cast<float2*>(x3w_smem);   // [D+3] (lambda1, lambda1) of bin k
+    float2* dAb = lzb + (D + 3);                          // [D+3] weight of bin k into cell (k-1)/3, broadcast
+    float2* dBb = dAb + (D + 3);                          // [D+3] ... into cell (k-1)/3 + 1
+    float* win_all = reinterpret_cast<float*>(dBb + (D + 3));
+    for (int k = threadIdx.x; k < D + 3; k += 128) {
+        float l0 = 0.f, l1 = 0.f, wa = 0.f, wb = 0.f;
+        if (k < D) {
+            int t0, t1;
+            src_index<true>(scale, k, Dl, t0, t1, l0, l1);
+            const int jb = k == 0 ? 0 : (k - 1) / 3;
+            wa = (t0 == jb ? l0 : 0.f) + (t1 == jb ? l1 : 0.f);
+            wb = (t0 == jb + 1 ? l0 : 0.f) + (t1 == jb + 1 ? l1 : 0.f);
+        }
+        lzb[k] = f2b(l1); dAb[k] = f2b(wa); dBb[k] = f2b(wb);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int task = blockIdx.y * 4 + warp;
+    if (task >= n_tasks) return;
+    float* win = win_all + warp * kBwWin;
+    const int rbi = task / nJ, jc = task - rbi * nJ;
+    const int rb = rbi - 1;                               // block row, -1 .. Hl-1
+    const int j0 = jc * kBwJ, j1 = min(j0 + kBwJ, Dl);
+    const int jb0 = max(j0 - 1, 0);                       // first k-block (its B part feeds cell j0)
+    const int b = blockIdx.z;
+    const int c_first = blockIdx.x * 31 - 1;
+    const int c_raw = c_first + lane;
+    const bool lane_on = c_raw <= Wl - 1;
+    const int c = min(c_raw, Wl - 1);
+
+    X3Axis aw, ah;
+    x3_axis(scale, c, Wl, aw);
+    if (!lane_on) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { aw.wa[i] = 0.f; aw.wb[i] = 0.f; aw.valid[i] = false; }
+    }
+    x3_axis(scale, rb, Hl, ah);
+    const size_t plane = (size_t)Hl * Wl;
+    const size_t img = (size_t)H * W;
+    const float* base = cost + (size_t)b * Dl * plane;
+
+    // ---- stage the window: bins jb0..min(j1,Dl-1), rows (lo0, lo1), columns clamp(c_first + u), u = 0..33 ----
+    {
+        const int nb = min(j1, Dl - 1) - jb0 + 1;
+        const int gc0 = min(max(c_first + lane, 0), Wl - 1);
+        const int gc1 = min(max(c_first + 32 + lane, 0), Wl - 1);     // lanes 0,1 also fetch u = 32, 33
+        for (int q = 0; q < nb; ++q) {
+            const float* s0 = base + (size_t)(jb0 + q) * plane + (size_t)ah.lo0 * Wl;
+            const float* s1 = base + (size_t)(jb0 + q) * plane + (size_t)ah.lo1 * Wl;
+            float* d = win + q * 2 * kBwCols;
+            __pipeline_memcpy_async(d + lane, s0 + gc0, 4);
+            __pipeline_memcpy_async(d + kBwCols + lane, s1 + gc0, 4);
+            if (lane < 2) {
+                __pipeline_memcpy_async(d + 32 + lane, s0 + gc1, 4);
+                __pipeline_memcpy_async(d + kBwCols + 32 + lane, s1 + gc1, 4);
+            }
+        }
+        __pipeline_commit();
+    }
+
+    // ---- per-pixel data (overlaps the window copy) ----
+    const float* gd = gdisp + (size_t)b * img;
+    const float* dp = disp + (size_t)b * img;
+    const float* sm = stats + (size_t)b * 2 * img;
+    float2 mneg[4], gneg[4], dsp[4];
+    float mnegS, gnegS, dspS;
+    float gabs = 0.f;
+    {
+        float m9[9], g9[9], d9[9];
+#pragma unroll
+        for (int ph = 0; ph < 3; ++ph)
+#pragma unroll
+            for (int pw = 0; pw < 3; ++pw) {
+                const int i = ph * 3 + pw;
+                const size_t o = (size_t)ah.idx[ph] * W + aw.idx[pw];   // clamped -> always a real pixel
+                const bool ok = ah.valid[ph] && aw.valid[pw];
+                m9[i] = -__ldg(sm + o);
+                d9[i] = __ldg(dp + o);
+                g9[i] = ok ? -__ldg(gd + o) * __ldg(sm + img + o) : 0.f;
+                gabs = fmaxf(gabs, fabsf(g9[i]));
+            }
+#pragma unroll
+        for (int ph = 0; ph < 3; ++ph) {
+            mneg[ph] = f2(m9[ph * 3], m9[ph * 3 + 1]); gneg[ph] = f2(g9[ph * 3], g9[ph * 3 + 1]); dsp[ph] = f2(d9[ph * 3], d9[ph * 3 + 1]);
+        }
+        mneg[3] = f2(m9[2], m9[5]); gneg[3] = f2(g9[2], g9[5]); dsp[3] = f2(d9[2], d9[5]);
+        mnegS = m9[8]; gnegS = g9[8]; dspS = d9[8];
+    }
+    float* gout = gcost + (size_t)b * Dl * plane;
+    float* sout = scratch + (size_t)b * Dl * plane;
+    const bool store_lane = lane >= 1 && lane_on;
+    const bool has_a = rb >= 0;                // cell row rb exists
+    const bool has_b = rb + 1 <= Hl - 1;       // cell row rb+1 exists
+
+    // sparse ground truth: no upstream gradient anywhere in the warp's 32 blocks -> zeros, no exp2 work
+    if (!__any_sync(0xffffffffu, gabs != 0.f)) {
+        __pipeline_wait_prior(0);
+        if (store_lane)
+            for (int jb = j0; jb < j1; ++jb) {
+                if (has_a) gout[(size_t)jb * plane + (size_t)rb * Wl + c] = 0.f;
+                if (has_b) sout[(size_t)jb * plane + (size_t)(rb + 1) * Wl + c] = 0.f;
+            }
+        return;
+    }
+
+    // packed weights
+    const float2 w0p = f2(aw.l0[0], aw.l0[1]), w1p = f2(aw.l1[0], aw.l1[1]);
+    const float2 w0c = f2b(aw.l0[2]), w1c = f2b(aw.l1[2]);
+    float2 h0b[3], h1b[3], hAb[3], hBb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        h0b[i] = f2b(ah.l0[i] * kX3NegLog2e); h1b[i] = f2b(ah.l1[i] * kX3NegLog2e);
+        hAb[i] = f2b(ah.wa[i]); hBb[i] = f2b(ah.wb[i]);
+    }
+    const float2 h0p = f2(h0b[0].x, h0b[1].x), h1p = f2(h1b[0].x, h1b[1].x);
+
+    // t = blend(bin at window pointer p) + mneg   (relative exponent of the low-res bin for the 4 pairs + scalar)
+    auto blend = [&](const float* p, float2 (&o)[4], float& oS) {
+        const float2 v0 = f2b(p[0]), v1 = f2b(p[1]), v2 = f2b(p[kBwCols]), v3 = f2b(p[kBwCols + 1]);
+        const float2 x0p = fma2(w0p, v0, mul2(w1p, v1)), x1p = fma2(w0p, v2, mul2(w1p, v3));
+        const float2 x0c = fma2(w0c, v0, mul2(w1c, v1)), x1c = fma2(w0c, v2, mul2(w1c, v3));
+#pragma unroll
+        for (int ph = 0; ph < 3; ++ph) o[ph] = fma2(h0b[ph], x0p, fma2(h1b[ph], x1p, mneg[ph]));
+        o[3] = fma2(h0p, x0c, fma2(h1p, x1c, mneg[3]));
+        oS = __fmaf_rn(h0b[2].x, x0c.x, __fmaf_rn(h1b[2].x, x1c.x, mnegS));
+    };
+    // separable transpose of the bilinear blend for one bin part: returns the warp-combined (A row, B row) values
+    auto transpose = [&](const float2 (&g)[4], float gS, float& vA, float& vB) {
+        const float2 uA = fma2(hAb[2], g[2], fma2(hAb[1], g[1], mul2(hAb[0], g[0])));   // cols 0,1
+        const float2 uB = fma2(hBb[2], g[2], fma2(hBb[1], g[1], mul2(hBb[0], g[0])));
+        const float uA2 = __fmaf_rn(ah.wa[2], gS, __fmaf_rn(ah.wa[1], g[3].y, ah.wa[0] * g[3].x));   // col 2
+        const float uB2 = __fmaf_rn(ah.wb[2], gS, __fmaf_rn(ah.wb[1], g[3].y, ah.wb[0] * g[3].x));
+        const float tAA = __fmaf_rn(aw.wa[2], uA2, __fmaf_rn(aw.wa[1], uA.y, aw.wa[0] * uA.x));
+        const float tAB = __fmaf_rn(aw.wb[2], uA2, __fmaf_rn(aw.wb[1], uA.y, aw.wb[0] * uA.x));
+        const float tBA = __fmaf_rn(aw.wa[2], uB2, __fmaf_rn(aw.wa[1], uB.y, aw.wa[0] * uB.x));
+        const float tBB = __fmaf_rn(aw.wb[2], uB2, __fmaf_rn(aw.wb[1], uB.y, aw.wb[0] * uB.x));
+        vA = tAA + __shfl_up_sync(0xffffffffu, tAB, 1);    // cell column c: own block's A part + left block's B part
+        vB = tBA + __shfl_up_sync(0xffffffffu, tBB, 1);
+    };
+
+    __pipeline_wait_prior(0);
+    __syncwarp();
+    float2 a[4], t[4];
+    float aS, tS;
+    // running pointers: window slab of the k-block's upper bin, bin tables, output rows
+    const float* wp = win + lane;
+    const float* wlast = wp + (min(j1, Dl - 1) - jb0) * (2 * kBwCols);
+    blend(wp, a, aS);
+    const float2* lp = lzb + 3 * jb0 + 1;
+    const float2* ap = dAb + 3 * jb0 + 1;
+    const float2* bp = dBb + 3 * jb0 + 1;
+    float* ga = gout + (size_t)j0 * plane + (size_t)max(rb, 0) * Wl + c;
+    float* gb = sout + (size_t)j0 * plane + (size_t)min(rb + 1, Hl - 1) * Wl + c;
+    const bool st_a = store_lane && has_a, st_b = store_lane && has_b;
+    float pA = 0.f, pB = 0.f;        // "B" bin part of the previous k-block (cell jb), split by row part
+    const float2 one = f2b(1.f), two = f2b(2.f), neg1 = f2b(-1.f);
+    float kf = (float)(3 * jb0 + 1);
+
+    // full-res bin 0 (lambda1 == 0) sits exactly on low-res bin 0 and feeds cell 0 only: its share enters
+    // k-block 0's "A" sums as an initial value
+    float2 s0i[4] = {f2b(0.f), f2b(0.f), f2b(0.f), f2b(0.f)};
+    float s0iS = 0.f;
+    if (jb0 == 0 && j0 == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s0i[i] = mul2(dAb[0], mul2(ex2_2(a[i]), fma2(dsp[i], neg1, f2b(0.f))));
+        s0iS = dAb[0].x * (ex2_approx(aS) * (0.f - dspS));
+    }
+
+    for (int jb = jb0; jb < j1; ++jb) {
+        if (wp < wlast) wp += 2 * kBwCols;   // upper bin min(jb+1, Dl-1)
+        blend(wp, t, tS);
+        const float2 l1 = lp[0], l2 = lp[1], l3 = lp[2];
+        const float2 a1 = ap[0], a2 = ap[1], a3 = ap[2];
+        const float2 b1 = bp[0], b2 = bp[1], b3 = bp[2];
+        lp += 3; ap += 3; bp += 3;
+        const float2 kfb = f2b(kf);
+        float2 g0[4], g1[4];
+        float g0S, g1S;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 dlt = fma2(a[i], neg1, t[i]);
+            const float2 dk = fma2(dsp[i], neg1, kfb);           // k1 - disp
+            const float2 u1 = mul2(ex2_2(fma2(l1, dlt, a[i])), dk);
+            const float2 u2 = mul2(ex2_2(fma2(l2, dlt, a[i])), add2(dk, one));
+            const float2 u3 = mul2(ex2_2(fma2(l3, dlt, a[i])), add2(dk, two));
+            const float2 s0 = fma2(a3, u3, fma2(a2, u2, fma2(a1, u1, s0i[i])));
+            const float2 s1 = fma2(b3, u3, fma2(b2, u2, mul2(b1, u1)));
+            g0[i] = mul2(gneg[i], s0); g1[i] = mul2(gneg[i], s1);
+            a[i] = t[i];
+            s0i[i] = f2b(0.f);
+        }
+        {
+            const float dlt = tS - aS;
+            const float dk = kf - dspS;
+            const float u1 = ex2_approx(__fmaf_rn(l1.x, dlt, aS)) * dk;
+            const float u2 = ex2_approx(__fmaf_rn(l2.x, dlt, aS)) * (dk + 1.f);
+            const float u3 = ex2_approx(__fmaf_rn(l3.x, dlt, aS)) * (dk + 2.f);
+            const float s0 = __fmaf_rn(a3.x, u3, __fmaf_rn(a2.x, u2, __fmaf_rn(a1.x, u1, s0iS)));
+            const float s1 = __fmaf_rn(b3.x, u3, __fmaf_rn(b2.x, u2, b1.x * u1));
+            g0S = gnegS * s0; g1S = gnegS * s1;
+            aS = tS;
+            s0iS = 0.f;
+        }
+        kf += 3.f;
+        float v0A, v0B, v1A, v1B;
+        transpose(g0, g0S, v0A, v0B);
+        transpose(g1, g1S, v1A, v1B);
+        if (jb >= j0) {
+            // cell jb: own k-block's A bin part + previous k-block's B bin part
+            if (st_a) *ga = v0A + pA;
+            if (st_b) *gb = v0B + pB;
+            ga += plane; gb += plane;
+        }
+        pA = v1A;
+        pB = v1B;
+    }
+}
+
+// gcost += scratch, with the rows that never receive a "B" part (row 0 gets block row -1's; all rows are
+// written by exactly one task in each buffer) -- plain elementwise add, fixed order => deterministic.
+__global__ void __launch_bounds__(256)
+head_bwd_combine_kernel(float* __restrict__ gcost, const float* __restrict__ scratch, size_t n4, size_t n) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n4) {
+        float4 a = reinterpret_cast<float4*>(gcost)[i];
+        const float4 s = __ldcs(reinterpret_cast<const float4*>(scratch) + i);
+        a.x += s.x; a.y += s.y; a.z += s.z; a.w += s.w;
+        reinterpret_cast<float4*>(gcost)[i] = a;
+    }
+    if (i == 0)
+        for (size_t k = n4 * 4; k < n; ++k) gcost[k] += scratch[k];
+}
+
+}  // namespace rag

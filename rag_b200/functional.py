@@ -132,13 +132,16 @@ def disp_head_backward(cost_lr, gdisp, disp, stats, maxdisp: int, variant: int |
     if gcost.numel() == 0:
         return gcost
     L = _cabi.lib()
+    # work buffer for the two-buffer kernel (same size as the gradient; the caller owns all memory)
+    scratch = torch.empty_like(cost_lr) if (maxdisp == 3 * dl and variant in (None, 2)) else None
+    sp = scratch.data_ptr() if scratch is not None else None
     with torch.cuda.device(cost_lr.device):
         if variant is None:
             rc = L.rag_disp_head_bwd(cost_lr.data_ptr(), gdisp.data_ptr(), disp.data_ptr(), stats.data_ptr(),
-                                     gcost.data_ptr(), b, dl, hl, wl, maxdisp, _stream(cost_lr))
+                                     gcost.data_ptr(), sp, b, dl, hl, wl, maxdisp, _stream(cost_lr))
         else:
             rc = L.rag_disp_head_bwd_v(cost_lr.data_ptr(), gdisp.data_ptr(), disp.data_ptr(), stats.data_ptr(),
-                                       gcost.data_ptr(), b, dl, hl, wl, maxdisp, variant, _stream(cost_lr))
+                                       gcost.data_ptr(), sp, b, dl, hl, wl, maxdisp, variant, _stream(cost_lr))
     _cabi.check(rc, "rag_disp_head_bwd")
     return gcost
 

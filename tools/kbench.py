@@ -111,9 +111,9 @@ def main():
                 print("head_fwd variant", v, "skipped:", e)
     if want("head_bwd"):
         disp, stats = F_.disp_head_forward(cost_lr, md, True)
-        for v in (1, 0):
+        for v in (2, 1, 0):
             try:
-                it = a.iters if v == 1 else 2
+                it = a.iters if v >= 1 else 2
                 med, best = timeit(lambda: F_.disp_head_backward(cost_lr, gd, disp, stats, md, variant=v), it, flush)
                 report("head_bwd", v, med, best, hb_bytes)
             except RuntimeError as e:

@@ -20,7 +20,7 @@ for (b, dl, hl, wl, md) in [(1, 16, 5, 36, 48), (2, 8, 3, 7, 24), (1, 20, 9, 4, 
     x3 = md == 3 * dl
     for vf in [0] + ([1, 2, 3] if x3 else []) + ([4, 5, 6, 7] if x3 and wl % 4 == 0 else []):
         disp, st = F_.disp_head_forward(cl, md, True, variant=vf)
-    for vb in [0] + ([1] if x3 else []):
+    for vb in [0] + ([1, 2] if x3 else []):
         F_.disp_head_backward(cl, gd, disp, st, md, variant=vb)
     F_.upsample_trilinear(cl, md, True)
 p = torch.softmax(torch.randn(1, 24, 6, 10, device=dev, generator=g), 1).contiguous().requires_grad_(True)
