@@ -150,8 +150,8 @@ cv_fwd_persistent_kernel(const float* __restrict__ x, const float* __restrict__ 
 // backward
 // ---------------------------------------------------------------------------------------------
 // Vector path (Wf % 4 == 0).  grid: x over Hf*Wv vectors, y = c, z = b.
-template <int NT>
-__global__ void __launch_bounds__(NT)
+template <int NT, int U, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 cv_bwd_v4_kernel(const float* __restrict__ g, float* __restrict__ gx, float* __restrict__ gy,
                  int C, int Df, int Hf, int Wf) {
     const int Wv = Wf >> 2;
@@ -166,12 +166,11 @@ cv_bwd_v4_kernel(const float* __restrict__ g, float* __restrict__ gx, float* __r
     const float4* gr = gl + (size_t)C * Df * planeV;
 
     float4 ax = make_float4(0.f, 0.f, 0.f, 0.f), ay = ax;
-    constexpr int U = 4;
-    // d runs from the first multiple-of-4 boundary above Df-1 down to 0 so that s = d & 3 = 3-u is
-    // a compile-time constant inside the unrolled body
+    // d runs from the first multiple-of-4 boundary above Df-1 down to 0 in blocks of U (4 or 2) so that
+    // s = d & 3 is a compile-time constant inside the unrolled body
     for (int dq = ((Df + 3) & ~3) - 1; dq >= 0; dq -= U) {
         float4 tl[U], ta[U], tb[U];
-        const int q = dq >> 2;                      // same q for the 4 disparities of this block
+        const int q = dq >> 2;                      // same q for the U disparities of this block
         const bool inA = (wv + q) < Wv;
         const bool inB = (wv + q + 1) < Wv;
 #pragma unroll
@@ -181,7 +180,7 @@ cv_bwd_v4_kernel(const float* __restrict__ g, float* __restrict__ gx, float* __r
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             tl[u] = (dv && (w0 + 3 >= d)) ? ld_stream(gl + (size_t)d * planeV) : z;
             ta[u] = (dv && inA) ? __ldg(gr + (size_t)d * planeV + q) : z;
-            tb[u] = (dv && inB && (3 - u) > 0) ? __ldg(gr + (size_t)d * planeV + q + 1) : z;
+            tb[u] = (dv && inB && ((U == 4 ? 3 - u : (d & 3)) > 0)) ? __ldg(gr + (size_t)d * planeV + q + 1) : z;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -194,7 +193,7 @@ cv_bwd_v4_kernel(const float* __restrict__ g, float* __restrict__ gx, float* __r
                 if (w0 + 3 >= d) ax.w = ax.w + tl[u].w;
                 // gy[w'] += g[d][w'+d], elements s..s+3 of the 8-float window (A,B), s = 3-u
                 if (inA) {
-                    const int s = 3 - u;
+                    const int s = (U == 4) ? 3 - u : (d & 3);
                     const float e0 = s == 0 ? ta[u].x : s == 1 ? ta[u].y : s == 2 ? ta[u].z : ta[u].w;
                     const float e1 = s == 0 ? ta[u].y : s == 1 ? ta[u].z : s == 2 ? ta[u].w : tb[u].x;
                     const float e2 = s == 0 ? ta[u].z : s == 1 ? ta[u].w : s == 2 ? tb[u].x : tb[u].y;
@@ -312,13 +311,17 @@ int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, i
 int cost_volume_bwd(const float* g, float* gx, float* gy, int B, int C, int Df, int Hf, int Wf,
                     int variant, cudaStream_t st) {
     if (int e = check_cv_args(g, gx, gy, B, C, Df, Hf, Wf)) return e;
-    if (variant < 0 || variant > 1) return fail(RAG_E_VARIANT, "cost_volume_bwd: unknown variant %d", variant);
+    if (variant < 0 || variant > 3) return fail(RAG_E_VARIANT, "cost_volume_bwd: unknown variant %d", variant);
     const bool a16 = aligned(g, 16) && aligned(gx, 16) && aligned(gy, 16);
-    if (variant == 0 && Wf % 4 == 0 && a16) {
+    if (variant != 1 && Wf % 4 == 0 && a16) {
         constexpr int NT = 128;
         const int PV = Hf * (Wf / 4);
         dim3 grid((PV + NT - 1) / NT, C, B);
-        cv_bwd_v4_kernel<NT><<<grid, NT, 0, st>>>(g, gx, gy, C, Df, Hf, Wf);
+        // variant 3 = 12-CTA/SM build (2 disparities in flight, 40 registers): measured SLOWER than the 4-deep
+        // build at every size (profiles/r1_kbench_cv_bwd.jsonl), kept for A/B only
+        const bool hi_occ = variant == 3;
+        if (hi_occ) cv_bwd_v4_kernel<NT, 2, 12><<<grid, NT, 0, st>>>(g, gx, gy, C, Df, Hf, Wf);
+        else cv_bwd_v4_kernel<NT, 4, 1><<<grid, NT, 0, st>>>(g, gx, gy, C, Df, Hf, Wf);
     } else {
         constexpr int NT = 256;
         const int PE = Hf * Wf;

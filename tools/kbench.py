@@ -96,7 +96,7 @@ def main():
         del dst
     if want("cv_bwd"):
         gc = torch.randn(b, 2 * c, df, hf, wf, device=dev, generator=g)
-        for v in (0, 1):
+        for v in (0, 1, 2, 3):
             med, best = timeit(lambda: F_.cost_volume_backward(gc, c, variant=v), a.iters, flush)
             report("cv_bwd", v, med, best, vol_bytes)
         med, best = timeit(lambda: gc.sum(), a.iters, flush)
