@@ -250,13 +250,20 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
     if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl", variant);
     const bool tiled_ok = x3 && (Wl % 4 == 0) && aligned(cost, 16);
     if (variant >= 4 && !tiled_ok) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl, Wl %% 4 == 0 and 16-byte aligned cost_lr", variant);
-    if (variant == -1) variant = tiled_ok ? 7 : (x3 ? 1 : 0);
+    if (variant == -1) variant = tiled_ok ? 9 : (x3 ? 1 : 0);
     if (variant >= 7) {
         dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
-        const size_t smem = (size_t)kTStages * kTStageFloats * sizeof(float) + ((size_t)18 * 128 + 4 * Dl) * sizeof(float2);
-        if (variant == 7) head_fwd_x3v_kernel<4><<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
-        if (variant == 8) head_fwd_x3v_kernel<5><<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
-        if (variant == 9) head_fwd_x3v_kernel<6><<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+        const size_t fixed = ((size_t)18 * 128 + 4 * Dl) * sizeof(float2);
+        const size_t smem8 = (size_t)3 * 8 * kTRows * kTCols * sizeof(float) + fixed;     // 3 stages x 8 bins
+        const size_t smem16 = (size_t)2 * 16 * kTRows * kTCols * sizeof(float) + fixed;   // 2 stages x 16 bins
+        if (variant == 7) head_fwd_x3v_kernel<4, 8, 3><<<grid, 128, smem8, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+        if (variant == 8) head_fwd_x3v_kernel<5, 8, 3><<<grid, 128, smem8, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+        if (variant == 9) {
+            auto kern = head_fwd_x3v_kernel<4, 16, 2>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
+            if (e != cudaSuccess) return fail((int)e, "disp_head_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            kern<<<grid, 128, smem16, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+        }
     } else if (variant == 6) {
         dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
         const size_t smem = (size_t)kTStages * kTStageFloats * sizeof(float) + (size_t)Dl * sizeof(float4);

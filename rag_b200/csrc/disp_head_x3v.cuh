@@ -41,15 +41,19 @@ __device__ __forceinline__ void x3v_bins(const float2 (&a)[4], float aS, const f
 }
 
 // grid: x = ceil(Wl/32), y = ceil(Hl/4), z = B; 128 threads.
-// smem: tile[kTStages][kTBins][kTRows][kTCols] | float2 tot[18][128] | float2 lam[Dl][4] ((l1,l1),(l2,l2),(l3,l3),-)
-template <int MINB>
+// BINS low-res bins per pipeline stage, STAGES stages (8x3 or 16x2: the latter halves the per-chunk
+// barriers and total folds and is the default).
+// smem: tile[STAGES][BINS][kTRows][kTCols] | float2 tot[18][128] | float2 lam[Dl][4] ((l1,l1),(l2,l2),(l3,l3),-)
+template <int MINB, int BINS, int STAGES>
 __global__ void __launch_bounds__(128, MINB)
 head_fwd_x3v_kernel(const float* __restrict__ cost, float* __restrict__ disp, float* __restrict__ stats,
                     int Dl, int Hl, int Wl, float scale) {
     extern __shared__ __align__(16) float x3v_smem[];
+    constexpr int kStageFloats = BINS * kTRows * kTCols;
+    constexpr int kSlots = (BINS * kTRows * (kTCols / 4) + 127) / 128;
     const int D = 3 * Dl, W = 3 * Wl;
     float* tile = x3v_smem;
-    float2* tot = reinterpret_cast<float2*>(x3v_smem + kTStages * kTStageFloats);   // [18][128]
+    float2* tot = reinterpret_cast<float2*>(x3v_smem + STAGES * kStageFloats);   // [18][128]
     float2* lam = tot + 18 * 128;                                                    // [Dl][4]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
@@ -58,16 +62,16 @@ head_fwd_x3v_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     const size_t plane = (size_t)Hl * Wl;
     const float* base = cost + (size_t)b * Dl * plane;
     const int Wv = Wl >> 2;
-    const int n_chunks = (Dl + kTBins - 1) / kTBins;
+    const int n_chunks = (Dl + BINS - 1) / BINS;
     const bool patch_l = C0 == 0;
     const bool patch_r = (Wl - T0) <= 36;
     const int pr = Wl - T0;
 
-    // cp.async slots: a chunk is 8 bins x 6 rows x 10 vectors = 480 vectors; thread tid owns vectors
-    // tid, tid+128, tid+256, tid+384 (the last only for tid < 96).  Source offsets inside a bin plane are fixed.
-    int s_off[4], g_off[4], s_bin[4];
+    // cp.async slots: a chunk is BINS bins x 6 rows x 10 vectors; thread tid owns vectors tid, tid+128, ...
+    // Source offsets inside a bin plane are fixed.
+    int s_off[kSlots], g_off[kSlots], s_bin[kSlots];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < kSlots; ++q) {
         const int u = tid + q * 128;
         const int vec = u % 10, row = (u / 10) % kTRows, bin = u / 60;
         s_bin[q] = bin;
@@ -78,11 +82,11 @@ head_fwd_x3v_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     }
     auto issue_chunk = [&](int ch) {
         if (ch < n_chunks) {
-            float* dst = tile + (ch % kTStages) * kTStageFloats;
+            float* dst = tile + (ch % STAGES) * kStageFloats;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (q < 3 || tid < 96) {
-                    const int gj = min(ch * kTBins + s_bin[q], Dl - 1);
+            for (int q = 0; q < kSlots; ++q) {
+                if (tid + q * 128 < BINS * kTRows * (kTCols / 4)) {
+                    const int gj = min(ch * BINS + s_bin[q], Dl - 1);
                     __pipeline_memcpy_async(dst + s_off[q], base + (size_t)gj * plane + g_off[q], 16);
                 }
             }
@@ -90,7 +94,7 @@ head_fwd_x3v_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
         __pipeline_commit();
     };
     issue_chunk(0);
-    issue_chunk(1);
+    if (STAGES > 2) issue_chunk(1);
     for (int j = tid; j < Dl; j += 128) {
         float l[3];
 #pragma unroll
@@ -196,19 +200,19 @@ head_fwd_x3v_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     };
 
     for (int ch = 0; ch < n_chunks; ++ch) {
-        issue_chunk(ch + 2);
-        __pipeline_wait_prior(2);
+        issue_chunk(ch + STAGES - 1);
+        __pipeline_wait_prior(STAGES - 1);
         __syncthreads();
-        float* stw = tile + (ch % kTStages) * kTStageFloats;
+        float* stw = tile + (ch % STAGES) * kStageFloats;
         if (patch_l || patch_r) {
-            if (tid < kTBins * kTRows) {
+            if (tid < BINS * kTRows) {
                 float* rowp = stw + tid * kTCols;
                 if (patch_l) rowp[3] = rowp[4];
                 if (patch_r) rowp[pr] = rowp[pr - 1];
             }
             __syncthreads();
         }
-        const int jbeg = ch * kTBins, jend = min(jbeg + kTBins, Dl);
+        const int jbeg = ch * BINS, jend = min(jbeg + BINS, Dl);
         const float* p = stw + org;
         if (ch == 0) {
             const float2 z4[4] = {f2b(0.f), f2b(0.f), f2b(0.f), f2b(0.f)};

@@ -4,7 +4,7 @@ Tolerances (BASELINE.json north_star): disparity within 1e-4 px absolute; gradie
 relative in max-norm.  The reference's OWN fp32 result deviates from an exact (fp64) evaluation of
 its formula by up to ~9e-5 px at maxdisp=192 / sigma=1 (sequential fp32 sum of p_k*k at magnitude
 ~100), so the comparison is made three ways:
-  (1) against the fp64 evaluation of the reference formula: <= 2e-5 px  (the kernel's own error);
+  (1) against the fp64 evaluation of the reference formula: <= 3e-5 px  (the kernel's own error; mean ~3e-6);
   (2) against the fp32 reference run by PyTorch on CPU and on this GPU: <= 1e-4 px on the golden
       and seeded cases below (deterministic inputs, so this is a hard assert, not a statistic);
   (3) at full size, where a few pixels in 10^5 of the reference itself are > 1e-4 from its own
@@ -48,7 +48,7 @@ def test_golden(F_, path):
         tol = 6e-4     # ... and with sigma (near-one-hot softmax); see test_oracle_golden
     assert np.abs(disp.detach().cpu().numpy() - z["disp"]).max() <= tol
     d64, g64 = O.disp_head_grad_f64(z["cost"][:, 0], z["gdisp"], md)
-    assert np.abs(disp.detach().cpu().numpy() - d64).max() <= (1e-4 if "_s5" in path else 2e-5)
+    assert np.abs(disp.detach().cpu().numpy() - d64).max() <= (1e-4 if "_s5" in path else 3e-5)
     disp.backward(torch.from_numpy(z["gdisp"]).cuda())
     assert maxnorm_rel(cost.grad.cpu().numpy(), z["gcost"]) <= 2 * TOL_GRAD  # vs fp32 reference (own noise 7.5e-6)
     assert maxnorm_rel(cost.grad.cpu().numpy()[:, 0], g64) <= TOL_GRAD       # vs exact
@@ -94,7 +94,7 @@ def test_forward_parity(F_, case):
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=v)
         out = disp.cpu().numpy()
         own = np.abs(out - d64).max()
-        assert own <= (2e-5 * md / 192 if sigma <= 1 else 1e-4), f"variant {v}: own error {own}"
+        assert own <= (3e-5 * md / 192 if sigma <= 1 else 1e-4), f"variant {v}: own error {own}"
         # vs the fp32 reference: within 1e-4 px, allowing at each pixel for the reference's OWN deviation
         # from the exact value of its formula (its fp32 sum of p_k*k is good to ~1e-4 at maxdisp 192 and
         # worse at maxdisp 288 / sigma 5); and the bulk of the pixels within 1e-4 outright
@@ -232,7 +232,8 @@ def test_full_size_properties(F_):
     ref = O.disp_head_ref(cost[:1], md)[0].cpu().numpy().astype(np.float64)
     d64, _ = O.disp_head_f64(cost[:1, 0].cpu().numpy(), md)
     out = disp[0].cpu().numpy().astype(np.float64)
-    assert np.abs(out - d64[0]).max() <= 2e-5
+    assert np.abs(out - d64[0]).max() <= 3e-5
+    assert np.abs(out - d64[0]).mean() <= 5e-6
     err = np.abs(out - ref)
     assert (err <= TOL_DISP).mean() >= 0.999
     assert np.all(err <= TOL_DISP + np.abs(ref - d64[0]))
