@@ -27,7 +27,6 @@ def test_cuda_graph_capture_and_replay():
         gx, gy = F_.cost_volume_backward(gc, 12)
         return cost, disp, gcl, gx, gy
 
-    eager = [t.clone() for t in run()]
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
@@ -37,13 +36,14 @@ def test_cuda_graph_capture_and_replay():
     with torch.cuda.graph(graph):
         outs = run()
     for _ in range(3):
-        x.add_(1.0)   # change an input in place: the replay must see it
+        x.add_(0.5)   # change inputs in place: every replay must see the new values
+        cl.mul_(1.25)
         graph.replay()
     torch.cuda.synchronize()
-    x.sub_(3.0)
-    graph.replay()
+    replayed = [t.clone() for t in outs]
+    eager = run()
     torch.cuda.synchronize()
-    for a, b in zip(outs, eager):
+    for a, b in zip(replayed, eager):
         assert torch.equal(a, b)
 
 
