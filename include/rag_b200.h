@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RAG_B200_ABI_VERSION 4
+#define RAG_B200_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
@@ -119,6 +119,18 @@ RAG_API int rag_loss_metrics_sums(const float* est, const float* gt, double* sum
  * where mask true, else 0.  n_mask_total read from device `sums` rows (sum over b of sums[b][0]). */
 RAG_API int rag_smooth_l1_bwd(const float* est, const float* gt, const double* sums, const float* gloss,
                       float* gest, int B, int H, int W, float maxdisp, void* stream);
+
+/* Fused cost volume + first Matching-Net convolution (inference): the volume is never materialised.
+ * Replaces src/models/rag_model.py:375-383 followed by `self.stem3d0[i](cost)` (rag_model.py:341), i.e.
+ * ConvBR_3d(2C -> O, 3x3x3, stride 1, pad 1) of src/automl/operations_3d.py:31-47:
+ *   out = relu?( scale[o] * conv3d(cost_volume(x, y), w)[o] + shift[o] )
+ * x,y [B,C,Hf,Wf]; w [O,2C,3,3,3] (Conv3d.weight, bias-free); scale/shift [O] = eval-mode BatchNorm folded
+ * (gamma/sqrt(var+eps), beta - mean*scale), NULL = identity; out [B,O,Df,Hf,Wf].  fp32 accumulation
+ * (cuDNN's default for this layer is TF32).  Forward only: training keeps the materialised path. */
+RAG_API int rag_cv_stem_fwd(const float* x, const float* y, const float* w, const float* scale, const float* shift,
+                    int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, void* stream);
+RAG_API int rag_cv_stem_fwd_v(const float* x, const float* y, const float* w, const float* scale, const float* shift,
+                      int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, int variant, void* stream);
 
 /* Eval-time input staging: uint8 HWC image -> ImageNet-normalised fp32 CHW, zero-padded on the
  * top and right.  Replaces src/dataloaders/data_io.py:6-13 + stereo_dataset.py:88-102.

@@ -16,6 +16,7 @@ int loss_metrics_scratch(int, int);
 int loss_metrics_sums(const float*, const float*, double*, double*, int, int, int, float, cudaStream_t);
 int smooth_l1_bwd(const float*, const float*, const double*, const float*, float*, int, int, int, float, cudaStream_t);
 int normalize_pad(const uint8_t*, float*, int, int, int, int, int, cudaStream_t);
+int cv_stem_fwd(const float*, const float*, const float*, const float*, const float*, int, float*, int, int, int, int, int, int, int, cudaStream_t);
 }  // namespace rag
 
 using namespace rag;
@@ -77,6 +78,14 @@ RAG_API int rag_loss_metrics_sums(const float* est, const float* gt, double* sum
 RAG_API int rag_smooth_l1_bwd(const float* est, const float* gt, const double* sums, const float* gloss, float* gest,
                       int B, int H, int W, float maxdisp, void* stream) {
     return smooth_l1_bwd(est, gt, sums, gloss, gest, B, H, W, maxdisp, ST(stream));
+}
+RAG_API int rag_cv_stem_fwd(const float* x, const float* y, const float* w, const float* scale, const float* shift,
+                    int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, void* stream) {
+    return cv_stem_fwd(x, y, w, scale, shift, relu, out, B, C, O, Df, Hf, Wf, -1, ST(stream));
+}
+RAG_API int rag_cv_stem_fwd_v(const float* x, const float* y, const float* w, const float* scale, const float* shift,
+                      int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, int variant, void* stream) {
+    return cv_stem_fwd(x, y, w, scale, shift, relu, out, B, C, O, Df, Hf, Wf, variant, ST(stream));
 }
 RAG_API int rag_normalize_pad(const uint8_t* img, float* out, int B, int H, int W, int top_pad, int right_pad, void* stream) {
     return normalize_pad(img, out, B, H, W, top_pad, right_pad, ST(stream));

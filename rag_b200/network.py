@@ -21,7 +21,18 @@ from __future__ import annotations
 import torch
 
 from .functional import cost_volume, disp_head
+from .fused_stem import VirtualCostVolume, stem_forward
 from .modules import CostVolume, Disp, DisparityRegression  # noqa: F401  (re-exported)
+
+# set by install(..., fuse_stem=True): the patched forwards then hand the Matching Net a VirtualCostVolume
+# and its first layer (ConvBR_3d, made fusion-aware) runs cost volume + conv + BN + ReLU as one kernel
+_FUSE_STEM = False
+
+
+def _volume(x, y, maxdisp):
+    if _FUSE_STEM:
+        return VirtualCostVolume(x, y, maxdisp)
+    return cost_volume(x, y, maxdisp)
 
 
 def _head(self, cost):
@@ -36,7 +47,7 @@ def network_forward(self, left, right, t, task_arch=None, path=None):
     """Replacement for Network.forward (rag_model.py:369-387)."""
     x = self.feature(left, task_arch, path)
     y = self.feature(right, task_arch, path)
-    cost = cost_volume(x, y, self.maxdisp)          # rag_model.py:375-383
+    cost = _volume(x, y, self.maxdisp)              # rag_model.py:375-383
     cost = self.matching(cost, task_arch, path)
     return _head(self, cost)                        # rag_model.py:386
 
@@ -45,7 +56,7 @@ def network_search_forward(self, left, right, t, selected_ops):
     """Replacement for Network.search_forward (rag_model.py:688-706)."""
     x = self.search_feature(left, selected_ops)
     y = self.search_feature(right, selected_ops)
-    cost = cost_volume(x, y, self.maxdisp)          # rag_model.py:694-702
+    cost = _volume(x, y, self.maxdisp)              # rag_model.py:694-702
     cost = self.search_matching(cost, selected_ops, t)
     return _head(self, cost)
 
@@ -54,17 +65,31 @@ def basic_network_forward(self, left, right, fea_ops, mat_ops):
     """Replacement for BasicNetwork.forward (mdenas_basicmodel.py:76-97)."""
     x = self.feature(left, fea_ops)
     y = self.feature(right, fea_ops)
-    cost = cost_volume(x, y, self.maxdisp)          # mdenas_basicmodel.py:83-91
+    cost = cost_volume(x, y, self.maxdisp)          # mdenas_basicmodel.py:83-91 (supernet: always materialised)
     cost = self.matching(cost, mat_ops)
     return _head(self, cost)
 
 
-def install(rag_model=None, mdenas_basicmodel=None) -> dict:
+def install(rag_model=None, mdenas_basicmodel=None, operations_3d=None, fuse_stem: bool = False) -> dict:
     """Bind the B200 hot path onto the reference's modules (pass the imported module objects
     ``models.rag_model`` and/or ``automl.mdenas_basicmodel``).  Returns what was patched.
     New networks constructed afterwards get ``rag_b200.Disp``; existing instances keep working
-    because the patched ``forward`` methods bypass ``self.disp`` when it is the reference's."""
+    because the patched ``forward`` methods bypass ``self.disp`` when it is the reference's.
+
+    ``fuse_stem=True`` (needs ``operations_3d`` = the imported ``automl.operations_3d``) additionally makes
+    ``ConvBR_3d.forward`` fusion-aware and lets the patched forwards skip materialising the volume: the
+    first Matching-Net layer (rag_model.py:341) then runs as csrc/cv_stem.cu in inference; training and
+    any non-matching layer geometry fall back to the materialised volume automatically.  NOTE: only the
+    growable ``Network`` starts its Matching Net with a ConvBR_3d on the raw volume in all configurations;
+    the search supernet (``BasicNetwork``/``AutoMatching``) keeps the materialised volume."""
+    global _FUSE_STEM
     done = {}
+    if fuse_stem:
+        if operations_3d is None:
+            raise ValueError("fuse_stem=True needs operations_3d (the reference's automl.operations_3d module)")
+        operations_3d.ConvBR_3d.forward = stem_forward
+        _FUSE_STEM = True
+        done["operations_3d"] = ["ConvBR_3d.forward"]
     if rag_model is not None:
         rag_model.Network.forward = network_forward
         rag_model.Network.search_forward = network_search_forward

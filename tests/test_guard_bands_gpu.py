@@ -89,6 +89,20 @@ def test_head_guards(L, shape):
     assert intact(bu, b * md * 9 * hl * wl)
 
 
+def test_fused_stem_guards(L):
+    g = gen(4)
+    for (b, c, hf, wf, df, o) in [(1, 12, 4, 40, 16, 12), (2, 12, 3, 38, 10, 5), (1, 12, 3, 16, 2, 12), (1, 5, 3, 20, 8, 4)]:
+        x, y = randn((b, c, hf, wf), g).cuda(), randn((b, c, hf, wf), g).cuda()
+        w = randn((o, 2 * c, 3, 3, 3), g).cuda()
+        n = b * o * df * hf * wf
+        for v in (0,) + ((1,) if (c == 12 and df >= 3) else ()):
+            buf, out = window(n)
+            assert L.rag_cv_stem_fwd_v(x.data_ptr(), y.data_ptr(), w.data_ptr(), None, None, 0, out.data_ptr(), b, c, o, df, hf, wf, v, st()) == 0
+            torch.cuda.synchronize()
+            assert intact(buf, n), f"cv_stem variant {v} wrote out of bounds"
+            assert not (out == CANARY).any(), f"cv_stem variant {v} left outputs unwritten"
+
+
 def test_misc_guards(L):
     g = gen(3)
     b, h, w = 3, 37, 53

@@ -102,6 +102,22 @@ def main():
         med, best = timeit(lambda: gc.sum(), a.iters, flush)
         report("torch_sum_same_bytes(r)", -1, med, best, vol_bytes)
         del gc
+    if want("cv_stem"):
+        from rag_b200.fused_stem import cv_stem_forward
+        wgt = torch.randn(12, 24, 3, 3, 3, device=dev, generator=g) * 0.05
+        sc = torch.rand(12, device=dev, generator=g) + 0.5
+        sh = torch.randn(12, device=dev, generator=g)
+        out_bytes = 4 * (12 * df * hf * wf + 2 * c * hf * wf) * b
+        med, best = timeit(lambda: cv_stem_forward(x, y, wgt, sc, sh, True, md), a.iters, flush)
+        report("cv_stem_fused(conv+bn+relu)", 1, med, best, out_bytes)
+        conv = torch.nn.Conv3d(24, 12, 3, padding=1, bias=False).to(dev)
+        bn = torch.nn.BatchNorm3d(12).to(dev).eval()
+        with torch.no_grad():
+            for tf32 in (True, False):
+                torch.backends.cudnn.allow_tf32 = tf32
+                med, best = timeit(lambda: torch.relu_(bn(conv(F_.cost_volume_forward(x, y, df)))), 3, flush)
+                report("cost_volume+cudnn_conv3d_bn_relu(tf32=%s)" % tf32, -1, med, best, out_bytes)
+            torch.backends.cudnn.allow_tf32 = True
     if want("head_fwd"):
         for v in (9, 8, 7):
             try:
