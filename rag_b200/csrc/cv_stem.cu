@@ -22,11 +22,14 @@
 // the LF/RF rows (RF as 4 pre-shifted copies so the shifted read is an aligned LDS.128) and the border
 // tables, phase 3 streams the Df x Wf output rows with 128-bit stores, optionally applying the folded
 // eval-mode BatchNorm (scale, shift) and ReLU.  Roofline: HBM store stream of the [B,O,Df,Hf,Wf] output.
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 
 namespace rag {
 
 constexpr int kStemPad = 4;   // zero columns on each side of every shared-memory row
+constexpr int kStemStages = 3; // depth of the per-thread cp.async ring of the packed kernel
 
 // exact tap-by-tap value (conv only) for output (d, w); maps[m] rows are padded by kStemPad zeros
 __device__ __forceinline__ float stem_taps(const float* maps, int Wp, int Df, int Wf, int d, int w) {
@@ -73,27 +76,37 @@ cv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, con
         }
         wsm[i] = v;
     }
-    for (int i = tid; i < 33 * Wp; i += NT) maps[i] = 0.f;   // maps, LF, RF incl. their zero pads
+    // zero pads of all 33 rows (maps, LF, RF) and the RF rows themselves (their shifted copies leave the first s slots untouched)
+    for (int i = tid; i < 33 * 2 * kStemPad; i += NT) {
+        const int row = i / (2 * kStemPad), k = i - row * (2 * kStemPad);
+        maps[row * Wp + (k < kStemPad ? k : Wf + k)] = 0.f;
+    }
     __syncthreads();
 
-    // ---- phase 1: the 18 row maps, one column per thread ----
+    // ---- phase 1: the 18 row maps, one column per thread; x/y rows walked with pointer bumps ----
     const size_t img = (size_t)Hf * Wf;
-    const float* xb = x + (size_t)b * C * img;
-    const float* yb = y + (size_t)b * C * img;
+    const bool up = h > 0, dn = h < Hf - 1;
     for (int col = tid; col < Wf; col += NT) {
         float a[9], r[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) { a[i] = 0.f; r[i] = 0.f; }
+        const float* px = x + (size_t)b * C * img + (size_t)h * Wf + col;
+        const float* py = y + (size_t)b * C * img + (size_t)h * Wf + col;
+        const float4* wl = reinterpret_cast<const float4*>(wsm);
+        const float4* wr = reinterpret_cast<const float4*>(wsm + C * 36);
+#pragma unroll 2
         for (int c = 0; c < C; ++c) {
+            // issue the (up to) six loads of this channel first, then the 54 FMAs
+            const float x1 = __ldg(px), y1 = __ldg(py);
+            const float x0 = up ? __ldg(px - Wf) : 0.f, y0 = up ? __ldg(py - Wf) : 0.f;
+            const float x2 = dn ? __ldg(px + Wf) : 0.f, y2 = dn ? __ldg(py + Wf) : 0.f;
+            px += img; py += img;
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
-                const int hh = h + kh - 1;
-                if (hh < 0 || hh >= Hf) continue;
-                const float xv = __ldg(xb + (size_t)c * img + (size_t)hh * Wf + col);
-                const float yv = __ldg(yb + (size_t)c * img + (size_t)hh * Wf + col);
-                const float4* wl = reinterpret_cast<const float4*>(wsm + (c * 3 + kh) * 12);
-                const float4* wr = reinterpret_cast<const float4*>(wsm + ((C + c) * 3 + kh) * 12);
-                const float4 l0 = wl[0], l1 = wl[1], l2 = wl[2], r0 = wr[0], r1 = wr[1], r2 = wr[2];
+                const float xv = kh == 0 ? x0 : kh == 1 ? x1 : x2;
+                const float yv = kh == 0 ? y0 : kh == 1 ? y1 : y2;
+                const float4 l0 = wl[kh * 3 + 0], l1 = wl[kh * 3 + 1], l2 = wl[kh * 3 + 2];
+                const float4 r0 = wr[kh * 3 + 0], r1 = wr[kh * 3 + 1], r2 = wr[kh * 3 + 2];
                 a[0] = __fmaf_rn(l0.x, xv, a[0]); a[1] = __fmaf_rn(l0.y, xv, a[1]); a[2] = __fmaf_rn(l0.z, xv, a[2]);
                 a[3] = __fmaf_rn(l0.w, xv, a[3]); a[4] = __fmaf_rn(l1.x, xv, a[4]); a[5] = __fmaf_rn(l1.y, xv, a[5]);
                 a[6] = __fmaf_rn(l1.z, xv, a[6]); a[7] = __fmaf_rn(l1.w, xv, a[7]); a[8] = __fmaf_rn(l2.x, xv, a[8]);
@@ -101,6 +114,7 @@ cv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, con
                 r[3] = __fmaf_rn(r0.w, yv, r[3]); r[4] = __fmaf_rn(r1.x, yv, r[4]); r[5] = __fmaf_rn(r1.y, yv, r[5]);
                 r[6] = __fmaf_rn(r1.z, yv, r[6]); r[7] = __fmaf_rn(r1.w, yv, r[7]); r[8] = __fmaf_rn(r2.x, yv, r[8]);
             }
+            wl += 9; wr += 9;
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
@@ -111,20 +125,26 @@ cv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, con
     __syncthreads();
 
     // ---- phase 2: collapsed rows per disparity class (0: d=0 -> kd in {1,2}; 1: interior; 2: d=Df-1 -> kd in {0,1}) ----
-    for (int i = tid; i < 3 * Wf; i += NT) {
-        const int cls = i / Wf, col = i - cls * Wf;
-        const int kd0 = cls == 0 ? 1 : 0, kd1 = cls == 2 ? 1 : 2;
-        float lf = 0.f, rf = 0.f;
-        for (int kd = kd0; kd <= kd1; ++kd)
+    for (int col = tid; col < Wf; col += NT) {
+        float S[3], T[3];
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                lf += maps[(kd * 3 + kw) * Wp + kStemPad + col + kw - 1];
-                rf += maps[(9 + kd * 3 + kw) * Wp + kStemPad + col + kw - kd];
+        for (int kd = 0; kd < 3; ++kd) {
+            const float* ar = maps + (kd * 3) * Wp + kStemPad + col;
+            const float* rr = maps + (9 + kd * 3) * Wp + kStemPad + col - kd;
+            S[kd] = ar[-1] + ar[Wp] + ar[2 * Wp + 1];
+            T[kd] = rr[0] + rr[Wp + 1] + rr[2 * Wp + 2];
+        }
+        const float lf[3] = {S[1] + S[2], S[0] + S[1] + S[2], S[0] + S[1]};
+        const float rf[3] = {T[1] + T[2], T[0] + T[1] + T[2], T[0] + T[1]};
+#pragma unroll
+        for (int cls = 0; cls < 3; ++cls) {
+            LF[cls * Wp + kStemPad + col] = lf[cls];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {           // copy s holds RF shifted right by s: copy_s[i] = RF[i - s]
+                if (col + s < Wf) RF[(cls * 4 + s) * Wp + kStemPad + col + s] = rf[cls];
+                if (col < s) RF[(cls * 4 + s) * Wp + kStemPad + col] = 0.f;
             }
-        LF[cls * Wp + kStemPad + col] = lf;
-#pragma unroll
-        for (int s = 0; s < 4; ++s)             // copy s holds RF shifted right by s: copy_s[i] = RF[i - s]
-            if (col + s < Wf) RF[(cls * 4 + s) * Wp + kStemPad + col + s] = rf;
+        }
     }
     // border tables, evaluated tap by tap: the diagonal band w - d in [-2, 1] and the last column
     for (int i = tid; i < 5 * Df; i += NT) {
@@ -145,16 +165,22 @@ cv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, con
     const size_t dstride = (size_t)Hf * Wf;
     if ((Wf & 3) == 0) {
         const int Wv = Wf >> 2;
-        for (int i = tid; i < Df * Wv; i += NT) {
-            const int d = i / Wv, w0 = (i - d * Wv) << 2;
+        // items (d, wv) in row-major order dealt round-robin to threads; (d, wv) advanced without divisions
+        const int stepd = NT / Wv, stepw = NT - stepd * Wv;
+        int d = tid / Wv, wv = tid - d * Wv;
+        float* op = ob + (size_t)d * dstride + 4 * wv;
+        const size_t opstep = (size_t)stepd * dstride + 4 * stepw;
+        while (d < Df) {
+            const int w0 = wv << 2;
             const int cls = d == 0 ? 0 : (d == Df - 1 ? 2 : 1);
             const int u0 = w0 - d;
             float4 v;
             if (u0 >= 2 && w0 + 3 <= Wf - 2) {           // all four interior: aligned reads of LF and of RF copy (d & 3)
-                const int q = d >> 2, s = d & 3;
                 const float4 lf = *reinterpret_cast<const float4*>(LF + cls * Wp + kStemPad + w0);
-                const float4 rf = *reinterpret_cast<const float4*>(RF + (cls * 4 + s) * Wp + kStemPad + w0 - 4 * q);
+                const float4 rf = *reinterpret_cast<const float4*>(RF + (cls * 4 + (d & 3)) * Wp + kStemPad + w0 - (d & ~3));
                 v = make_float4(lf.x + rf.x, lf.y + rf.y, lf.z + rf.z, lf.w + rf.w);
+            } else if (u0 + 3 <= -3) {                   // fully masked: every tap sees zeros
+                v = make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
                 float e[4];
 #pragma unroll
@@ -168,7 +194,9 @@ cv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, con
                 v = make_float4(e[0], e[1], e[2], e[3]);
             }
             v = make_float4(finish(v.x), finish(v.y), finish(v.z), finish(v.w));
-            st_stream(reinterpret_cast<float4*>(ob + (size_t)d * dstride + w0), v);
+            st_stream(reinterpret_cast<float4*>(op), v);
+            d += stepd; wv += stepw; op += opstep;
+            if (wv >= Wv) { wv -= Wv; ++d; op += dstride - Wf; }
         }
     } else {
         for (int i = tid; i < Df * Wf; i += NT) {
@@ -181,6 +209,192 @@ cv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, con
             else v = LF[cls * Wp + kStemPad + col] + RF[cls * 4 * Wp + kStemPad + u];
             st_stream(ob + (size_t)d * dstride + col, finish(v));
         }
+    }
+}
+
+// Second generation of the fused kernel (default): the first one was issue bound (profiles/: 777 M warp
+// instructions per launch, 24 thread instructions per output float against a store-stream budget of ~5.5).
+//   * phase 1 on packed FP32: a thread owns a PAIR of adjacent columns of one side (left: x -> A maps,
+//     right: y -> R maps); data pairs come from one LDG.64, the nine tap weights are kept in shared
+//     memory pre-duplicated as (w,w) so each LDS.128 feeds two FFMA2 -- 9 FFMA2 per (channel, row) for two
+//     columns instead of 18 FFMA per column;
+//   * phase 3 with the block size a multiple of Wf/4: a thread keeps its column group for every
+//     disparity row, so the LF vector lives in registers, the RF read is one LDS.128 through a pointer
+//     that moves 16 bytes per step, and no index arithmetic is left in the loop.
+// Needs Wf % 4 == 0.  Same shared-memory layout otherwise.
+template <int C>
+__global__ void __launch_bounds__(512, 2)
+cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w,
+                    const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                    float* __restrict__ out, int O, int Df, int Hf, int Wf) {
+    extern __shared__ __align__(16) float stem_smem[];
+    const int Wp = Wf + 2 * kStemPad;
+    float* wsm = stem_smem;                       // [side][c][kh][20]: 9 (kd,kw) weights duplicated (w,w) + pad
+    float* maps = wsm + 2 * C * 3 * 20;
+    float* LF = maps + 18 * Wp;
+    float* RF = LF + 3 * Wp;
+    float* band = RF + 12 * Wp;
+    float* lastcol = band + 4 * Df;
+    // per-thread cp.async ring for phase 1: [kStemStages][3 rows][NT] float2, 8-byte aligned
+    float2* ring = reinterpret_cast<float2*>(lastcol + ((Df + 3) & ~3));
+    const int h = blockIdx.x, o = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const size_t img = (size_t)Hf * Wf;
+    const bool up = h > 0, dn = h < Hf - 1;
+    const int NP = Wf >> 1;
+
+    // phase-1 prefetch: every thread fetches ITS OWN column pair of the three input rows of channel c into its
+    // private ring slots, so no block barrier is needed between producer and consumer (same thread)
+    auto fetch_c = [&](const float* src, int c, int stage) {
+        float2* slot = ring + (size_t)stage * 3 * NT + tid;
+        const float* p = src + (size_t)c * img;
+        __pipeline_memcpy_async(slot + NT, p, 8);
+        if (up) __pipeline_memcpy_async(slot, p - Wf, 8);
+        if (dn) __pipeline_memcpy_async(slot + 2 * NT, p + Wf, 8);
+    };
+    {   // first item of this thread: start its loads before the (latency-bound) weight regrouping below
+        const int item = tid;
+        if (item < 2 * NP) {
+            const int side = item >= NP ? 1 : 0;
+            const float* src = (side ? y : x) + (size_t)b * C * img + (size_t)h * Wf + ((item - side * NP) << 1);
+#pragma unroll
+            for (int c = 0; c < kStemStages - 1; ++c) { fetch_c(src, c, c); __pipeline_commit(); }
+        }
+    }
+
+    for (int i = tid; i < 2 * C * 3 * 20; i += NT) {
+        const int t2 = i % 20, kh = (i / 20) % 3, c = (i / 60) % C, side = i / (60 * C);
+        const int t = t2 >> 1;
+        float v = 0.f;
+        if (t < 9) {
+            const int kd = t / 3, kw = t % 3;
+            v = __ldg(w + ((((size_t)o * 2 * C + side * C + c) * 3 + kd) * 3 + kh) * 3 + kw);
+        }
+        wsm[i] = v;
+    }
+    for (int i = tid; i < 33 * 2 * kStemPad; i += NT) {
+        const int row = i / (2 * kStemPad), k = i - row * (2 * kStemPad);
+        maps[row * Wp + (k < kStemPad ? k : Wf + k)] = 0.f;
+    }
+    __syncthreads();
+
+    // ---- phase 1: items = (side, column pair), input rows through the per-thread cp.async ring ----
+    for (int item = tid; item < 2 * NP; item += NT) {
+        const int side = item >= NP ? 1 : 0;
+        const int col = (item - side * NP) << 1;
+        const float* src = (side ? y : x) + (size_t)b * C * img + (size_t)h * Wf + col;
+        if (item != tid) {                         // later passes (NT < Wf): restart the pipeline for this item
+#pragma unroll
+            for (int c = 0; c < kStemStages - 1; ++c) { fetch_c(src, c, c); __pipeline_commit(); }
+        }
+        const float4* wp = reinterpret_cast<const float4*>(wsm + side * C * 60);
+        float2 acc[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            if (c + kStemStages - 1 < C) fetch_c(src, c + kStemStages - 1, (c + kStemStages - 1) % kStemStages);
+            __pipeline_commit();
+            __pipeline_wait_prior(kStemStages - 1);        // channel c has landed
+            const float2* slot = ring + (size_t)(c % kStemStages) * 3 * NT + tid;
+            const float2 z2 = make_float2(0.f, 0.f);
+            const float2 v1 = slot[NT];
+            const float2 v0 = up ? slot[0] : z2;
+            const float2 v2 = dn ? slot[2 * NT] : z2;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const float2 v = kh == 0 ? v0 : kh == 1 ? v1 : v2;
+                const float4 q0 = wp[kh * 5 + 0], q1 = wp[kh * 5 + 1], q2 = wp[kh * 5 + 2], q3 = wp[kh * 5 + 3], q4 = wp[kh * 5 + 4];
+                acc[0] = __ffma2_rn(make_float2(q0.x, q0.y), v, acc[0]); acc[1] = __ffma2_rn(make_float2(q0.z, q0.w), v, acc[1]);
+                acc[2] = __ffma2_rn(make_float2(q1.x, q1.y), v, acc[2]); acc[3] = __ffma2_rn(make_float2(q1.z, q1.w), v, acc[3]);
+                acc[4] = __ffma2_rn(make_float2(q2.x, q2.y), v, acc[4]); acc[5] = __ffma2_rn(make_float2(q2.z, q2.w), v, acc[5]);
+                acc[6] = __ffma2_rn(make_float2(q3.x, q3.y), v, acc[6]); acc[7] = __ffma2_rn(make_float2(q3.z, q3.w), v, acc[7]);
+                acc[8] = __ffma2_rn(make_float2(q4.x, q4.y), v, acc[8]);
+            }
+            wp += 15;
+        }
+        float* dst = maps + (side * 9) * Wp + kStemPad + col;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) *reinterpret_cast<float2*>(dst + i * Wp) = acc[i];
+    }
+    __syncthreads();
+
+    // ---- phase 2 (as in the first kernel) ----
+    for (int col = tid; col < Wf; col += NT) {
+        float S[3], T[3];
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd) {
+            const float* ar = maps + (kd * 3) * Wp + kStemPad + col;
+            const float* rr = maps + (9 + kd * 3) * Wp + kStemPad + col - kd;
+            S[kd] = ar[-1] + ar[Wp] + ar[2 * Wp + 1];
+            T[kd] = rr[0] + rr[Wp + 1] + rr[2 * Wp + 2];
+        }
+        const float lf[3] = {S[1] + S[2], S[0] + S[1] + S[2], S[0] + S[1]};
+        const float rf[3] = {T[1] + T[2], T[0] + T[1] + T[2], T[0] + T[1]};
+#pragma unroll
+        for (int cls = 0; cls < 3; ++cls) {
+            LF[cls * Wp + kStemPad + col] = lf[cls];
+#pragma unroll
+            for (int s2 = 0; s2 < 4; ++s2) {
+                if (col + s2 < Wf) RF[(cls * 4 + s2) * Wp + kStemPad + col + s2] = rf[cls];
+                if (col < s2) RF[(cls * 4 + s2) * Wp + kStemPad + col] = 0.f;
+            }
+        }
+    }
+    for (int i = tid; i < 5 * Df; i += NT) {
+        const int d = i / 5, j = i - d * 5;
+        const int col = j < 4 ? d - 2 + j : Wf - 1;
+        const float v = (col >= 0 && col < Wf) ? stem_taps(maps, Wp, Df, Wf, d, col) : 0.f;
+        if (j < 4) band[d * 4 + j] = v; else lastcol[d] = v;
+    }
+    __syncthreads();
+
+    // ---- phase 3: thread keeps its 4-column group; rows d = d0, d0 + rows_per_pass, ... ----
+    // Main pass is branch-free: every element is LF + RF (masked to 0 where w - d <= -3, i.e. all taps masked);
+    // the 5 border elements per disparity row (diagonal band, last column) are patched afterwards from the
+    // tap-by-tap tables.
+    const float sc = scale ? __ldg(scale + o) : 1.f, sh = shift ? __ldg(shift + o) : 0.f;
+    auto finish = [&](float v) {
+        v = __fmaf_rn(v, sc, sh);
+        return relu ? fmaxf(v, 0.f) : v;
+    };
+    const int Wv = Wf >> 2;
+    const int rpp = NT / Wv;                       // rows per pass (NT is a multiple of Wv)
+    const int d0 = tid / Wv, wv = tid - d0 * Wv, w0 = wv << 2;
+    float* obase = out + (((size_t)b * O + o) * Df * Hf + h) * (size_t)Wf;
+    const size_t dstride = (size_t)Hf * Wf;
+    if (d0 < rpp) {
+        float* op = obase + (size_t)d0 * dstride + w0;
+        const size_t ostep = (size_t)rpp * dstride;
+        const float4 lf1 = *reinterpret_cast<const float4*>(LF + 1 * Wp + kStemPad + w0);
+        const float zero_val = finish(0.f);
+        for (int d = d0; d < Df; d += rpp, op += ostep) {
+            const int cls = d == 0 ? 0 : (d == Df - 1 ? 2 : 1);
+            const int u0 = w0 - d;
+            float4 v;
+            if (u0 + 3 <= -3) {                     // fully masked group (warp-coherent: whole left part of a row)
+                v = make_float4(zero_val, zero_val, zero_val, zero_val);
+            } else {
+                const float4 lf = cls == 1 ? lf1 : *reinterpret_cast<const float4*>(LF + cls * Wp + kStemPad + w0);
+                // RF copy (d & 3) at vector offset w0 - 4*(d >> 2); for u0 < 0 this reads the zero pad / garbage that is masked below
+                const int ro = max(w0 - (d & ~3), -kStemPad);
+                const float4 rf = *reinterpret_cast<const float4*>(RF + (cls * 4 + (d & 3)) * Wp + kStemPad + ro);
+                v.x = u0 + 0 >= -2 ? finish(lf.x + rf.x) : zero_val;
+                v.y = u0 + 1 >= -2 ? finish(lf.y + rf.y) : zero_val;
+                v.z = u0 + 2 >= -2 ? finish(lf.z + rf.z) : zero_val;
+                v.w = u0 + 3 >= -2 ? finish(lf.w + rf.w) : zero_val;
+            }
+            st_stream(reinterpret_cast<float4*>(op), v);
+        }
+    }
+    __syncthreads();                               // main-pass stores of this CTA are ordered before the patches
+    for (int i = tid; i < 5 * Df; i += NT) {
+        const int d = i / 5, j = i - d * 5;
+        const int col = j < 4 ? d - 2 + j : Wf - 1;
+        if (col < 0 || col >= Wf) continue;
+        if (j == 4 && col - d <= 1) continue;      // last column already covered by the band entries
+        const float v = j < 4 ? band[d * 4 + j] : lastcol[d];
+        obase[(size_t)d * dstride + col] = finish(v);
     }
 }
 
@@ -227,12 +441,29 @@ int cv_stem_fwd(const float* x, const float* y, const float* w, const float* sca
     if (B <= 0 || C <= 0 || O <= 0 || Df <= 0 || Hf <= 0 || Wf <= 0 || B > 65535 || O > 65535 || Hf > 2147483647 / 4)
         return fail(RAG_E_SHAPE, "cv_stem_fwd: bad shape B=%d C=%d O=%d Df=%d Hf=%d Wf=%d", B, C, O, Df, Hf, Wf);
     if ((size_t)O * Df * Hf * Wf >= ((size_t)1 << 40)) return fail(RAG_E_SHAPE, "cv_stem_fwd: output too large");
-    if (variant < -1 || variant > 1) return fail(RAG_E_VARIANT, "cv_stem_fwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 2) return fail(RAG_E_VARIANT, "cv_stem_fwd: unknown variant %d", variant);
     const size_t smem = ((size_t)2 * C * 36 + (size_t)33 * (Wf + 2 * kStemPad) + (size_t)5 * Df) * sizeof(float);
     const bool fast_ok = C == 12 && Df >= 3 && Wf >= 8 && smem <= 200 * 1024 && aligned(out, 16) && Hf <= 65535 * 32;
-    if (variant == 1 && !fast_ok) return fail(RAG_E_VARIANT, "cv_stem_fwd: variant 1 needs C == 12, Df >= 3, Wf >= 8 and a 16-byte aligned output");
-    if (variant == -1) variant = fast_ok ? 1 : 0;
-    if (variant == 1) {
+    if (variant >= 1 && !fast_ok) return fail(RAG_E_VARIANT, "cv_stem_fwd: variants 1/2 need C == 12, Df >= 3, Wf >= 8 and a 16-byte aligned output");
+    const bool packed_ok = fast_ok && Wf % 4 == 0 && Wf / 4 <= 512 && aligned(x, 8) && aligned(y, 8);
+    if (variant == 2 && !packed_ok) return fail(RAG_E_VARIANT, "cv_stem_fwd: variant 2 needs Wf %% 4 == 0, Wf <= 2048 and 8-byte aligned features");
+    if (variant == -1) variant = packed_ok ? 2 : (fast_ok ? 1 : 0);
+    if (variant == 2) {
+        auto kern = cv_stem_fwd2_kernel<12>;
+        // block = a multiple of Wf/4 (a thread keeps its column group in phase 3), as close to 384 threads as possible
+        const int Wv = Wf / 4;
+        int k = 384 / Wv;
+        if (k < 1) k = 1;
+        int nt = k * Wv;
+        if (nt < 128) nt = ((128 + Wv - 1) / Wv) * Wv;
+        const size_t smem2 = ((size_t)2 * C * 60 + (size_t)33 * (Wf + 2 * kStemPad) + (size_t)4 * Df + ((Df + 3) & ~3)) * sizeof(float) +
+                             (size_t)kStemStages * 3 * nt * sizeof(float2);
+        if (smem2 > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+            if (e != cudaSuccess) return fail((int)e, "cv_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        }
+        kern<<<dim3(Hf, O, B), nt, smem2, st>>>(x, y, w, scale, shift, relu, out, O, Df, Hf, Wf);
+    } else if (variant == 1) {
         auto kern = cv_stem_fwd_kernel<12>;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

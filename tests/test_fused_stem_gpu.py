@@ -79,7 +79,7 @@ def test_fused_stem_matches_reference(shape):
         full_ref = ref_stem(x, y, layer, md)
         scale = layer.bn.weight * torch.rsqrt(layer.bn.running_var + layer.bn.eps)
         shift = layer.bn.bias - layer.bn.running_mean * scale
-        for v in (None, 0) + ((1,) if (c == 12 and int(md / 3) >= 3 and wf >= 8) else ()):
+        for v in (None, 0) + ((1,) if (c == 12 and int(md / 3) >= 3 and wf >= 8) else ()) + ((2,) if (c == 12 and int(md / 3) >= 3 and wf >= 8 and wf % 4 == 0) else ()):
             conv = cv_stem_forward(x, y, layer.conv.weight, maxdisp=md, variant=v)
             assert conv.shape == conv_ref.shape
             err = (conv - conv_ref).abs().max().item() / conv_ref.abs().max().item()

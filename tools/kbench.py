@@ -108,8 +108,9 @@ def main():
         sc = torch.rand(12, device=dev, generator=g) + 0.5
         sh = torch.randn(12, device=dev, generator=g)
         out_bytes = 4 * (12 * df * hf * wf + 2 * c * hf * wf) * b
-        med, best = timeit(lambda: cv_stem_forward(x, y, wgt, sc, sh, True, md), a.iters, flush)
-        report("cv_stem_fused(conv+bn+relu)", 1, med, best, out_bytes)
+        for v in (2, 1):
+            med, best = timeit(lambda: cv_stem_forward(x, y, wgt, sc, sh, True, md, variant=v), a.iters, flush)
+            report("cv_stem_fused(conv+bn+relu)", v, med, best, out_bytes)
         conv = torch.nn.Conv3d(24, 12, 3, padding=1, bias=False).to(dev)
         bn = torch.nn.BatchNorm3d(12).to(dev).eval()
         with torch.no_grad():
