@@ -148,6 +148,52 @@ def torch_cuda_reference(workload, dev, reps=5):
             "what": "reference op sequence (rag_model.py:375-383,18-44) through PyTorch eager CUDA kernels on this GPU, 1 pair per call"}
 
 
+def fused_stem_row(x, y, df, md, sub):
+    """SURVEY.md section 8f rank 1 (reported beside the headline, not part of `value`): cost volume + first
+    Matching-Net layer (ConvBR_3d 2C->C, 3x3x3, eval-mode BN, ReLU).  Fused kernel (volume never
+    materialised, fp32) vs the reference composition on the materialised volume through cuDNN (TF32 default)."""
+    import torch
+
+    from rag_b200 import functional as F_
+    from rag_b200.fused_stem import cv_stem_forward
+
+    dev = x.device
+    xs, ys = x[:sub], y[:sub]
+    c = x.shape[1]
+    g = torch.Generator(device=dev).manual_seed(11)
+    conv = torch.nn.Conv3d(2 * c, c, 3, padding=1, bias=False).to(dev)
+    bn = torch.nn.BatchNorm3d(c).to(dev).eval()
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.3, generator=g)
+        bn.running_var.uniform_(0.5, 2.0, generator=g)
+        scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+        shift = bn.bias - bn.running_mean * scale
+
+        def t(fn, n):
+            fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / n
+
+        fused = t(lambda: cv_stem_forward(xs, ys, conv.weight, scale, shift, True, md), 10)
+        ref = t(lambda: torch.relu_(bn(conv(F_.cost_volume_forward(xs, ys, df)))), 3)
+        a = cv_stem_forward(xs[:1], ys[:1], conv.weight, scale, shift, True, md)
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        b_ = torch.relu_(bn(conv(F_.cost_volume_forward(xs[:1], ys[:1], df))))
+        torch.backends.cudnn.allow_tf32 = old
+        err = ((a - b_).abs().max() / b_.abs().max()).item()
+    torch.cuda.empty_cache()
+    return {"what": "cost volume + stem3d0 (Conv3d 24->12 3x3x3 + BN(eval) + ReLU), %d pairs" % sub,
+            "fused_ms": round(fused, 4), "cost_volume_plus_cudnn_tf32_ms": round(ref, 4), "speedup": round(ref / fused, 1),
+            "max_rel_err_vs_fp32_cudnn": err}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -365,9 +411,12 @@ def run_gpu(args):
 
     cpu = None
     torch_gpu = None
+    next_rows = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu, _ = cpu_reference(args.workload, budget_s=12.0)
         torch_gpu = torch_cuda_reference(args.workload, dev)
+        if not bwd:
+            next_rows = fused_stem_row(x, y, df, md, sub)
 
     if rank == 0:
         line = {
@@ -378,7 +427,7 @@ def run_gpu(args):
                        "volume": [b, 2 * c, df, hf, wf], "head_in": [b, 1, df, hf, wf], "maxdisp": md,
                        "l2": "no explicit flush: every step streams %.2f GB (>> 126 MB L2) through HBM" % (path_bytes / 1e9),
                        "sharding": "stereo pairs across ranks, no data-path collective"},
-            "roofline": roofline, "path": path, "cpu_baseline": cpu, "torch_cuda_reference": torch_gpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "path": path, "cpu_baseline": cpu, "torch_cuda_reference": torch_gpu, "next_rows": next_rows, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
