@@ -116,6 +116,7 @@ head_fwd_generic_kernel(const float* __restrict__ cost, float* __restrict__ disp
 #include "disp_head_x3u.cuh"
 #include "disp_head_x3v.cuh"
 #include "disp_head_x3w.cuh"
+#include "disp_head_x3r.cuh"
 namespace rag {
 
 // ---------------------------------------------------------------------------------------------
@@ -244,14 +245,31 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
                   int variant, cudaStream_t st) {
     if (!cost || !disp) return fail(RAG_E_NULL, "disp_head_fwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 9) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 13) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
     if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl", variant);
     const bool tiled_ok = x3 && (Wl % 4 == 0) && aligned(cost, 16);
     if (variant >= 4 && !tiled_ok) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl, Wl %% 4 == 0 and 16-byte aligned cost_lr", variant);
-    if (variant == -1) variant = tiled_ok ? 9 : (x3 ? 1 : 0);
-    if (variant >= 7) {
+    if (variant == -1) variant = tiled_ok ? 10 : (x3 ? 1 : 0);
+    if (variant >= 10) {
+        // cube-root kernels; fp32-lambda correction: 10 = from the second chunk on (default), 11 = never,
+        // 12 = every step, 13 = as 10 with a 3 CTAs/SM register budget
+        dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
+        const size_t smem = (size_t)2 * 16 * kTRows * kTCols * sizeof(float) + ((size_t)18 * 128 + 2 * Dl) * sizeof(float2);
+        auto launch = [&](auto kern) -> int {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "disp_head_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            kern<<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+            return RAG_OK;
+        };
+        int e = RAG_OK;
+        if (variant == 10) e = launch(head_fwd_x3r_kernel<4, 16, 2, 2>);
+        if (variant == 11) e = launch(head_fwd_x3r_kernel<4, 16, 2, 0>);
+        if (variant == 12) e = launch(head_fwd_x3r_kernel<4, 16, 2, 1>);
+        if (variant == 13) e = launch(head_fwd_x3r_kernel<3, 16, 2, 2>);
+        if (e) return e;
+    } else if (variant >= 7) {
         dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
         const size_t fixed = ((size_t)18 * 128 + 4 * Dl) * sizeof(float2);
         const size_t smem8 = (size_t)3 * 8 * kTRows * kTCols * sizeof(float) + fixed;     // 3 stages x 8 bins

@@ -120,7 +120,7 @@ def main():
                 report("cost_volume+cudnn_conv3d_bn_relu(tf32=%s)" % tf32, -1, med, best, out_bytes)
             torch.backends.cudnn.allow_tf32 = True
     if want("head_fwd"):
-        for v in (9, 8, 7):
+        for v in (10, 11, 12, 13, 9):
             try:
                 med, best = timeit(lambda: F_.disp_head_forward(cost_lr, md, True, variant=v), a.iters, flush)
                 report("head_fwd", v, med, best, hf_bytes)
