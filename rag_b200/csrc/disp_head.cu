@@ -21,6 +21,8 @@
 // Bound: NOT HBM. Per output pixel the head needs maxdisp exp2 on the SFU (16 lanes/clk/SM): 192
 // MUFU.EX2 per pixel = 8 SMSP-clk per pixel-bin, which is the floor of this kernel (~7 us per
 // 288x576 pair); the x3 kernel is organised so that everything else (blend, sums) fits under it.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace rag {
@@ -254,20 +256,23 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
     if (variant == -1) variant = tiled_ok ? 10 : (x3 ? 1 : 0);
     if (variant >= 10) {
         // cube-root kernels; fp32-lambda correction: 10 = from the second chunk on (default), 11 = never,
-        // 12 = every step, 13 = as 10 with a 3 CTAs/SM register budget
-        dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
-        const size_t smem = (size_t)2 * 16 * kTRows * kTCols * sizeof(float) + ((size_t)18 * 128 + 2 * Dl) * sizeof(float2);
+        // 12 = every step + TwoSum totals (most accurate), 13 = as 10 with TwoSum totals.
+        // (5 block rows per CTA would fill the last wave of the 480x960 B=8 grid better, but 5 warps do not
+        // spread evenly over the 4 SM sub-partitions: measured 202 us vs 165 us.)
+        constexpr int warps = 4;
+        dim3 grid((Wl + 31) / 32, (Hl + warps - 1) / warps, B);
+        const size_t smem = (size_t)2 * 16 * (warps + 2) * kTCols * sizeof(float) + ((size_t)18 * 32 * warps + 2 * Dl) * sizeof(float2);
         auto launch = [&](auto kern) -> int {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "disp_head_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            kern<<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+            kern<<<grid, 32 * warps, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
             return RAG_OK;
         };
         int e = RAG_OK;
-        if (variant == 10) e = launch(head_fwd_x3r_kernel<4, 16, 2, 2>);
-        if (variant == 11) e = launch(head_fwd_x3r_kernel<4, 16, 2, 0>);
-        if (variant == 12) e = launch(head_fwd_x3r_kernel<4, 16, 2, 1>);
-        if (variant == 13) e = launch(head_fwd_x3r_kernel<3, 16, 2, 2>);
+        if (variant == 11) e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 0, false>);
+        else if (variant == 12) e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 1, true>);
+        else if (variant == 13) e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 2, true>);
+        else e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 2, false>);
         if (e) return e;
     } else if (variant >= 7) {
         dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);

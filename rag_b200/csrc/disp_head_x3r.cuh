@@ -91,23 +91,27 @@ __device__ __forceinline__ void x3r_step(const float& c, float& cn, float& c2, f
     q = __fmaf_rn(nk3, s2, c);
 }
 
-// grid: x = ceil(Wl/32), y = ceil(Hl/4), z = B; 128 threads.
-// smem: tile[STAGES][BINS][kTRows][kTCols] | float2 tot[18][128] | float2 kap[Dl][2] ((k1,k1),(k2,k2))
-template <int MINB, int BINS, int STAGES, int CORR>
-__global__ void __launch_bounds__(128, MINB)
+// grid: x = ceil(Wl/32), y = ceil(Hl/WARPS), z = B; 32*WARPS threads (a CTA owns WARPS block rows x 32 block
+// columns; the host picks WARPS in {4, 5} for the fuller last wave).
+// smem: tile[STAGES][BINS][WARPS+2][kTCols] | float2 tot[18][NT] | float2 kap[Dl][2] ((k1,k1),(k2,k2))
+template <int WARPS, int MINB, int BINS, int STAGES, int CORR, bool TWOSUM>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
 head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, float* __restrict__ stats,
                     int Dl, int Hl, int Wl, float scale) {
     static_assert(BINS % 2 == 0, "two bins are staged per pass");
+    constexpr int NT = 32 * WARPS, ROWS = WARPS + 2, HALF = NT / 2;
+    static_assert(HALF >= ROWS * (kTCols / 4), "half a CTA stages one bin slab per pass");
+    static_assert(NT >= BINS * ROWS, "one thread per window row for the edge patches");
     extern __shared__ __align__(16) float x3r_smem[];
-    constexpr int kStageFloats = BINS * kTRows * kTCols;
-    constexpr int kBinFloats = kTRows * kTCols;
+    constexpr int kStageFloats = BINS * ROWS * kTCols;
+    constexpr int kBinFloats = ROWS * kTCols;
     const int D = 3 * Dl, W = 3 * Wl;
     float* tile = x3r_smem;
     float2* tot = reinterpret_cast<float2*>(x3r_smem + STAGES * kStageFloats);   // [18][128]
-    float2* kap = tot + 18 * 128;                                                   // [Dl][2]
+    float2* kap = tot + 18 * NT;                                                   // [Dl][2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.z;
-    const int C0 = blockIdx.x * 32, R0 = blockIdx.y * 4;
+    const int C0 = blockIdx.x * 32, R0 = blockIdx.y * WARPS;
     const int T0 = C0 - 4;
     const size_t plane = (size_t)Hl * Wl;
     const float* base = cost + (size_t)b * Dl * plane;
@@ -117,11 +121,11 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     const bool patch_r = (Wl - T0) <= 36;
     const int pr = Wl - T0;
 
-    // window staging: one bin slab = 6 rows x 10 vectors.  Threads 0..59 copy the even bins of a chunk,
-    // threads 64..123 the odd ones; a thread's (row, vector) and so its source offset inside a bin
-    // plane never change.
-    const int st_half = tid >> 6, st_u = tid & 63;
-    const bool st_on = st_u < kTRows * (kTCols / 4);
+    // window staging: one bin slab = ROWS rows x 10 vectors.  The first half of the CTA copies the even bins
+    // of a chunk, the second half the odd ones; a thread's (row, vector) and so its source offset inside
+    // a bin plane never change.
+    const int st_half = tid >= HALF ? 1 : 0, st_u = tid - st_half * HALF;
+    const bool st_on = st_u < ROWS * (kTCols / 4);
     const int st_row = st_u / (kTCols / 4), st_vec = st_u % (kTCols / 4);
     const int st_soff = st_half * kBinFloats + st_row * kTCols + st_vec * 4;
     const float* st_src = base + (size_t)min(max(R0 - 1 + st_row, 0), Hl - 1) * Wl + 4 * min(max((T0 >> 2) + st_vec, 0), Wv - 1);
@@ -140,7 +144,7 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     if (STAGES > 2) issue_chunk(1);
     // kappa_q(j) = 3 ln2 (lambda_fp32(3j+1+q) - q/3), q = 1, 2: the 3 converts du (z/3 domain) to dz.
     // lambda - fl(q/3) is exact in fp32 (Sterbenz); fl(1/3) - 1/3 = 2^-25/3, fl(2/3) - 2/3 = 2^-24/3.
-    for (int j = tid; j < Dl; j += 128) {
+    for (int j = tid; j < Dl; j += NT) {
         float k12[2];
 #pragma unroll
         for (int q = 1; q <= 2; ++q) {
@@ -157,7 +161,7 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     }
     float2* mytot = tot + tid;
 #pragma unroll
-    for (int s = 0; s < 18; ++s) mytot[s * 128] = f2b(0.f);
+    for (int s = 0; s < 18; ++s) mytot[s * NT] = f2b(0.f);
 
     const int r_raw = R0 + warp, c_raw = C0 + lane;
     const bool active = r_raw < Hl && c_raw < Wl;
@@ -173,8 +177,10 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
         src_index<true>(scale, 3 * c + i, Wl, i0, i1, wl0[i], wl1[i]);
     }
     const int org = (r - R0) * kTCols + (c - C0 + 3);
-    const float2 wA = f2(wl0[0], wl0[2]), wB = f2(wl1[0], wl1[2]);       // columns 0 and 2 of a row
-    const float2 hA = f2(hs0[0], hs0[2]), hB = f2(hs1[0], hs1[2]);       // rows 0 and 2 of the centre column
+    // col 0 = wl0[0]*v0 + wl1[0]*v1, col 2 = wl0[2]*v1 + wl1[2]*v2  ->  (col0,col2) = wM*v1 + wO*(v0,v2)
+    const float2 wO = f2(wl0[0], wl1[2]), wM = f2(wl1[0], wl0[2]);
+    // centre column: row 0 = hs0[0]*v1[0] + hs1[0]*v1[1], row 2 = hs0[2]*v1[1] + hs1[2]*v1[2]
+    const float2 hO = f2(hs0[0], hs1[2]), hM = f2(hs1[0], hs0[2]);
     const float2 h00 = f2b(hs0[0]), h10 = f2b(hs1[0]), h02 = f2b(hs0[2]), h12 = f2b(hs1[2]);
     const float2 s3b = f2b(kS3);
 
@@ -187,35 +193,48 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
 
     // (z - m)/3 of the nine pixels at the low-res bin whose window slab starts at p
     auto blend = [&](const float* p, const float2 (&mn)[4], float mnS, float2 (&o)[4], float& oS) {
+        // operands are either natural pairs of two separate loads ((v0,v2) of a row, (v1 row0, v1 row2)) or
+        // scalars broadcast by the instruction, so no pair has to be assembled with MOVs
         float2 xc[3];
-        float v1[3];
 #pragma unroll
         for (int rr = 0; rr < 3; ++rr) {
-            const float v0 = p[rr * kTCols + 0], v2 = p[rr * kTCols + 2];
-            v1[rr] = p[rr * kTCols + 1];
-            xc[rr] = fma2(wA, f2(v0, v1[rr]), mul2(wB, f2(v1[rr], v2)));
+            const float2 v02 = f2(p[rr * kTCols + 0], p[rr * kTCols + 2]);
+            xc[rr] = fma2(wM, f2b(p[rr * kTCols + 1]), mul2(wO, v02));      // (col 0, col 2) of window row rr
         }
+        const float2 v1e = f2(p[0 * kTCols + 1], p[2 * kTCols + 1]);
+        const float v1c = p[1 * kTCols + 1];
         o[0] = fma2(h00, xc[0], fma2(h10, xc[1], mn[0]));
         o[1] = fma2(s3b, xc[1], mn[1]);
         o[2] = fma2(h02, xc[1], fma2(h12, xc[2], mn[2]));
-        o[3] = fma2(hA, f2(v1[0], v1[1]), fma2(hB, f2(v1[1], v1[2]), mn[3]));
-        oS = __fmaf_rn(kS3, v1[1], mnS);
+        o[3] = fma2(hM, f2b(v1c), fma2(hO, v1e, mn[3]));
+        oS = __fmaf_rn(kS3, v1c, mnS);
     };
+    // group sums -> totals.  TWOSUM keeps (hi, lo) totals with an error-free TwoSum; otherwise the four
+    // chunk sums are simply added in fp32 (at most ~1.5 ulp on top of the in-chunk rounding).
     auto fold = [&]() {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float2 hi = mytot[(4 * i + 0) * 128], lo = mytot[(4 * i + 1) * 128];
-            two_sum_acc(hi, lo, st[i].S);
-            mytot[(4 * i + 0) * 128] = hi; mytot[(4 * i + 1) * 128] = lo;
-            hi = mytot[(4 * i + 2) * 128]; lo = mytot[(4 * i + 3) * 128];
-            two_sum_acc(hi, lo, st[i].T);
-            mytot[(4 * i + 2) * 128] = hi; mytot[(4 * i + 3) * 128] = lo;
+            if (TWOSUM) {
+                float2 hi = mytot[(4 * i + 0) * NT], lo = mytot[(4 * i + 1) * NT];
+                two_sum_acc(hi, lo, st[i].S);
+                mytot[(4 * i + 0) * NT] = hi; mytot[(4 * i + 1) * NT] = lo;
+                hi = mytot[(4 * i + 2) * NT]; lo = mytot[(4 * i + 3) * NT];
+                two_sum_acc(hi, lo, st[i].T);
+                mytot[(4 * i + 2) * NT] = hi; mytot[(4 * i + 3) * NT] = lo;
+            } else {
+                mytot[(4 * i + 0) * NT] = add2(mytot[(4 * i + 0) * NT], st[i].S);
+                mytot[(4 * i + 2) * NT] = add2(mytot[(4 * i + 2) * NT], st[i].T);
+            }
             st[i].S = f2b(0.f); st[i].T = f2b(0.f);
         }
-        float2 d = mytot[16 * 128], n = mytot[17 * 128];
-        two_sum_acc(d.x, d.y, so.S);
-        two_sum_acc(n.x, n.y, so.T);
-        mytot[16 * 128] = d; mytot[17 * 128] = n;
+        float2 d = mytot[16 * NT], n = mytot[17 * NT];
+        if (TWOSUM) {
+            two_sum_acc(d.x, d.y, so.S);
+            two_sum_acc(n.x, n.y, so.T);
+        } else {
+            d.x += so.S; n.x += so.T;
+        }
+        mytot[16 * NT] = d; mytot[17 * NT] = n;
         so.S = 0.f; so.T = 0.f;
     };
     // rare path: the new bin's exponent `t` exceeds the pixel's reference by more than kX3rTau.  The
@@ -229,9 +248,9 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
                 const float f = ex2_approx(-tt), f3 = ex2_approx(-3.f * tt);
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
-                    float2 v = mytot[(slot + s) * 128];
+                    float2 v = mytot[(slot + s) * NT];
                     if (hi_lane) v.y *= f3; else v.x *= f3;
-                    mytot[(slot + s) * 128] = v;
+                    mytot[(slot + s) * NT] = v;
                 }
                 cc *= f; ps *= f; q *= f; c2 = cc * cc;
                 mn -= tt; aa -= tt; tt = 0.f;
@@ -244,9 +263,9 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
         }
         if (tS > kX3rTau) {
             const float f = ex2_approx(-tS), f3 = ex2_approx(-3.f * tS);
-            float2 d = mytot[16 * 128], n = mytot[17 * 128];
+            float2 d = mytot[16 * NT], n = mytot[17 * NT];
             d.x *= f3; d.y *= f3; n.x *= f3; n.y *= f3;
-            mytot[16 * 128] = d; mytot[17 * 128] = n;
+            mytot[16 * NT] = d; mytot[17 * NT] = n;
             so.c[cur] *= f; so.ps *= f; so.q *= f; so.c2 = so.c[cur] * so.c[cur];
             mnegS -= tS; aS -= tS; tS = 0.f;
         }
@@ -270,21 +289,40 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     };
     using I0 = std::integral_constant<int, 0>;
     using I1 = std::integral_constant<int, 1>;
-    // the steps of one chunk: two groups per trip, exponent registers (ua -> ub -> ua) and c halves ping-pong
+    // the steps of one chunk: two groups per trip, exponent registers (ua -> ub -> ua) and c halves ping-pong.
+    // A pixel running away from its reference (rare) BREAKS out of the hot loop, is handled below it and
+    // the loop is re-entered, so that the hot loop is straight-line code with fall-through exits only.
+    auto hot = [&](const float2 (&t)[4], float tS) { return __any_sync(0xffffffffu, maxof(t, tS) > kX3rTau); };
     auto run_chunk = [&](auto corr_tag, const float* p, int n_it, const float2* kp) {
-        for (; n_it >= 2; n_it -= 2) {
-            blend(p, mneg, mnegS, ub, ubS);
-            if (maxof(ub, ubS) > kX3rTau) rescale(I0{}, ub, ubS, ua, uaS);
-            group(I0{}, corr_tag, ua, uaS, ub, ubS, kp[0], kp[1]);
-            blend(p + kBinFloats, mneg, mnegS, ua, uaS);
-            if (maxof(ua, uaS) > kX3rTau) rescale(I1{}, ua, uaS, ub, ubS);
+        for (;;) {
+            int rare = 0;
+            for (; n_it >= 2; n_it -= 2) {
+                blend(p, mneg, mnegS, ub, ubS);
+                if (hot(ub, ubS)) { rare = 1; break; }
+                group(I0{}, corr_tag, ua, uaS, ub, ubS, kp[0], kp[1]);
+                blend(p + kBinFloats, mneg, mnegS, ua, uaS);
+                if (hot(ua, uaS)) { rare = 2; break; }
+                group(I1{}, corr_tag, ub, ubS, ua, uaS, kp[2], kp[3]);
+                p += 2 * kBinFloats;
+                kp += 4;
+            }
+            if (rare == 0) break;
+            if (rare == 1) {
+                rescale(I0{}, ub, ubS, ua, uaS);
+                group(I0{}, corr_tag, ua, uaS, ub, ubS, kp[0], kp[1]);
+                blend(p + kBinFloats, mneg, mnegS, ua, uaS);
+                if (hot(ua, uaS)) rescale(I1{}, ua, uaS, ub, ubS);
+            } else {
+                rescale(I1{}, ua, uaS, ub, ubS);
+            }
             group(I1{}, corr_tag, ub, ubS, ua, uaS, kp[2], kp[3]);
             p += 2 * kBinFloats;
             kp += 4;
+            n_it -= 2;
         }
         if (n_it == 1) {
             blend(p, mneg, mnegS, ub, ubS);
-            if (maxof(ub, ubS) > kX3rTau) rescale(I0{}, ub, ubS, ua, uaS);
+            if (hot(ub, ubS)) rescale(I0{}, ub, ubS, ua, uaS);
             group(I0{}, corr_tag, ua, uaS, ub, ubS, kp[0], kp[1]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) { ua[i] = ub[i]; st[i].c[0] = st[i].c[1]; }
@@ -298,7 +336,7 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
         __syncthreads();
         float* stw = tile + (ch % STAGES) * kStageFloats;
         if (patch_l || patch_r) {
-            if (tid < BINS * kTRows) {
+            if (tid < BINS * ROWS) {
                 float* rowp = stw + tid * kTCols;
                 if (patch_l) rowp[3] = rowp[4];
                 if (patch_r) rowp[pr] = rowp[pr - 1];
@@ -347,26 +385,28 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     if (!active) return;
 
     const size_t img = (size_t)3 * Hl * W;
+    float* dp = disp + (size_t)b * img + (size_t)(3 * r) * W + 3 * c;
+    float* sp = stats ? stats + (size_t)b * 2 * img + (size_t)(3 * r) * W + 3 * c : nullptr;
     // totals: d = sum 2^(z_k - m), n = -sum (k - kc) 2^(z_k - m)
     auto emit = [&](int ph, int pw, float dhi, float dlo, float nhi, float nlo, float mn) {
-        const size_t o = (size_t)(3 * r + ph) * W + (3 * c + pw);
-        const float inv = 1.f / (dhi + dlo);
+        const int o = ph * W + pw;
+        const float inv = __frcp_rn(dhi + dlo);
         const float q = nhi * inv;
         const float rr2 = __fmaf_rn(-q, dhi, nhi) + (nlo - q * dlo);
-        disp[(size_t)b * img + o] = kc - (q + rr2 * inv);
-        if (stats) {
+        dp[o] = kc - (q + rr2 * inv);
+        if (sp) {
             // reference exponent in the z domain: m = -3*mn = mhi + mlo; the rounding residue mlo is
             // folded into the stored normaliser so that 2^(z - mhi) * inv' == 2^(z - m) * inv
             const float mhi = -3.f * mn;
             const float mlo = __fmaf_rn(-3.f, mn, -mhi);
-            stats[(size_t)b * 2 * img + o] = mhi;
-            stats[(size_t)b * 2 * img + img + o] = inv * ex2_approx(-mlo);
+            sp[o] = mhi;
+            sp[img + o] = inv * ex2_approx(-mlo);
         }
     };
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float2 dhi = mytot[(4 * i + 0) * 128], dlo = mytot[(4 * i + 1) * 128];
-        const float2 nhi = mytot[(4 * i + 2) * 128], nlo = mytot[(4 * i + 3) * 128];
+        const float2 dhi = mytot[(4 * i + 0) * NT], dlo = mytot[(4 * i + 1) * NT];
+        const float2 nhi = mytot[(4 * i + 2) * NT], nlo = mytot[(4 * i + 3) * NT];
         if (i < 3) {
             emit(i, 0, dhi.x, dlo.x, nhi.x, nlo.x, mneg[i].x);
             emit(i, 2, dhi.y, dlo.y, nhi.y, nlo.y, mneg[i].y);
@@ -376,7 +416,7 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
         }
     }
     {
-        const float2 d = mytot[16 * 128], n = mytot[17 * 128];
+        const float2 d = mytot[16 * NT], n = mytot[17 * NT];
         emit(1, 1, d.x, d.y, n.x, n.y, mnegS);
     }
 }
