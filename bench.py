@@ -278,7 +278,7 @@ def run_gpu(args):
     from rag_b200 import _cabi
     from rag_b200 import functional as F_
     from rag_b200.modules import CostVolume, Disp
-    from rag_b200.pipeline import HostPipeline
+    from rag_b200.pipeline import HostPipeline, OverlappedPath
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -336,28 +336,62 @@ def run_gpu(args):
     for _ in range(Wm):
         out = step()
     del out
+
+    # ---- serial pass: the kernels back to back on one stream, each bracketed by events.  This is where the
+    # per-kernel durations (roofline) come from; for the training workload it is also the timed region. ----
+    def serial_pass():
+        barrier()
+        t0, t1 = ev(), ev()
+        t0.record()
+        for k in range(K):
+            out = step(marks[k])
+        t1.record()
+        torch.cuda.synchronize()
+        del out
+        return t0.elapsed_time(t1)
+
+    # ---- overlapped pass (inference workloads): cost volume and disparity head on two streams, the
+    # schedule of rag_b200.pipeline.OverlappedPath for a stream of batches ----
+    opath = OverlappedPath(md, dev) if not bwd else None
+
+    def overlapped_step():
+        outs = [opath.step(x[i:i + sub], y[i:i + sub], cl[i:i + sub]) for i in range(0, b, sub)]
+        return outs
+
+    def overlapped_pass():
+        for _ in range(Wm):
+            outs = overlapped_step()
+        opath.join()
+        barrier()
+        t0, t1 = ev(), ev()
+        t0.record()
+        for k in range(K):
+            outs = overlapped_step()
+        opath.join()
+        t1.record()
+        torch.cuda.synchronize()
+        del outs
+        return t0.elapsed_time(t1)
+
     sampler = ClockSampler(local) if rank == 0 else None
+    serial_ms = None
+    if not bwd:
+        serial_ms = serial_pass()            # untimed for `value`: kernel durations only
     barrier()
     n0 = _cabi.launch_count()
     if sampler: sampler.start()
-    t_start, t_end = ev(), ev()
-    t_start.record()
-    for k in range(K):
-        out = step(marks[k])
-    t_end.record()
-    torch.cuda.synchronize()
+    total_ms = overlapped_pass() if not bwd else serial_pass()
     if sampler: clocks = sampler.stop()
-    launches = _cabi.launch_count() - n0
+    launches = _cabi.launch_count() - n0 - (0 if bwd else Wm * 2 * (b // sub))   # minus the warm-up launches of the pass
     barrier()
-    total_ms = t_start.elapsed_time(t_end)
-    del out
     if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([total_ms, serial_ms if serial_ms is not None else total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        total_ms = float(t[0].item())
+        serial_ms = float(t[1].item()) if serial_ms is not None else None
     value = world * b * K / (total_ms * 1e-3)
 
-    # per-kernel average durations inside the timed region
+    # per-kernel average durations (serial pass: each kernel alone on the GPU, back to back)
     n_seg = 4 if bwd else 2
     seg_ms = [sum(marks[k][i].elapsed_time(marks[k][i + 1]) for k in range(K)) / K for i in range(n_seg)]
     cvb, hfb, hbb = alg_bytes(c, hf, wf, df)
@@ -365,21 +399,32 @@ def run_gpu(args):
     n_sub = b // sub
     cv_ms = seg_ms[0] / n_sub                       # average duration of ONE cost-volume launch
     achieved = cvb * sub / (cv_ms * 1e-3) / 1e9
+    lean = wf % 4 == 0
     roofline = {
-        "bound": "hbm", "kernel": "cv_fwd_kernel<4,256> (cost-volume forward)", "achieved": round(achieved, 1), "peak": peak,
-        "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic("cv_fwd_kernel"),
+        "bound": "hbm", "kernel": ("cv_fwd_lean_kernel<256,2,true>" if lean else "cv_fwd_kernel") + " (cost-volume forward)",
+        "achieved": round(achieved, 1), "peak": peak,
+        "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic("cv_fwd_lean_kernel" if lean else "cv_fwd_kernel"),
         "peak_source": peak_src, "alg_bytes_per_launch": cvb * sub, "avg_launch_ms": round(cv_ms, 5),
+        "timed_in": "serial pass of %d steps in this run (kernels back to back on one stream, CUDA events around each)" % K,
+        "note": "a write-only stream: the measured peak is a COPY (read+write) figure, a pure fill of the same bytes runs at ~7.45 TB/s",
     }
     path_bytes = (cvb + hfb + ((cvb + hbb) if bwd else 0)) * b
     kernels = {"cv_fwd_ms": seg_ms[0], "head_fwd_ms": seg_ms[1]}
     if bwd:
         kernels.update({"head_bwd_ms": seg_ms[2], "cv_bwd_ms": seg_ms[3]})
+    step_ms = total_ms / K
     path = {
-        "alg_bytes_per_step": path_bytes, "achieved_GBps": round(path_bytes / (total_ms / K * 1e-3) / 1e9, 1),
-        "frac_of_hbm_peak": round(path_bytes / (total_ms / K * 1e-3) / 1e9 / peak, 4),
+        "alg_bytes_per_step": path_bytes, "achieved_GBps": round(path_bytes / (step_ms * 1e-3) / 1e9, 1),
+        "frac_of_hbm_peak": round(path_bytes / (step_ms * 1e-3) / 1e9 / peak, 4),
+        "schedule": ("serial: the four kernels back to back on one stream" if bwd else
+                     "overlapped: cost volume and disparity head on two streams (rag_b200.pipeline.OverlappedPath); the two kernels of a step have no "
+                     "data dependence (in the network the Matching Net sits between them: head of batch i runs beside the volume of batch i+1)"),
         "kernel_ms": {k: round(v, 5) for k, v in kernels.items()},
-        "note": "the head kernels are SFU (exp2) bound, not HBM bound; see DESIGN.md",
+        "note": "the head kernels are FP32-pipe bound (one exp2 + 7-12 FP32 ops per pixel per low-res bin), not HBM bound; see DESIGN.md",
     }
+    if serial_ms is not None:
+        path["serial"] = {"ms_per_step": round(serial_ms / K, 5), "pairs_per_s": round(world * b * K / (serial_ms * 1e-3), 1),
+                          "frac_of_hbm_peak": round(path_bytes / (serial_ms / K * 1e-3) / 1e9 / peak, 4)}
 
     # ---- e2e: HOST buffers through the public pipeline (H2D + kernels + D2H per step) ----
     pipe = HostPipeline(md, dev)

@@ -94,7 +94,13 @@ RAG_API int rag_disparity_regression_bwd(const float* gout, float* gp, int B, in
 RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int Dl, int Hl, int Wl,
                            int maxdisp, int fma_index, void* stream);
 
-/* ---- variants (tuning / A-B measurement only; the functions above pick the default) -------- */
+/* ---- variants (tuning / A-B measurement only; the functions above pick the default) --------
+ * Two ids matter to callers that overlap the two kernels of the path on two streams (the cost volume of
+ * one batch with the disparity head of another, rag_b200.pipeline.OverlappedPath): launch the cost
+ * volume FIRST with RAG_CV_FWD_SHARED -- a persistent grid of one 512-thread CTA per SM whose store
+ * stream leaves most of the SM to the FP32-bound head -- then the head with its default variant. */
+#define RAG_CV_FWD_LEAN 29    /* default when Wf % 4 == 0: persistent, one 256-thread CTA per SM           */
+#define RAG_CV_FWD_SHARED 32  /* same kernel, one 512-thread CTA per SM: best when sharing SMs with the head */
 RAG_API int rag_cost_volume_fwd_v(const float* x, const float* y, float* cost,
                           int B, int C, int Df, int Hf, int Wf, int variant, void* stream);
 RAG_API int rag_cost_volume_bwd_v(const float* gcost, float* gx, float* gy,

@@ -23,7 +23,7 @@ using namespace rag;
 #define ST(s) static_cast<cudaStream_t>(s)
 
 // default variants (picked from the measurements in profiles/)
-static constexpr int kCvFwdDefault = 0;
+static constexpr int kCvFwdDefault = -1;    // -1 = lean persistent kernel when Wf % 4 == 0 and pointers are 16-byte aligned, cv_fwd_kernel otherwise
 static constexpr int kCvBwdDefault = 0;
 static constexpr int kHeadFwdDefault = -1;  // -1 = x3 kernel when maxdisp == 3*Dl, generic otherwise
 static constexpr int kHeadBwdDefault = -1;

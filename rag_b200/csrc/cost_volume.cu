@@ -16,7 +16,11 @@
 //   Df-1 down to 0 accumulating in fp32 -- exactly the order in which autograd accumulates the
 //   CopySlices gradients -- so the result is bit-identical to the reference; loads are 128-bit,
 //   coalesced, and issued U disparities ahead of the dependent adds.  No atomics, no reduction tree.
+#include <algorithm>
+
 #include "common.cuh"
+#include "cv_tma.cuh"
+#include "cv_lean.cuh"
 
 namespace rag {
 
@@ -276,10 +280,87 @@ static int launch_cv_fwd(const float* x, const float* y, float* cost, int B, int
     return check_launch("cost_volume_fwd");
 }
 
+static bool cv_lean_ok(const float* x, const float* y, const float* cost, int Wf) {
+    return Wf % 4 == 0 && Wf <= 2048 && aligned(x, 16) && aligned(y, 16) && aligned(cost, 16);
+}
+
+template <int NT = 256, int VPT = 2>
+static int launch_cv_fwd_lean(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
+                              int per_sm, int dchunk, cudaStream_t st, size_t smem_floor = 0, bool dyn = false) {
+    const int Wv = Wf / 4, Df4 = (Df + 3) & ~3;
+    const size_t row_bytes = (size_t)16 * (Df4 + Wf + 4);          // four images of one row
+    int R = std::min(Hf, (NT * VPT) / Wv);
+    while (R > 1 && R * row_bytes > 64 * 1024) --R;
+    const size_t smem = std::max(R * row_bytes, smem_floor);
+    if (smem > 200 * 1024) return fail(RAG_E_SHAPE, "cost_volume_fwd(lean): Df=%d Wf=%d do not fit shared memory", Df, Wf);
+    static std::atomic<unsigned> ticket{0};
+    auto kern = dyn ? cv_fwd_lean_kernel<NT, VPT, true> : cv_fwd_lean_kernel<NT, VPT, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // the L1/shared split of an SM cannot change while CTAs are resident: ask for the largest shared-memory
+    // carve-out so that this kernel and the disparity head (which does the same) can share an SM
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return fail((int)e, "cost_volume_fwd(lean): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const int n_tiles = (Hf + R - 1) / R;
+    if (dchunk <= 0 || dchunk > Df) dchunk = (Df + 3) & ~3;
+    const int n_dchunks = (Df + dchunk - 1) / dchunk;
+    const long long n_items = (long long)B * C * n_tiles * n_dchunks;
+    const int grid = (int)(per_sm > 0 ? std::min<long long>(n_items, (long long)kNumSMs * per_sm) : n_items);
+    const int slot = dyn ? (int)(ticket.fetch_add(1) % 64u) : 0;
+    kern<<<grid, NT, smem, st>>>(x, y, cost, B * C, C, Df, Hf, Wf, R, n_tiles, dchunk, n_dchunks, slot);
+    return check_launch("cost_volume_fwd(lean)");
+}
+
+static bool cv_tma_ok(const float* x, const float* y, const float* cost, int Df, int Wf) {
+    return Wf % 4 == 0 && Df % 4 == 0 && Df <= Wf && aligned(x, 16) && aligned(y, 16) && aligned(cost, 16);
+}
+
+static int launch_cv_fwd_tma(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
+                             int R, int per_sm, int mode, cudaStream_t st) {
+    constexpr int NT = 128;
+    R = R > Hf ? Hf : R;
+    const size_t row_floats = (size_t)Wf + 4 * (size_t)(Df + Wf + 4);
+    while (R > 1 && 4 * (Df + 2 * R * row_floats) > 200 * 1024) --R;
+    const size_t smem = 4 * (Df + 2 * R * row_floats);
+    if (smem > 200 * 1024) return fail(RAG_E_SHAPE, "cost_volume_fwd(tma): Wf=%d too wide for shared memory", Wf);
+    auto kern = mode == 1 ? cv_fwd_tma_kernel<NT, 1> : mode == 2 ? cv_fwd_tma_kernel<NT, 2> : cv_fwd_tma_kernel<NT, 0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "cost_volume_fwd(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    static std::atomic<unsigned> ticket{0};
+    const int n_tiles = (Hf + R - 1) / R;
+    const int dchunk = std::min(16, Df), n_dchunks = (Df + dchunk - 1) / dchunk;
+    const long long n_items = (long long)B * C * n_tiles * n_dchunks;
+    const int grid = (int)std::min<long long>(n_items, (long long)kNumSMs * per_sm);
+    kern<<<grid, NT, smem, st>>>(x, y, cost, B, C, Df, Hf, Wf, R, n_tiles, dchunk, n_dchunks, (int)(ticket.fetch_add(1) % 64u));
+    return check_launch("cost_volume_fwd(tma)");
+}
+
 int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
                     int variant, cudaStream_t st) {
     if (int e = check_cv_args(x, y, cost, B, C, Df, Hf, Wf)) return e;
-    if (variant < 0 || variant > 10) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 32) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
+    if (variant == -1) variant = cv_lean_ok(x, y, cost, Wf) ? RAG_CV_FWD_LEAN : 0;
+    if (variant >= 18) {   // lean thread-stationary kernel, persistent: 18 = 2 CTAs/SM, 19 = 1, 20 = 3, 21 = 4
+        if (!cv_lean_ok(x, y, cost, Wf))
+            return fail(RAG_E_VARIANT, "cost_volume_fwd: lean variants need Wf %% 4 == 0, Wf <= 2048 and 16-byte aligned pointers");
+        // 22-25: 16-disparity chunks per item; 22 = 2 CTAs/SM, 23 = 1, 24 = 4, 25 = one CTA per item (not persistent)
+        // 31 / 32: as 29 with 128 threads x 4 vectors / 512 threads x 1 vector per thread
+        if (variant == 31) return launch_cv_fwd_lean<128, 4>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
+        if (variant == 32) return launch_cv_fwd_lean<512, 1>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
+        // 28-30: persistent with in-order (atomic counter) item hand-out, 16-disparity chunks: 2 / 1 / 4 CTAs per SM
+        if (variant >= 28) return launch_cv_fwd_lean(x, y, cost, B, C, Df, Hf, Wf, variant == 28 ? 2 : variant == 29 ? 1 : 4, 16, st, 0, true);
+        // 26 / 27: as 25 with the shared-memory request padded so that only 1 / 2 CTAs fit an SM
+        if (variant >= 26) return launch_cv_fwd_lean(x, y, cost, B, C, Df, Hf, Wf, 0, 16, st, variant == 26 ? 120 * 1024 : 76 * 1024);
+        if (variant >= 22) return launch_cv_fwd_lean(x, y, cost, B, C, Df, Hf, Wf, variant == 22 ? 2 : variant == 23 ? 1 : variant == 24 ? 4 : 0, 16, st);
+        return launch_cv_fwd_lean(x, y, cost, B, C, Df, Hf, Wf, variant == 18 ? 2 : variant == 19 ? 1 : variant == 20 ? 3 : 4, 0, st);
+    }
+    if (variant >= 11) {   // TMA bulk-store kernel: 11 = R4 x 1 CTA/SM, 12 = R4 x 2, 13 = R2 x 2, 14 = R8 x 1
+        if (!cv_tma_ok(x, y, cost, Df, Wf))
+            return fail(RAG_E_VARIANT, "cost_volume_fwd: TMA variants need Wf %% 4 == 0, Df %% 4 == 0, Df <= Wf and 16-byte aligned pointers");
+        // 15 = R2 x 4 CTAs/SM; 16 / 17 = EXPERIMENTS writing only the right / left half (output incomplete)
+        const int R = (variant == 13 || variant == 15) ? 2 : variant == 14 ? 8 : 4;
+        const int per_sm = variant == 15 ? 4 : (variant == 11 || variant == 14) ? 1 : 2;
+        return launch_cv_fwd_tma(x, y, cost, B, C, Df, Hf, Wf, R, per_sm, variant == 16 ? 1 : variant == 17 ? 2 : 0, st);
+    }
     if (variant >= 8) {   // persistent: exactly 3 (variant 8), 4 (9) or 2 (10) 128-thread CTAs per SM, ~20 KB tiles
         if (!(Wf % 4 == 0 && aligned(x, 16) && aligned(y, 16) && aligned(cost, 16)))
             return fail(RAG_E_VARIANT, "cost_volume_fwd: persistent variants need Wf %% 4 == 0 and 16-byte aligned pointers");

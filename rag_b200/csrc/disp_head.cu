@@ -247,7 +247,7 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
                   int variant, cudaStream_t st) {
     if (!cost || !disp) return fail(RAG_E_NULL, "disp_head_fwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 13) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 16) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
     if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl", variant);
@@ -261,9 +261,13 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
         // spread evenly over the 4 SM sub-partitions: measured 202 us vs 165 us.)
         constexpr int warps = 4;
         dim3 grid((Wl + 31) / 32, (Hl + warps - 1) / warps, B);
-        const size_t smem = (size_t)2 * 16 * (warps + 2) * kTCols * sizeof(float) + ((size_t)18 * 32 * warps + 2 * Dl) * sizeof(float2);
+        size_t smem = (size_t)2 * 16 * (warps + 2) * kTCols * sizeof(float) + ((size_t)18 * 32 * warps + 2 * Dl) * sizeof(float2);
+        if (variant == 14) smem = std::max<size_t>(smem, 58 * 1024);   // 14 / 15 / 16 = as 10, at most 3 / 2 / 1 CTAs per SM (SM sharing)
+        if (variant == 15) smem = std::max<size_t>(smem, 80 * 1024);
+        if (variant == 16) smem = std::max<size_t>(smem, 120 * 1024);
         auto launch = [&](auto kern) -> int {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return fail((int)e, "disp_head_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             kern<<<grid, 32 * warps, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
             return RAG_OK;

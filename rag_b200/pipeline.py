@@ -10,7 +10,50 @@ from __future__ import annotations
 
 import torch
 
+from . import functional as F_
 from .modules import CostVolume, Disp
+
+CV_FWD_SHARED = 32   # include/rag_b200.h RAG_CV_FWD_SHARED
+
+
+class OverlappedPath:
+    """Device-resident schedule of the hot path for a STREAM of batches: the cost volume runs on one
+    CUDA stream and the disparity head on another, so the HBM-bound volume kernel of one batch shares
+    the SMs with the FP32-bound head kernel of another (in the network the Matching Net sits between the
+    two operators of a batch, so what overlaps in deployment is head(batch i) with volume(batch i+1)).
+
+    ``step`` only enqueues; results are ordered on the returned events (or ``join()``).  The volume kernel
+    is launched first with the SM-sharing variant (a persistent grid that is resident at once), which is
+    what lets the head's CTAs be dispatched next to it instead of behind it.
+    """
+
+    def __init__(self, maxdisp: int = 192, device: torch.device | str = "cuda"):
+        self.device = torch.device(device)
+        self.maxdisp = maxdisp
+        self.s_cv = torch.cuda.Stream(self.device)
+        self.s_head = torch.cuda.Stream(self.device)
+
+    def step(self, x: torch.Tensor, y: torch.Tensor, cost_lr: torch.Tensor, want_stats: bool = False):
+        """x, y [B,C,Hf,Wf] and cost_lr [B,1,Dl,Hl,Wl] on the device, ready on the current stream.
+        Returns (cost, disp, stats_or_None); cost is valid on ``self.s_cv``, disp/stats on ``self.s_head``."""
+        cur = torch.cuda.current_stream(self.device)
+        self.s_cv.wait_stream(cur)
+        self.s_head.wait_stream(cur)
+        with torch.no_grad():
+            with torch.cuda.stream(self.s_cv):
+                cost = F_.cost_volume_forward(x, y, int(self.maxdisp / 3), variant=CV_FWD_SHARED if x.shape[-1] % 4 == 0 else None)
+            with torch.cuda.stream(self.s_head):
+                disp, stats = F_.disp_head_forward(cost_lr, self.maxdisp, want_stats=want_stats)
+        for t in (x, y):
+            t.record_stream(self.s_cv)
+        cost_lr.record_stream(self.s_head)
+        return cost, disp, stats
+
+    def join(self):
+        """Make the current stream wait for everything enqueued so far."""
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_stream(self.s_cv)
+        cur.wait_stream(self.s_head)
 
 
 class HostPipeline:

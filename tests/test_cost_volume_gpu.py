@@ -44,6 +44,8 @@ SHAPES = [
     (1, 4, 3, 10, 48),       # Wf < Df
     (3, 1, 1, 4, 3),         # Df = 1
     (1, 12, 33, 64, 100),    # Df = 33 (not a multiple of 4), ragged row tile
+    (2, 5, 11, 36, 48),      # TMA kernel: ragged row tiles (Hf % R != 0), Df = 16
+    (1, 2, 6, 64, 192),      # TMA kernel: Df == Wf (last disparity keeps a single column)
 ]
 
 
@@ -53,7 +55,9 @@ def test_forward_bit_exact(F_, shape):
     g = gen(hash(shape) % 1000)
     x, y = randn((b, c, hf, wf), g), randn((b, c, hf, wf), g)
     ref = O.cost_volume_ref(x, y, md)
-    for variant in (None, 0, 1, 2, 3) + ((4, 8, 9, 10) if wf % 4 == 0 else ()):
+    df = int(md / 3)
+    tma = (11, 12, 13, 14) if (wf % 4 == 0 and df % 4 == 0 and df <= wf) else ()
+    for variant in (None, 0, 1, 2, 3) + ((4, 8, 9, 10, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32) if wf % 4 == 0 else ()) + tma:
         out = F_.cost_volume_forward(x.cuda(), y.cuda(), int(md / 3), variant=variant)
         assert torch.equal(out.cpu(), ref), f"variant {variant}"
 

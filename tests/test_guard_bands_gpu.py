@@ -32,14 +32,14 @@ def st():
     return torch.cuda.current_stream().cuda_stream
 
 
-@pytest.mark.parametrize("shape", [(2, 12, 9, 36, 96), (1, 3, 5, 37, 30), (1, 4, 7, 70, 192), (1, 2, 3, 10, 48), (1, 12, 33, 64, 100)], ids=str)
+@pytest.mark.parametrize("shape", [(2, 12, 9, 36, 96), (1, 3, 5, 37, 30), (1, 4, 7, 70, 192), (1, 2, 3, 10, 48), (1, 12, 33, 64, 100), (1, 3, 9, 64, 192)], ids=str)
 def test_cost_volume_guards(L, shape):
     b, c, hf, wf, md = shape
     df = int(md / 3)
     g = gen(1)
     x, y = randn((b, c, hf, wf), g).cuda(), randn((b, c, hf, wf), g).cuda()
     n = b * 2 * c * df * hf * wf
-    variants = [0, 1, 2, 3] + ([4, 8, 9, 10] if wf % 4 == 0 else [])
+    variants = [0, 1, 2, 3] + ([4, 8, 9, 10, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32] if wf % 4 == 0 else []) + ([11, 12, 13, 14] if (wf % 4 == 0 and df % 4 == 0 and df <= wf) else [])
     for v in variants:
         buf, out = window(n)
         assert L.rag_cost_volume_fwd_v(x.data_ptr(), y.data_ptr(), out.data_ptr(), b, c, df, hf, wf, v, st()) == 0
@@ -64,7 +64,7 @@ def test_head_guards(L, shape):
     cl = randn((b, 1, dl, hl, wl), g).cuda()
     npx = b * 9 * hl * wl
     x3 = md == 3 * dl
-    fv = [0] + ([1, 2, 3] if x3 else []) + ([4, 5, 6, 7, 8, 9, 10, 11, 12, 13] if x3 and wl % 4 == 0 else [])
+    fv = [0] + ([1, 2, 3] if x3 else []) + ([4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14] if x3 and wl % 4 == 0 else [])
     for v in fv:
         bd, disp = window(npx)
         bs, stats = window(2 * npx)

@@ -80,3 +80,49 @@ def test_non_current_device():
     assert (disp.cpu() - O.disp_head_ref(cl, 48)).abs().max().item() <= 1e-4
     with pytest.raises(RuntimeError):
         CostVolume(48)(x.to("cuda:0"), y.to("cuda:1"))
+
+
+def test_overlapped_path_matches_the_serial_modules():
+    """Two-stream schedule (cost volume on one stream, head on another, many steps in flight): every step's
+    outputs are bit-identical to the serial modules', and the persistent cost-volume kernel's work counters
+    rearm themselves launch after launch (a stale counter would leave rows unwritten)."""
+    from rag_b200 import functional as F_
+    from rag_b200.pipeline import OverlappedPath
+
+    g = gen(8)
+    md = 96
+    op = OverlappedPath(md)
+    batches = [(randn((2, 12, 9, 64), g).cuda(), randn((2, 12, 9, 64), g).cuda(), randn((2, 1, 32, 9, 64), g).cuda()) for _ in range(4)]
+    outs = []
+    for rep in range(40):                       # far more launches than counter slots in flight
+        x, y, cl = batches[rep % 4]
+        outs.append(op.step(x, y, cl, want_stats=True))
+    op.join()
+    torch.cuda.synchronize()
+    for rep, (cost, disp, stats) in enumerate(outs):
+        x, y, cl = batches[rep % 4]
+        assert torch.equal(cost, F_.cost_volume_forward(x, y, md // 3, variant=0)), f"step {rep}: volume"
+        d2, s2 = F_.disp_head_forward(cl, md, True)
+        assert torch.equal(disp, d2) and torch.equal(stats, s2), f"step {rep}: head"
+    assert torch.equal(outs[0][0].cpu(), O.cost_volume_ref(batches[0][0].cpu(), batches[0][1].cpu(), md))
+
+
+def test_persistent_cost_volume_under_concurrent_launches():
+    """Launches of the persistent kernel on several streams at once use different counter slots."""
+    from rag_b200 import functional as F_
+
+    g = gen(9)
+    xs = [randn((1, 6, 11, 36), g).cuda() for _ in range(6)]
+    ys = [randn((1, 6, 11, 36), g).cuda() for _ in range(6)]
+    streams = [torch.cuda.Stream() for _ in range(6)]
+    torch.cuda.synchronize()
+    outs = [[] for _ in range(6)]
+    for rep in range(10):
+        for i, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                outs[i].append(F_.cost_volume_forward(xs[i], ys[i], 16))
+    torch.cuda.synchronize()
+    for i in range(6):
+        ref = O.cost_volume_ref(xs[i].cpu(), ys[i].cpu(), 48)
+        for o in outs[i]:
+            assert torch.equal(o.cpu(), ref)

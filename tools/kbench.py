@@ -81,7 +81,7 @@ def main():
         return not a.only or k in a.only.split(",")
 
     if want("cv_fwd"):
-        for v in (0, 8, 9, 10):
+        for v in (0, 29, 32):
             med, best = timeit(lambda: F_.cost_volume_forward(x, y, df, variant=v), a.iters, flush)
             report("cv_fwd", v, med, best, vol_bytes)
         # torch baseline for scale: a plain device copy of the same number of bytes
@@ -120,7 +120,7 @@ def main():
                 report("cost_volume+cudnn_conv3d_bn_relu(tf32=%s)" % tf32, -1, med, best, out_bytes)
             torch.backends.cudnn.allow_tf32 = True
     if want("head_fwd"):
-        for v in (10, 11, 12, 13, 9):
+        for v in (10, 14, 11, 12, 13, 9):
             try:
                 med, best = timeit(lambda: F_.disp_head_forward(cost_lr, md, True, variant=v), a.iters, flush)
                 report("head_fwd", v, med, best, hf_bytes)

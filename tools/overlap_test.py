@@ -14,7 +14,7 @@ from rag_b200 import _cabi
 L = _cabi.lib()
 disp = torch.empty(b, 3 * hf, 3 * wf, device="cuda")
 
-def run(cv_variant, head_first, n=20, overlap=True):
+def run(cv_variant, head_first, n=20, overlap=True, head_variant=-1):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -23,7 +23,7 @@ def run(cv_variant, head_first, n=20, overlap=True):
         def cv():
             L.rag_cost_volume_fwd_v(x.data_ptr(), y.data_ptr(), cost.data_ptr(), b, c, df, hf, wf, cv_variant, (s1 if overlap else torch.cuda.current_stream()).cuda_stream)
         def hd():
-            L.rag_disp_head_fwd(cl.data_ptr(), disp.data_ptr(), None, b, df, hf, wf, md, (s2 if overlap else torch.cuda.current_stream()).cuda_stream)
+            L.rag_disp_head_fwd_v(cl.data_ptr(), disp.data_ptr(), None, b, df, hf, wf, md, head_variant, (s2 if overlap else torch.cuda.current_stream()).cuda_stream)
         if head_first: hd(); cv()
         else: cv(); hd()
     if overlap:
@@ -33,7 +33,9 @@ def run(cv_variant, head_first, n=20, overlap=True):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 
-for cvv in (0, 8, 9, 10):
-    run(cvv, False); run(cvv, True)
-    print(json.dumps({"cv_variant": cvv, "serial_ms": round(run(cvv, False, overlap=False), 4),
-                      "overlap_cv_first_ms": round(run(cvv, False), 4), "overlap_head_first_ms": round(run(cvv, True), 4)}))
+for cvv in (29, 31, 32):
+    for hv in (10, 15, 16):
+        run(cvv, False, head_variant=hv); run(cvv, True, head_variant=hv)
+        print(json.dumps({"cv_variant": cvv, "head_variant": hv, "serial_ms": round(run(cvv, False, overlap=False, head_variant=hv), 4),
+                          "overlap_cv_first_ms": round(run(cvv, False, head_variant=hv), 4),
+                          "overlap_head_first_ms": round(run(cvv, True, head_variant=hv), 4)}), flush=True)
