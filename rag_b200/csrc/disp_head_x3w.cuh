@@ -25,7 +25,7 @@ constexpr int kBwBins = kBwJ + 2;        // low-res bins a task reads
 constexpr int kBwCols = 34;              // window width: 32 block columns + 1 + pad
 constexpr int kBwWin = kBwBins * 2 * kBwCols;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gdisp, const float* __restrict__ disp,
                     const float* __restrict__ stats, float* __restrict__ gcost, float* __restrict__ scratch,
                     int Dl, int Hl, int Wl, float scale, int nJ, int n_tasks) {
@@ -185,7 +185,8 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
     float* ga = gout + (size_t)j0 * plane + (size_t)max(rb, 0) * Wl + c;
     float* gb = sout + (size_t)j0 * plane + (size_t)min(rb + 1, Hl - 1) * Wl + c;
     const bool st_a = store_lane && has_a, st_b = store_lane && has_b;
-    float pA = 0.f, pB = 0.f;        // "B" bin part of the previous k-block (cell jb), split by row part
+    float2 pg[4] = {f2b(0.f), f2b(0.f), f2b(0.f), f2b(0.f)};   // "B" bin part of the previous k-block, per pixel
+    float pgS = 0.f;
     const float2 one = f2b(1.f), two = f2b(2.f), neg1 = f2b(-1.f);
     float kf = (float)(3 * jb0 + 1);
 
@@ -235,17 +236,21 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
             s0iS = 0.f;
         }
         kf += 3.f;
-        float v0A, v0B, v1A, v1B;
-        transpose(g0, g0S, v0A, v0B);
-        transpose(g1, g1S, v1A, v1B);
+        // cell jb = this k-block's "A" bin part + the previous k-block's "B" bin part: the spatial transpose is
+        // linear, so the two parts are added per pixel first and transposed ONCE
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g0[i] = add2(g0[i], pg[i]);
+        g0S += pgS;
         if (jb >= j0) {
-            // cell jb: own k-block's A bin part + previous k-block's B bin part
-            if (st_a) *ga = v0A + pA;
-            if (st_b) *gb = v0B + pB;
+            float vA, vB;
+            transpose(g0, g0S, vA, vB);
+            if (st_a) *ga = vA;
+            if (st_b) *gb = vB;
             ga += plane; gb += plane;
         }
-        pA = v1A;
-        pB = v1B;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pg[i] = g1[i];
+        pgS = g1S;
     }
 }
 
