@@ -1,9 +1,9 @@
-"""Own error of the head-forward variants vs the fp64 evaluation of the reference formula (test-side tool:
+"""Own error of the head-forward variants vs the fp64 evaluation of the reference formula (test infrastructure, lives under tests/ because it
 imports the oracle).  usage: own_error.py [v ...]"""
 import os, sys
 import numpy as np
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # tests/ -> repo root
 sys.path.insert(0, ROOT)
 from rag_b200 import functional as F_
 from oracle import rag_oracle as O
