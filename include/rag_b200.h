@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RAG_B200_ABI_VERSION 5
+#define RAG_B200_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
@@ -137,6 +137,14 @@ RAG_API int rag_cv_stem_fwd(const float* x, const float* y, const float* w, cons
                     int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, void* stream);
 RAG_API int rag_cv_stem_fwd_v(const float* x, const float* y, const float* w, const float* scale, const float* shift,
                       int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, int variant, void* stream);
+
+/* The Matching Net's last layer, the producer of the head's input (inference):
+ * `self.last_3_3d[i](...)` = ConvBR_3d(C, 1, 3, 1, 1, bn=False, relu=False), src/models/rag_model.py:269,361-365,
+ * i.e. a bias-free Conv3d C -> 1, 3x3x3, stride 1, zero padding 1 (src/automl/operations_3d.py:31-47):
+ *   out[b,0,d,h,w] = sum_{c,kd,kh,kw} w[0,c,kd,kh,kw] * in[b,c,d+kd-1,h+kh-1,w+kw-1]
+ * in [B,C,D,H,W]; w [1,C,3,3,3] (Conv3d.weight); out [B,1,D,H,W].  fp32 accumulation (cuDNN's default for
+ * this layer is TF32).  Needs W % 4 == 0 and 16-byte aligned in/out.  Forward only. */
+RAG_API int rag_conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int D, int H, int W, void* stream);
 
 /* Eval-time input staging: uint8 HWC image -> ImageNet-normalised fp32 CHW, zero-padded on the
  * top and right.  Replaces src/dataloaders/data_io.py:6-13 + stereo_dataset.py:88-102.

@@ -17,6 +17,7 @@ int loss_metrics_sums(const float*, const float*, double*, double*, int, int, in
 int smooth_l1_bwd(const float*, const float*, const double*, const float*, float*, int, int, int, float, cudaStream_t);
 int normalize_pad(const uint8_t*, float*, int, int, int, int, int, cudaStream_t);
 int cv_stem_fwd(const float*, const float*, const float*, const float*, const float*, int, float*, int, int, int, int, int, int, int, cudaStream_t);
+int conv3d_c1_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 }  // namespace rag
 
 using namespace rag;
@@ -86,6 +87,9 @@ RAG_API int rag_cv_stem_fwd(const float* x, const float* y, const float* w, cons
 RAG_API int rag_cv_stem_fwd_v(const float* x, const float* y, const float* w, const float* scale, const float* shift,
                       int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, int variant, void* stream) {
     return cv_stem_fwd(x, y, w, scale, shift, relu, out, B, C, O, Df, Hf, Wf, variant, ST(stream));
+}
+RAG_API int rag_conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int D, int H, int W, void* stream) {
+    return conv3d_c1_fwd(in, w, out, B, C, D, H, W, ST(stream));
 }
 RAG_API int rag_normalize_pad(const uint8_t* img, float* out, int B, int H, int W, int top_pad, int right_pad, void* stream) {
     return normalize_pad(img, out, B, H, W, top_pad, right_pad, ST(stream));

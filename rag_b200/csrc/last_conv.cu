@@ -1,0 +1,152 @@
+// `last_3_3d`: the Matching Net's last layer, the producer of the disparity head's input (SURVEY.md
+// section 8f rank 2).  Reference: src/models/rag_model.py:269 `ConvBR_3d(initial_fm, 1, 3, 1, 1, bn=False,
+// relu=False)` applied at :361-365 -> a bias-free Conv3d C -> 1, 3x3x3, stride 1, zero padding 1:
+//     out[b,0,d,h,w] = sum_{c,kd,kh,kw} W[0,c,kd,kh,kw] * in[b,c,d+kd-1,h+kh-1,w+kw-1]
+// Through cuDNN this layer costs 6.6 ms (TF32) / 32 ms (fp32) per 8 pairs at 480x960 on a B200 (one output
+// channel wastes a tensor-core tile); its floors are 0.19 ms of HBM (read the 1.26 GB input once) and 0.23 ms
+// of FP32 (8.5 GFMA at 128 lanes/clk/SM), so it is written here as a register-tiled fp32 direct convolution.
+//
+// A CTA owns a 16 x 8 x 64 (d,h,w) output tile of one pair and walks the C input channels; the channel's
+// 18 x 10 x 72 input tile (halo included, zero-filled outside the volume by cp.async zfill) is double-buffered
+// in shared memory.  A thread owns 4 (d) x 8 (w) outputs of one h: per input row (d', h') it loads the ten
+// inputs it needs (two LDS.128 + two LDS.32) and does up to 72 FFMAs with the channel's 27 weights held in
+// registers: 864 FFMA against ~115 other instructions per channel.
+// Fusing this layer INTO the head kernel was rejected: the head's CTA window has a (6/4)x(40/32) halo, so the
+// 324-MAC convolution would be recomputed 1.9x; instead the 105 MB result stays L2-resident (126 MB L2) for
+// the head that runs next.
+#include <cuda_pipeline.h>
+
+#include "common.cuh"
+
+namespace rag {
+
+constexpr int kLcDT = 16, kLcHT = 8, kLcWT = 64;            // output tile
+constexpr int kLcSD = kLcDT + 2, kLcSH = kLcHT + 2, kLcSW = kLcWT + 8;   // staged tile: w in [w0-4, w0+68)
+constexpr int kLcStage = kLcSD * kLcSH * kLcSW;             // floats per stage (12960)
+constexpr int kLcVecs = kLcStage / 4;                       // 16-byte vectors per stage (3240)
+constexpr int kLcSlots = (kLcVecs + 255) / 256;             // per-thread staging slots (13)
+
+// grid: x = ceil(W/64), y = ceil(H/8), z = B * ceil(D/16); 256 threads.
+// smem: 2 stages x kLcStage floats | weights [C][3][3][4]
+__global__ void __launch_bounds__(256, 2)
+conv3d_c1_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
+                 int C, int D, int H, int W, int n_dt) {
+    extern __shared__ __align__(16) float lc_smem[];
+    float* wsm = lc_smem + 2 * kLcStage;
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z / n_dt, dt = blockIdx.z - b * n_dt;
+    const int d0 = dt * kLcDT, h0 = blockIdx.y * kLcHT, w0 = blockIdx.x * kLcWT;
+    const size_t chan = (size_t)D * H * W;
+    const float* inb = in + (size_t)b * C * chan;
+
+    // staging slots: vector v of the stage <-> (d', h', 4 consecutive w); source offset inside a channel or -1
+    int goff[kLcSlots];
+#pragma unroll
+    for (int i = 0; i < kLcSlots; ++i) {
+        const int v = tid + i * 256;
+        const int row = v / (kLcSW / 4), vec = v - row * (kLcSW / 4);
+        const int dz = row / kLcSH, hy = row - dz * kLcSH;
+        const int gd = d0 - 1 + dz, gh = h0 - 1 + hy, gw = w0 - 4 + 4 * vec;
+        const bool ok = v < kLcVecs && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W;   // W % 4 == 0
+        goff[i] = ok ? (gd * H + gh) * W + gw : -1;
+    }
+    auto issue = [&](int c, int stage) {
+        if (c < C) {
+            const float* src = inb + (size_t)c * chan;
+            float* dst = lc_smem + stage * kLcStage + 4 * tid;
+#pragma unroll
+            for (int i = 0; i < kLcSlots; ++i) {
+                if (tid + i * 256 < kLcVecs) {
+                    const bool ok = goff[i] >= 0;
+                    __pipeline_memcpy_async(dst + i * 1024, ok ? src + goff[i] : src, 16, ok ? 0 : 16);   // zero fill outside
+                }
+            }
+        }
+        __pipeline_commit();
+    };
+    issue(0, 0);
+    for (int i = tid; i < C * 36; i += 256) {                // [c][kd][kh][4]: kw padded to 4
+        const int kw = i & 3, r = i >> 2;                    // r = (c*3 + kd)*3 + kh
+        wsm[i] = kw < 3 ? __ldg(w + r * 3 + kw) : 0.f;
+    }
+
+    // thread geometry: 4 d-groups x 8 h rows x 8 w-groups
+    const int tw = tid & 7, th = (tid >> 3) & 7, td = tid >> 6;
+    float acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
+    // first input needed by the thread: tile (d' = 4 td, h' = th, col = 8 tw + 3)  <->  (d0+4td-1, h0+th-1, w0+8tw-1)
+    const int toff = ((4 * td) * kLcSH + th) * kLcSW + 8 * tw;
+
+    for (int c = 0; c < C; ++c) {
+        issue(c + 1, (c + 1) & 1);
+        __pipeline_wait_prior(1);
+        __syncthreads();
+        const float* st = lc_smem + (c & 1) * kLcStage + toff;
+        float wr[3][3][3];
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const float4 q = *reinterpret_cast<const float4*>(wsm + ((c * 3 + kd) * 3 + kh) * 4);
+                wr[kd][kh][0] = q.x; wr[kd][kh][1] = q.y; wr[kd][kh][2] = q.z;
+            }
+#pragma unroll
+        for (int dz = 0; dz < 6; ++dz) {
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+                const float* p = st + (dz * kLcSH + kh) * kLcSW;
+                float v[10];
+                v[0] = p[3];
+                const float4 m0 = *reinterpret_cast<const float4*>(p + 4);
+                const float4 m1 = *reinterpret_cast<const float4*>(p + 8);
+                v[1] = m0.x; v[2] = m0.y; v[3] = m0.z; v[4] = m0.w;
+                v[5] = m1.x; v[6] = m1.y; v[7] = m1.z; v[8] = m1.w;
+                v[9] = p[12];
+#pragma unroll
+                for (int kd = 0; kd < 3; ++kd) {
+                    const int od = dz - kd;                  // output d (tile-local, within the thread's 4) fed by this row
+                    if (od < 0 || od > 3) continue;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        acc[od][i] = __fmaf_rn(wr[kd][kh][2], v[i + 2], __fmaf_rn(wr[kd][kh][1], v[i + 1], __fmaf_rn(wr[kd][kh][0], v[i], acc[od][i])));
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    const int h = h0 + th, wo = w0 + 8 * tw;
+    if (h < H && wo < W) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const int d = d0 + 4 * td + a;
+            if (d < D) {
+                float* o = out + (((size_t)b * D + d) * H + h) * W + wo;
+                reinterpret_cast<float4*>(o)[0] = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+                if (wo + 4 < W) reinterpret_cast<float4*>(o)[1] = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+            }
+        }
+    }
+}
+
+int conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int D, int H, int W, cudaStream_t st) {
+    if (!in || !w || !out) return fail(RAG_E_NULL, "conv3d_c1_fwd: null pointer");
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: non-positive dimension");
+    if (W % 4 != 0) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: W=%d must be a multiple of 4", W);
+    if ((size_t)D * H * W >= ((size_t)1 << 31)) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: D*H*W must be < 2^31");
+    if (C > 256) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: C=%d too large for the shared-memory weight table", C);
+    if (!aligned(in, 16) || !aligned(out, 16) || !aligned(w, 4)) return fail(RAG_E_ALIGN, "conv3d_c1_fwd: in/out must be 16-byte aligned");
+    const int n_dt = (D + kLcDT - 1) / kLcDT;
+    if ((long long)B * n_dt > 65535) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: B*ceil(D/16) must be <= 65535");
+    const size_t smem = ((size_t)2 * kLcStage + (size_t)C * 36) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(conv3d_c1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    dim3 grid((W + kLcWT - 1) / kLcWT, (H + kLcHT - 1) / kLcHT, B * n_dt);
+    conv3d_c1_kernel<<<grid, 256, smem, st>>>(in, w, out, C, D, H, W, n_dt);
+    return check_launch("conv3d_c1_fwd");
+}
+
+}  // namespace rag

@@ -20,6 +20,7 @@ import torch.nn.functional as F
 
 from . import _cabi
 from .functional import _require, _stream, cost_volume
+from .last_conv import conv_forward
 
 
 class VirtualCostVolume:
@@ -75,7 +76,7 @@ def _fusable(conv: nn.Conv3d, vol: VirtualCostVolume) -> bool:
 def stem_forward(self, x):
     """Replacement for ConvBR_3d.forward (operations_3d.py:41-47).  ``self`` has .conv, .bn, .use_bn, .relu."""
     if not isinstance(x, VirtualCostVolume):
-        x = self.conv(x)
+        x = conv_forward(self.conv, x)     # last_3_3d (C -> 1, inference) takes the hand-written kernel, the rest cuDNN
         if self.use_bn:
             x = self.bn(x)
         if self.relu:

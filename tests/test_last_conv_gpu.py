@@ -1,0 +1,92 @@
+"""the Matching Net's last layer (Conv3d C -> 1, 3x3x3) on the hand-written kernel."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests._util import gen, randn
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # (B, C, D, H, W)
+    (1, 12, 64, 16, 64),      # the layer's real depth/channels, one w tile
+    (2, 12, 20, 9, 68),       # ragged d / h / w tiles (W % 64 != 0, H % 8 != 0, D % 16 != 0)
+    (1, 3, 5, 3, 4),          # smaller than one tile in every axis
+    (1, 12, 17, 8, 132),      # two-and-a-bit w tiles, d tile boundary at 16
+    (1, 24, 33, 11, 200),     # another channel count
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=str)
+def test_conv3d_c1_matches_fp32_reference(shape):
+    from rag_b200.last_conv import conv3d_c1_forward
+
+    b, c, d, h, w = shape
+    g = gen(sum(shape))
+    x = randn((b, c, d, h, w), g)
+    wt = randn((1, c, 3, 3, 3), g) * 0.1
+    ref = F.conv3d(x.double(), wt.double(), padding=1)            # CPU fp64: the exact value of the reference's formula
+    ref32 = F.conv3d(x, wt, padding=1)                            # CPU fp32: the reference's own arithmetic
+    out = conv3d_c1_forward(x.cuda(), wt.cuda()).cpu()
+    scale = ref.abs().max().item()
+    assert (out.double() - ref).abs().max().item() <= 2e-6 * scale
+    assert (out - ref32).abs().max().item() <= 4e-6 * scale
+    # zero padding really is zero: an input that is non-zero only on the border planes
+    xb = torch.zeros_like(x)
+    xb[:, :, 0], xb[:, :, -1], xb[:, :, :, 0], xb[:, :, :, -1], xb[..., 0], xb[..., -1] = 1, 1, 1, 1, 1, 1
+    outb = conv3d_c1_forward(xb.cuda(), wt.cuda()).cpu()
+    assert (outb - F.conv3d(xb, wt, padding=1)).abs().max().item() <= 4e-6 * max(1.0, wt.abs().sum().item())
+
+
+def test_convbr_dropin_and_fallbacks():
+    """ConvBR_3d(C, 1, 3, 1, 1, bn=False, relu=False) through the patched forward: kernel under no_grad, the
+    reference's nn.Conv3d whenever a gradient is wanted or the layer is not the 1-output-channel one."""
+    import torch.nn as nn
+
+    from rag_b200 import _cabi
+    from rag_b200.fused_stem import stem_forward
+    from rag_b200.last_conv import qualifies
+
+    class ConvBR_3d(nn.Module):          # mirror of src/automl/operations_3d.py:31-47
+        def __init__(self, cin, cout, k, s, p, bn=True, relu=True):
+            super().__init__()
+            self.relu, self.use_bn = relu, bn
+            self.conv = nn.Conv3d(cin, cout, k, stride=s, padding=p, bias=False)
+            self.bn = nn.BatchNorm3d(cout)
+
+        forward = stem_forward
+
+    g = gen(3)
+    last = ConvBR_3d(12, 1, 3, 1, 1, bn=False, relu=False).cuda()
+    x = randn((1, 12, 16, 8, 64), g).cuda()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        n0 = _cabi.launch_count()
+        with torch.no_grad():
+            y = last(x)
+        assert _cabi.launch_count() == n0 + 1                       # the hand-written kernel ran
+        ref = last.conv(x)
+        assert (y - ref).abs().max().item() <= 4e-6 * ref.abs().max().item()
+        n0 = _cabi.launch_count()
+        yg = last(x.requires_grad_(True))                           # gradient wanted -> reference path
+        assert _cabi.launch_count() == n0 and yg.requires_grad
+        yg.sum().backward()
+        assert last.conv.weight.grad is not None
+        other = ConvBR_3d(12, 12, 3, 1, 1).cuda().eval()
+        with torch.no_grad():
+            assert not qualifies(other.conv, x)
+            other(x.detach())
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_errors_are_loud():
+    from rag_b200.last_conv import conv3d_c1_forward
+
+    with pytest.raises(RuntimeError):
+        conv3d_c1_forward(torch.zeros(1, 4, 4, 4, 6, device="cuda"), torch.zeros(1, 4, 3, 3, 3, device="cuda"))   # W % 4 != 0
+    with pytest.raises(RuntimeError):
+        conv3d_c1_forward(torch.zeros(1, 4, 4, 4, 8), torch.zeros(1, 4, 3, 3, 3))                                  # CPU tensors
+    with pytest.raises(RuntimeError):
+        conv3d_c1_forward(torch.zeros(1, 4, 4, 4, 8, device="cuda"), torch.zeros(2, 4, 3, 3, 3, device="cuda"))   # not 1 output channel

@@ -119,6 +119,21 @@ def main():
                 med, best = timeit(lambda: torch.relu_(bn(conv(F_.cost_volume_forward(x, y, df)))), 3, flush)
                 report("cost_volume+cudnn_conv3d_bn_relu(tf32=%s)" % tf32, -1, med, best, out_bytes)
             torch.backends.cudnn.allow_tf32 = True
+    if want("last_conv"):
+        from rag_b200.last_conv import conv3d_c1_forward
+        feat = torch.randn(b, 12, df, hf, wf, device=dev, generator=g)
+        wl = torch.randn(1, 12, 3, 3, 3, device=dev, generator=g) * 0.1
+        lc_bytes = 4 * (12 + 1) * df * hf * wf * b
+        med, best = timeit(lambda: conv3d_c1_forward(feat, wl), a.iters, flush)
+        report("last_3_3d conv (12->1, fp32)", 0, med, best, lc_bytes)
+        conv = torch.nn.Conv3d(12, 1, 3, padding=1, bias=False).to(dev)
+        with torch.no_grad():
+            for tf32 in (True, False):
+                torch.backends.cudnn.allow_tf32 = tf32
+                med, best = timeit(lambda: conv(feat), 3, flush)
+                report("cudnn_conv3d_12to1(tf32=%s)" % tf32, -1, med, best, lc_bytes)
+            torch.backends.cudnn.allow_tf32 = True
+        del feat
     if want("head_fwd"):
         for v in (10, 14, 11, 12, 13, 9):
             try:
