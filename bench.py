@@ -188,10 +188,23 @@ def fused_stem_row(x, y, df, md, sub):
         b_ = torch.relu_(bn(conv(F_.cost_volume_forward(xs[:1], ys[:1], df))))
         torch.backends.cudnn.allow_tf32 = old
         err = ((a - b_).abs().max() / b_.abs().max()).item()
+        # rank 2: last_3_3d (Conv3d C -> 1, 3x3x3), the producer of the head's input
+        from rag_b200.last_conv import conv3d_c1_forward
+        feat = torch.randn(sub, c, df, x.shape[2], x.shape[3], device=dev, generator=g)
+        last = torch.nn.Conv3d(c, 1, 3, padding=1, bias=False).to(dev)
+        lc = t(lambda: conv3d_c1_forward(feat, last.weight), 10)
+        lc_ref = t(lambda: last(feat), 3)
+        torch.backends.cudnn.allow_tf32 = False
+        lc_err = ((conv3d_c1_forward(feat[:1], last.weight) - last(feat[:1])).abs().max() / last(feat[:1]).abs().max()).item()
+        torch.backends.cudnn.allow_tf32 = old
+        del feat
     torch.cuda.empty_cache()
-    return {"what": "cost volume + stem3d0 (Conv3d 24->12 3x3x3 + BN(eval) + ReLU), %d pairs" % sub,
-            "fused_ms": round(fused, 4), "cost_volume_plus_cudnn_tf32_ms": round(ref, 4), "speedup": round(ref / fused, 1),
-            "max_rel_err_vs_fp32_cudnn": err}
+    return {"stem3d0": {"what": "cost volume + stem3d0 (Conv3d 24->12 3x3x3 + BN(eval) + ReLU), %d pairs" % sub,
+                        "fused_ms": round(fused, 4), "cost_volume_plus_cudnn_tf32_ms": round(ref, 4), "speedup": round(ref / fused, 1),
+                        "max_rel_err_vs_fp32_cudnn": err},
+            "last_3_3d": {"what": "last_3_3d (Conv3d %d->1 3x3x3, fp32 direct convolution), %d pairs" % (c, sub),
+                          "ms": round(lc, 4), "cudnn_tf32_ms": round(lc_ref, 4), "speedup": round(lc_ref / lc, 1),
+                          "max_rel_err_vs_fp32_cudnn": lc_err}}
 
 
 def run_reference(args):

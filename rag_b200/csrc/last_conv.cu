@@ -7,10 +7,10 @@
 // of FP32 (8.5 GFMA at 128 lanes/clk/SM), so it is written here as a register-tiled fp32 direct convolution.
 //
 // A CTA owns a 16 x 8 x 64 (d,h,w) output tile of one pair and walks the C input channels; the channel's
-// 18 x 10 x 72 input tile (halo included, zero-filled outside the volume by cp.async zfill) is double-buffered
-// in shared memory.  A thread owns 4 (d) x 8 (w) outputs of one h: per input row (d', h') it loads the ten
-// inputs it needs (two LDS.128 + two LDS.32) and does up to 72 FFMAs with the channel's 27 weights held in
-// registers: 864 FFMA against ~115 other instructions per channel.
+// 18 x 10 x 72 input tile (halo included, zero-filled outside the volume by cp.async zfill) is staged in
+// shared memory (one stage; the three resident CTAs of an SM cover each other's copies).  A thread owns 4 (d) x 8 (w) outputs of one h: per input row (d', h') it gets the ten
+// inputs it needs from two conflict-free LDS.128 plus two warp shuffles (the neighbours' edge elements) and
+// does up to 72 FFMAs with the channel's 27 weights held in registers: 864 FFMA per channel.
 // Fusing this layer INTO the head kernel was rejected: the head's CTA window has a (6/4)x(40/32) halo, so the
 // 324-MAC convolution would be recomputed 1.9x; instead the 105 MB result stays L2-resident (126 MB L2) for
 // the head that runs next.
@@ -21,50 +21,58 @@
 namespace rag {
 
 constexpr int kLcDT = 16, kLcHT = 8, kLcWT = 64;            // output tile
-constexpr int kLcSD = kLcDT + 2, kLcSH = kLcHT + 2, kLcSW = kLcWT + 8;   // staged tile: w in [w0-4, w0+68)
-constexpr int kLcStage = kLcSD * kLcSH * kLcSW;             // floats per stage (12960)
-constexpr int kLcVecs = kLcStage / 4;                       // 16-byte vectors per stage (3240)
-constexpr int kLcSlots = (kLcVecs + 255) / 256;             // per-thread staging slots (13)
+constexpr int kLcSD = kLcDT + 2, kLcSH = kLcHT + 2;        // staged tile: d in [d0-1, d0+17), h in [h0-1, h0+9)
+constexpr int kLcRowVecs = (kLcWT + 8) / 4;                 // ... w in [w0-4, w0+68): 18 vectors per row
+// Shared-memory rows are SKEWED: 4 floats of padding after every 32, so that the eight 8-float segments of
+// a row start in distinct bank groups and the threads' LDS.128 are conflict-free (unskewed: 2-way).
+constexpr int kLcSW = kLcWT + 8 + 8;                        // row stride (80 floats)
+__host__ __device__ constexpr int lc_skew(int col) { return col + 4 * (col >> 5); }
+constexpr int kLcRows = kLcSD * kLcSH;                      // 180 rows per stage
+constexpr int kLcStage = kLcRows * kLcSW;                   // floats per stage (14400)
+constexpr int kLcRowGroups = 256 / kLcRowVecs;              // 14 rows staged per pass (252 of 256 threads)
+constexpr int kLcSlots = (kLcRows + kLcRowGroups - 1) / kLcRowGroups;   // 13 passes
 
 // grid: x = ceil(W/64), y = ceil(H/8), z = B * ceil(D/16); 256 threads.
-// smem: 2 stages x kLcStage floats | weights [C][3][3][4]
-__global__ void __launch_bounds__(256, 2)
+// smem: STAGES x kLcStage floats | weights [C][3][3][4]
+template <int STAGES>
+__global__ void __launch_bounds__(256, STAGES == 1 ? 3 : 1)
 conv3d_c1_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
                  int C, int D, int H, int W, int n_dt) {
     extern __shared__ __align__(16) float lc_smem[];
-    float* wsm = lc_smem + 2 * kLcStage;
+    float* wsm = lc_smem + STAGES * kLcStage;
     const int tid = threadIdx.x;
     const int b = blockIdx.z / n_dt, dt = blockIdx.z - b * n_dt;
     const int d0 = dt * kLcDT, h0 = blockIdx.y * kLcHT, w0 = blockIdx.x * kLcWT;
     const size_t chan = (size_t)D * H * W;
     const float* inb = in + (size_t)b * C * chan;
 
-    // staging slots: vector v of the stage <-> (d', h', 4 consecutive w); source offset inside a channel or -1
+    // staging: a thread copies vector `svec` of rows srow0, srow0 + 14, ... (source offset inside a channel, or -1)
+    const int srow0 = tid / kLcRowVecs, svec = tid - srow0 * kLcRowVecs;
+    const bool stager = srow0 < kLcRowGroups;
     int goff[kLcSlots];
 #pragma unroll
     for (int i = 0; i < kLcSlots; ++i) {
-        const int v = tid + i * 256;
-        const int row = v / (kLcSW / 4), vec = v - row * (kLcSW / 4);
+        const int row = srow0 + i * kLcRowGroups;
         const int dz = row / kLcSH, hy = row - dz * kLcSH;
-        const int gd = d0 - 1 + dz, gh = h0 - 1 + hy, gw = w0 - 4 + 4 * vec;
-        const bool ok = v < kLcVecs && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W;   // W % 4 == 0
+        const int gd = d0 - 1 + dz, gh = h0 - 1 + hy, gw = w0 - 4 + 4 * svec;
+        const bool ok = stager && row < kLcRows && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W;   // W % 4 == 0
         goff[i] = ok ? (gd * H + gh) * W + gw : -1;
     }
     auto issue = [&](int c, int stage) {
-        if (c < C) {
+        if (c < C && stager) {
             const float* src = inb + (size_t)c * chan;
-            float* dst = lc_smem + stage * kLcStage + 4 * tid;
+            float* dst = lc_smem + stage * kLcStage + srow0 * kLcSW + lc_skew(4 * svec);
 #pragma unroll
             for (int i = 0; i < kLcSlots; ++i) {
-                if (tid + i * 256 < kLcVecs) {
+                if (srow0 + i * kLcRowGroups < kLcRows) {
                     const bool ok = goff[i] >= 0;
-                    __pipeline_memcpy_async(dst + i * 1024, ok ? src + goff[i] : src, 16, ok ? 0 : 16);   // zero fill outside
+                    __pipeline_memcpy_async(dst + i * kLcRowGroups * kLcSW, ok ? src + goff[i] : src, 16, ok ? 0 : 16);   // zero fill outside
                 }
             }
         }
         __pipeline_commit();
     };
-    issue(0, 0);
+    if (STAGES == 2) issue(0, 0);
     for (int i = tid; i < C * 36; i += 256) {                // [c][kd][kh][4]: kw padded to 4
         const int kw = i & 3, r = i >> 2;                    // r = (c*3 + kd)*3 + kh
         wsm[i] = kw < 3 ? __ldg(w + r * 3 + kw) : 0.f;
@@ -77,14 +85,23 @@ conv3d_c1_kernel(const float* __restrict__ in, const float* __restrict__ w, floa
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
-    // first input needed by the thread: tile (d' = 4 td, h' = th, col = 8 tw + 3)  <->  (d0+4td-1, h0+th-1, w0+8tw-1)
-    const int toff = ((4 * td) * kLcSH + th) * kLcSW + 8 * tw;
+    // the thread's ten inputs of a row are tile columns 8tw+3 .. 8tw+12: two aligned vectors (8tw+4, 8tw+8), the
+    // neighbours' edge elements by shuffle, and for the two lanes at the ends of the 64-column strip one scalar
+    const int toff = ((4 * td) * kLcSH + th) * kLcSW;
+    const int c0 = lc_skew(8 * tw + 4), c1 = lc_skew(8 * tw + 8);
+    const bool edge = tw == 0 || tw == 7;
+    const int ce = tw == 0 ? lc_skew(3) : lc_skew(68);
 
     for (int c = 0; c < C; ++c) {
-        issue(c + 1, (c + 1) & 1);
-        __pipeline_wait_prior(1);
+        if (STAGES == 2) {
+            issue(c + 1, (c + 1) & 1);
+            __pipeline_wait_prior(1);
+        } else {
+            issue(c, 0);                                  // single stage: the other CTAs of the SM cover the copy
+            __pipeline_wait_prior(0);
+        }
         __syncthreads();
-        const float* st = lc_smem + (c & 1) * kLcStage + toff;
+        const float* st = lc_smem + (STAGES == 2 ? (c & 1) : 0) * kLcStage + toff;
         float wr[3][3][3];
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd)
@@ -99,12 +116,15 @@ conv3d_c1_kernel(const float* __restrict__ in, const float* __restrict__ w, floa
             for (int kh = 0; kh < 3; ++kh) {
                 const float* p = st + (dz * kLcSH + kh) * kLcSW;
                 float v[10];
-                v[0] = p[3];
-                const float4 m0 = *reinterpret_cast<const float4*>(p + 4);
-                const float4 m1 = *reinterpret_cast<const float4*>(p + 8);
+                const float4 m0 = *reinterpret_cast<const float4*>(p + c0);
+                const float4 m1 = *reinterpret_cast<const float4*>(p + c1);
+                const float e = edge ? p[ce] : 0.f;
+                const float lft = __shfl_up_sync(0xffffffffu, m1.w, 1, 8);     // column 8tw+3 = the left neighbour's last
+                const float rgt = __shfl_down_sync(0xffffffffu, m0.x, 1, 8);   // column 8tw+12 = the right neighbour's first
+                v[0] = tw == 0 ? e : lft;
                 v[1] = m0.x; v[2] = m0.y; v[3] = m0.z; v[4] = m0.w;
                 v[5] = m1.x; v[6] = m1.y; v[7] = m1.z; v[8] = m1.w;
-                v[9] = p[12];
+                v[9] = tw == 7 ? e : rgt;
 #pragma unroll
                 for (int kd = 0; kd < 3; ++kd) {
                     const int od = dz - kd;                  // output d (tile-local, within the thread's 4) fed by this row
@@ -141,11 +161,15 @@ int conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int
     if (!aligned(in, 16) || !aligned(out, 16) || !aligned(w, 4)) return fail(RAG_E_ALIGN, "conv3d_c1_fwd: in/out must be 16-byte aligned");
     const int n_dt = (D + kLcDT - 1) / kLcDT;
     if ((long long)B * n_dt > 65535) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: B*ceil(D/16) must be <= 65535");
-    const size_t smem = ((size_t)2 * kLcStage + (size_t)C * 36) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(conv3d_c1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // one 57.6 KB stage: 3 CTAs per SM cover each other's copies (0.565 ms at B=8 480x960); a double-buffered
+    // CTA fits only once per SM and is slower (0.735 ms)
+    constexpr int stages = 1;
+    const size_t smem = ((size_t)stages * kLcStage + (size_t)C * 36) * sizeof(float);
+    auto kern = conv3d_c1_kernel<stages>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     dim3 grid((W + kLcWT - 1) / kLcWT, (H + kLcHT - 1) / kLcHT, B * n_dt);
-    conv3d_c1_kernel<<<grid, 256, smem, st>>>(in, w, out, C, D, H, W, n_dt);
+    kern<<<grid, 256, smem, st>>>(in, w, out, C, D, H, W, n_dt);
     return check_launch("conv3d_c1_fwd");
 }
 

@@ -126,3 +126,17 @@ def test_misc_guards(L):
     torch.cuda.synchronize()
     assert intact(bs, b * 8) and intact(bc, b * nscr) and intact(bg, b * h * w) and intact(bo, 2 * 3 * 12 * 18)
     assert intact(br, 70) and intact(bp, 2 * 24 * 35)
+
+
+@pytest.mark.parametrize("shape", [(1, 12, 17, 9, 68), (2, 3, 5, 3, 4), (1, 12, 32, 8, 64)], ids=str)
+def test_last_conv_guards(L, shape):
+    b, c, d, h, w = shape
+    g = gen(4)
+    x = randn((b, c, d, h, w), g).cuda()
+    wt = randn((1, c, 3, 3, 3), g).cuda()
+    n = b * d * h * w
+    buf, out = window(n)
+    assert L.rag_conv3d_c1_fwd(x.data_ptr(), wt.data_ptr(), out.data_ptr(), b, c, d, h, w, st()) == 0
+    torch.cuda.synchronize()
+    assert intact(buf, n), "conv3d_c1 wrote out of bounds"
+    assert not (out == CANARY).any(), "conv3d_c1 left output elements unwritten"
