@@ -47,6 +47,11 @@ class OverlappedPath:
         for t in (x, y):
             t.record_stream(self.s_cv)
         cost_lr.record_stream(self.s_head)
+        # the outputs live in the side streams' allocator pools but are consumed on the caller's stream (after
+        # join()): tell the caching allocator, so a freed block is not recycled under a running consumer
+        for t in (cost, disp, stats):
+            if t is not None:
+                t.record_stream(cur)
         return cost, disp, stats
 
     def join(self):
