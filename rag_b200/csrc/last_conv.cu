@@ -29,24 +29,32 @@ constexpr int kLcSW = kLcWT + 8 + 8;                        // row stride (80 fl
 __host__ __device__ constexpr int lc_skew(int col) { return col + 4 * (col >> 5); }
 constexpr int kLcRows = kLcSD * kLcSH;                      // 180 rows per stage
 constexpr int kLcStage = kLcRows * kLcSW;                   // floats per stage (14400)
-constexpr int kLcRowGroups = 256 / kLcRowVecs;              // 14 rows staged per pass (252 of 256 threads)
-constexpr int kLcSlots = (kLcRows + kLcRowGroups - 1) / kLcRowGroups;   // 13 passes
+
+
+// Weights live in CONSTANT memory (copied there device-to-device, stream-ordered, before the launch) so that
+// the FFMAs take them as uniform-register operands instead of 27 vector registers per thread.  Eight slots,
+// handed out round-robin, so that up to eight convolutions with different weights can be in flight.
+constexpr int kLcMaxC = 64, kLcSlotsW = 8;
+__constant__ float c_lcw[kLcSlotsW][kLcMaxC * 27];
 
 // grid: x = ceil(W/64), y = ceil(H/8), z = B * ceil(D/16); 256 threads.
-// smem: STAGES x kLcStage floats | weights [C][3][3][4]
-template <int STAGES>
-__global__ void __launch_bounds__(256, STAGES == 1 ? 3 : 1)
+// smem: STAGES x kLcStage floats
+// TH = output rows (h) per thread: 1 -> 256 threads, 2 -> 128 threads (twice the FMAs per shared-memory load)
+template <int STAGES, int TH>
+__global__ void __launch_bounds__(256 / TH, STAGES == 1 ? 3 : 1)
 conv3d_c1_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
-                 int C, int D, int H, int W, int n_dt) {
+                 int C, int D, int H, int W, int n_dt, int wslot) {
     extern __shared__ __align__(16) float lc_smem[];
-    float* wsm = lc_smem + STAGES * kLcStage;
     const int tid = threadIdx.x;
     const int b = blockIdx.z / n_dt, dt = blockIdx.z - b * n_dt;
     const int d0 = dt * kLcDT, h0 = blockIdx.y * kLcHT, w0 = blockIdx.x * kLcWT;
     const size_t chan = (size_t)D * H * W;
     const float* inb = in + (size_t)b * C * chan;
 
-    // staging: a thread copies vector `svec` of rows srow0, srow0 + 14, ... (source offset inside a channel, or -1)
+    // staging: a thread copies vector `svec` of rows srow0, srow0 + kLcRowGroups, ... (source offset inside a channel, or -1)
+    constexpr int NT = 256 / TH;
+    constexpr int kLcRowGroups = NT / kLcRowVecs;                            // rows staged per pass (14 or 7)
+    constexpr int kLcSlots = (kLcRows + kLcRowGroups - 1) / kLcRowGroups;   // passes (13 or 26)
     const int srow0 = tid / kLcRowVecs, svec = tid - srow0 * kLcRowVecs;
     const bool stager = srow0 < kLcRowGroups;
     int goff[kLcSlots];
@@ -73,18 +81,15 @@ conv3d_c1_kernel(const float* __restrict__ in, const float* __restrict__ w, floa
         __pipeline_commit();
     };
     if (STAGES == 2) issue(0, 0);
-    for (int i = tid; i < C * 36; i += 256) {                // [c][kd][kh][4]: kw padded to 4
-        const int kw = i & 3, r = i >> 2;                    // r = (c*3 + kd)*3 + kh
-        wsm[i] = kw < 3 ? __ldg(w + r * 3 + kw) : 0.f;
-    }
-
-    // thread geometry: 4 d-groups x 8 h rows x 8 w-groups
-    const int tw = tid & 7, th = (tid >> 3) & 7, td = tid >> 6;
-    float acc[4][8];
+    // thread geometry: 4 d-groups x (8 / TH) h groups x 8 w-groups
+    const int tw = tid & 7, th = ((tid >> 3) & (8 / TH - 1)) * TH, td = tid / (64 / TH);
+    float acc[4][TH][8];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
+        for (int r = 0; r < TH; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[a][r][i] = 0.f;
     // the thread's ten inputs of a row are tile columns 8tw+3 .. 8tw+12: two aligned vectors (8tw+4, 8tw+8), the
     // neighbours' edge elements by shuffle, and for the two lanes at the ends of the 64-column strip one scalar
     const int toff = ((4 * td) * kLcSH + th) * kLcSW;
@@ -106,15 +111,14 @@ conv3d_c1_kernel(const float* __restrict__ in, const float* __restrict__ w, floa
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-                const float4 q = *reinterpret_cast<const float4*>(wsm + ((c * 3 + kd) * 3 + kh) * 4);
-                wr[kd][kh][0] = q.x; wr[kd][kh][1] = q.y; wr[kd][kh][2] = q.z;
-            }
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) wr[kd][kh][kw] = c_lcw[wslot][c * 27 + (kd * 3 + kh) * 3 + kw];
 #pragma unroll
         for (int dz = 0; dz < 6; ++dz) {
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-                const float* p = st + (dz * kLcSH + kh) * kLcSW;
+            for (int hy = 0; hy < TH + 2; ++hy) {          // input row th + hy feeds output rows hy - kh
+                const float* p = st + (dz * kLcSH + hy) * kLcSW;
                 float v[10];
                 const float4 m0 = *reinterpret_cast<const float4*>(p + c0);
                 const float4 m1 = *reinterpret_cast<const float4*>(p + c1);
@@ -130,23 +134,32 @@ conv3d_c1_kernel(const float* __restrict__ in, const float* __restrict__ w, floa
                     const int od = dz - kd;                  // output d (tile-local, within the thread's 4) fed by this row
                     if (od < 0 || od > 3) continue;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        acc[od][i] = __fmaf_rn(wr[kd][kh][2], v[i + 2], __fmaf_rn(wr[kd][kh][1], v[i + 1], __fmaf_rn(wr[kd][kh][0], v[i], acc[od][i])));
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const int oh = hy - kh;              // output row (within the thread's TH)
+                        if (oh < 0 || oh >= TH) continue;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            acc[od][oh][i] = __fmaf_rn(wr[kd][kh][2], v[i + 2], __fmaf_rn(wr[kd][kh][1], v[i + 1], __fmaf_rn(wr[kd][kh][0], v[i], acc[od][oh][i])));
+                    }
                 }
             }
         }
         __syncthreads();
     }
 
-    const int h = h0 + th, wo = w0 + 8 * tw;
-    if (h < H && wo < W) {
+    const int wo = w0 + 8 * tw;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int d = d0 + 4 * td + a;
-            if (d < D) {
-                float* o = out + (((size_t)b * D + d) * H + h) * W + wo;
-                reinterpret_cast<float4*>(o)[0] = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
-                if (wo + 4 < W) reinterpret_cast<float4*>(o)[1] = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
+    for (int r = 0; r < TH; ++r) {
+        const int h = h0 + th + r;
+        if (h < H && wo < W) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const int d = d0 + 4 * td + a;
+                if (d < D) {
+                    float* o = out + (((size_t)b * D + d) * H + h) * W + wo;
+                    reinterpret_cast<float4*>(o)[0] = make_float4(acc[a][r][0], acc[a][r][1], acc[a][r][2], acc[a][r][3]);
+                    if (wo + 4 < W) reinterpret_cast<float4*>(o)[1] = make_float4(acc[a][r][4], acc[a][r][5], acc[a][r][6], acc[a][r][7]);
+                }
             }
         }
     }
@@ -157,19 +170,27 @@ int conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int
     if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: non-positive dimension");
     if (W % 4 != 0) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: W=%d must be a multiple of 4", W);
     if ((size_t)D * H * W >= ((size_t)1 << 31)) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: D*H*W must be < 2^31");
-    if (C > 256) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: C=%d too large for the shared-memory weight table", C);
+    if (C > kLcMaxC) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: C=%d exceeds the constant-memory weight table (%d)", C, kLcMaxC);
     if (!aligned(in, 16) || !aligned(out, 16) || !aligned(w, 4)) return fail(RAG_E_ALIGN, "conv3d_c1_fwd: in/out must be 16-byte aligned");
     const int n_dt = (D + kLcDT - 1) / kLcDT;
     if ((long long)B * n_dt > 65535) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: B*ceil(D/16) must be <= 65535");
     // one 57.6 KB stage: 3 CTAs per SM cover each other's copies (0.565 ms at B=8 480x960); a double-buffered
     // CTA fits only once per SM and is slower (0.735 ms)
     constexpr int stages = 1;
-    const size_t smem = ((size_t)stages * kLcStage + (size_t)C * 36) * sizeof(float);
-    auto kern = conv3d_c1_kernel<stages>;
+    const size_t smem = (size_t)stages * kLcStage * sizeof(float);
+    // two output rows per thread (128-thread CTAs, 18 instead of 12 FMAs per shared-memory load) pay off once
+    // the grid is several waves deep: 0.501 vs 0.554 ms at B=8 480x960, 0.126 vs 0.122 ms at B=4 288x576
+    const long long ctas = (long long)((W + kLcWT - 1) / kLcWT) * ((H + kLcHT - 1) / kLcHT) * B * n_dt;
+    const int TH = ctas >= 4LL * 3 * kNumSMs ? 2 : 1;
+    auto kern = TH == 2 ? conv3d_c1_kernel<stages, 2> : conv3d_c1_kernel<stages, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    static std::atomic<unsigned> ticket{0};
+    const int wslot = (int)(ticket.fetch_add(1) % (unsigned)kLcSlotsW);
+    e = cudaMemcpyToSymbolAsync(c_lcw, w, (size_t)C * 27 * sizeof(float), (size_t)wslot * kLcMaxC * 27 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: weight copy: %s", cudaGetErrorString(e));
     dim3 grid((W + kLcWT - 1) / kLcWT, (H + kLcHT - 1) / kLcHT, B * n_dt);
-    kern<<<grid, 256, smem, st>>>(in, w, out, C, D, H, W, n_dt);
+    kern<<<grid, 256 / TH, smem, st>>>(in, w, out, C, D, H, W, n_dt, wslot);
     return check_launch("conv3d_c1_fwd");
 }
 
