@@ -9,12 +9,17 @@ reference pads to 480x960 at eval (dataloaders/stereo_dataset.py:95-96; its Feat
 400x880) -> features [8,12,160,320], volume [8,24,64,160,320], head input [8,1,64,160,320],
 maxdisp 192.  `--workload train` is configs[2]: fwd+bwd, batch 4 per GPU at 288x576.
 
-Prints ONE JSON line (rank 0).  `value` = pairs/s with inputs resident in HBM (CUDA events, max over
-ranks); `e2e` = the same metric through rag_b200.pipeline.HostPipeline with pinned HOST buffers
-(H2D of the inputs and D2H of the disparity inside the timed region); `roofline` = the dominant
-kernel (cost-volume forward) against the measured HBM peak; `cpu_baseline` = the oracle port of the
-reference timed on this box's host cores.  `--impl reference` times the reference's CPU path
-(oracle port: the reference is pure PyTorch, so the port IS its op sequence) on the same config.
+Prints ONE JSON line (rank 0).  Inference workloads are timed on the two-stream schedule of
+rag_b200.pipeline.OverlappedPath (the cost volume of a batch shares the SMs with the disparity head of
+another): `value` = pairs/s of K such steps with inputs resident in HBM (CUDA events,
+max over ranks); `path.serial` = the same K steps with the kernels back to back on one stream, which is also
+where the per-kernel durations and `roofline` (the dominant kernel, cost-volume forward, against the measured
+HBM peak) come from.  The training workload (fwd+bwd) is timed serially.  `e2e` = the same metric through
+rag_b200.pipeline.HostPipeline with pinned HOST buffers (H2D of the inputs and D2H of the disparity inside the
+timed region); `cpu_baseline` = the oracle port of the reference timed on this box's host cores; `next_rows`
+= the SURVEY.md section 8f rows (fused stem, last_3_3d conv) beside the headline.  `--impl reference` times the
+reference's CPU path (oracle port: the reference is pure PyTorch, so the port IS its op sequence) on the
+same config.
 """
 from __future__ import annotations
 
