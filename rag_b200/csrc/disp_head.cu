@@ -247,7 +247,7 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
                   int variant, cudaStream_t st) {
     if (!cost || !disp) return fail(RAG_E_NULL, "disp_head_fwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 17) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 16) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
     if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl", variant);
@@ -276,7 +276,6 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
         if (variant == 11) e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 0, false>);
         else if (variant == 12) e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 1, true>);
         else if (variant == 13) e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 2, true>);
-        else if (variant == 17) e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 2, false, true>);   // 17 = 10 + cold-bin skipping
         else e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 2, false>);
         if (e) return e;
     } else if (variant >= 7) {

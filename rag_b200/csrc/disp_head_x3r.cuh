@@ -46,7 +46,6 @@ namespace rag {
 // the 2^24 threshold of the older kernels the whole-warp rescale path ran so often on large-magnitude costs
 // that the kernel took 0.39 ms instead of 0.17 ms at sigma = 20.)
 constexpr float kX3rTau = 32.0f;
-constexpr float kX3rCold = -16.0f;       // SKIP: a bin with (z - m)/3 below this has c < 2^-16 (see head_fwd_x3r_kernel)
 
 struct X3rPair {                          // per pixel pair
     float2 c[2];                          // ping-pong: c_j and (after the step) c_{j+1}
@@ -99,7 +98,7 @@ __device__ __forceinline__ void x3r_step(const float& c, float& cn, float& c2, f
 // grid: x = ceil(Wl/32), y = ceil(Hl/WARPS), z = B; 32*WARPS threads (a CTA owns WARPS block rows x 32 block
 // columns; the host picks WARPS in {4, 5} for the fuller last wave).
 // smem: tile[STAGES][BINS][WARPS+2][kTCols] | float2 tot[18][NT] | float2 kap[Dl][2] ((k1,k1),(k2,k2))
-template <int WARPS, int MINB, int BINS, int STAGES, int CORR, bool TWOSUM, bool SKIP = false>
+template <int WARPS, int MINB, int BINS, int STAGES, int CORR, bool TWOSUM>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, float* __restrict__ stats,
                     int Dl, int Hl, int Wl, float scale) {
@@ -297,29 +296,7 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     // the steps of one chunk: two groups per trip, exponent registers (ua -> ub -> ua) and c halves ping-pong.
     // A pixel running away from its reference (rare) BREAKS out of the hot loop, is handled below it and
     // the loop is re-entered, so that the hot loop is straight-line code with fall-through exits only.
-    // SKIP: trained networks give peaked distributions -- most low-res bins lie far below the pixel's reference.
-    // When bins j-1, j, j+1 are below 2^kX3rCold (z/3 domain) for all 32 x 9 pixels of the warp, the three
-    // full-res bins of group j add < 2^-45 to sums that are >= 1: the exp2 and the step are skipped and the
-    // carried terms are set to zero (warp-uniform test on the maximum that the rescale test needs anyway).
-    bool cold0 = false, cold1 = false;       // bins j-1 and j are cold (warp-uniform)
     auto hot = [&](float mx) { return __any_sync(0xffffffffu, mx > kX3rTau); };
-    auto step = [&](auto cur_tag, auto corr_tag, float mx, const float2 (&up)[4], float upS, const float2 (&un)[4], float unS,
-                    float2 k1, float2 k2) {
-        constexpr int cur = decltype(cur_tag)::value;
-        if (SKIP) {
-            const bool cold_new = __all_sync(0xffffffffu, mx < kX3rCold);
-            const bool skip = cold0 && cold1 && cold_new;
-            cold0 = cold1; cold1 = cold_new;
-            if (skip) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { st[i].c[cur ^ 1] = f2b(0.f); st[i].c2 = f2b(0.f); st[i].ps = f2b(0.f); st[i].q = f2b(0.f); }
-                so.c[cur ^ 1] = 0.f; so.c2 = 0.f; so.ps = 0.f; so.q = 0.f;
-                nk -= 3.f;
-                return;
-            }
-        }
-        group(cur_tag, corr_tag, up, upS, un, unS, k1, k2);
-    };
     auto run_chunk = [&](auto corr_tag, const float* p, int n_it, const float2* kp) {
         for (;;) {
             int rare = 0;
@@ -328,16 +305,15 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
                 blend(p, mneg, mnegS, ub, ubS);
                 mx = maxof(ub, ubS);
                 if (hot(mx)) { rare = 1; break; }
-                step(I0{}, corr_tag, mx, ua, uaS, ub, ubS, kp[0], kp[1]);
+                group(I0{}, corr_tag, ua, uaS, ub, ubS, kp[0], kp[1]);
                 blend(p + kBinFloats, mneg, mnegS, ua, uaS);
                 mx = maxof(ua, uaS);
                 if (hot(mx)) { rare = 2; break; }
-                step(I1{}, corr_tag, mx, ub, ubS, ua, uaS, kp[2], kp[3]);
+                group(I1{}, corr_tag, ub, ubS, ua, uaS, kp[2], kp[3]);
                 p += 2 * kBinFloats;
                 kp += 4;
             }
             if (rare == 0) break;
-            cold0 = cold1 = false;                 // the reference moves: previous verdicts no longer apply (never skipping is safe)
             if (rare == 1) {
                 rescale(I0{}, ub, ubS, ua, uaS);
                 group(I0{}, corr_tag, ua, uaS, ub, ubS, kp[0], kp[1]);
@@ -353,8 +329,7 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
         }
         if (n_it == 1) {
             blend(p, mneg, mnegS, ub, ubS);
-            if (hot(maxof(ub, ubS))) { rescale(I0{}, ub, ubS, ua, uaS); }
-            cold0 = cold1 = false;
+            if (hot(maxof(ub, ubS))) rescale(I0{}, ub, ubS, ua, uaS);
             group(I0{}, corr_tag, ua, uaS, ub, ubS, kp[0], kp[1]);
 #pragma unroll
             for (int i = 0; i < 4; ++i) { ua[i] = ub[i]; st[i].c[0] = st[i].c[1]; }

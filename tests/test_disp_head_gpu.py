@@ -89,7 +89,7 @@ def test_forward_parity(F_, case):
     ref_cpu = O.disp_head_ref(cost, md).numpy()
     ref_gpu = O.disp_head_ref(cost.cuda(), md).cpu().numpy()
     d64, _ = O.disp_head_f64(cost[:, 0].numpy(), md)
-    variants = [None, 0] + ([1, 2, 3] if md == 3 * dl else []) + ([4, 5, 6, 7, 9, 10, 12, 13, 17] if md == 3 * dl and wl % 4 == 0 else [])
+    variants = [None, 0] + ([1, 2, 3] if md == 3 * dl else []) + ([4, 5, 6, 7, 9, 10, 12, 13] if md == 3 * dl and wl % 4 == 0 else [])
     for v in variants:
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=v)
         out = disp.cpu().numpy()
@@ -153,7 +153,7 @@ def test_large_magnitude_costs_exercise_the_rescale_path(F_, sigma):
     # well conditioned = a 1-ulp change of the logits cannot move the result by more than ~1e-4
     top2 = np.sort(p64, axis=1)[:, -2:]
     clear = (top2[:, 1] > 0.999) | (sigma <= 30.0)
-    for v in (None, 0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13, 17):
+    for v in (None, 0, 1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 12, 13):
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=v)
         out = disp.cpu().numpy()
         assert np.isfinite(out).all() and out.min() >= 0 and out.max() <= md - 1, f"variant {v}"

@@ -64,7 +64,7 @@ def test_head_guards(L, shape):
     cl = randn((b, 1, dl, hl, wl), g).cuda()
     npx = b * 9 * hl * wl
     x3 = md == 3 * dl
-    fv = [0] + ([1, 2, 3] if x3 else []) + ([4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 17] if x3 and wl % 4 == 0 else [])
+    fv = [0] + ([1, 2, 3] if x3 else []) + ([4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14] if x3 and wl % 4 == 0 else [])
     for v in fv:
         bd, disp = window(npx)
         bs, stats = window(2 * npx)

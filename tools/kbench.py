@@ -136,7 +136,7 @@ def main():
             torch.backends.cudnn.allow_tf32 = True
         del feat
     if want("head_fwd"):
-        for v in (10, 17, 11, 9):
+        for v in (10, 11, 12, 13, 9):
             try:
                 med, best = timeit(lambda: F_.disp_head_forward(cost_lr, md, True, variant=v), a.iters, flush)
                 report("head_fwd", v, med, best, hf_bytes)
