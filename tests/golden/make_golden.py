@@ -146,6 +146,59 @@ def main():
     np.savez_compressed(os.path.join(HERE, "stage_h10_w14.npz"), img=img, top_pad=top_pad, right_pad=right_pad, out=padded)
     print("stage", padded.shape)
 
+    # ================= added later: own generator, so that the files above stay bit-identical =================
+    g2 = torch.Generator().manual_seed(4321)
+
+    # ---- head cases the x3 tiled kernels take (maxdisp == 3*Dl, Wl % 4 == 0) -------------------------------
+    cases_head2 = {
+        "head_b1_d64_h6_w8_md192_s1": (1, 64, 6, 8, 192, 1.0),
+        "head_b2_d32_h5_w12_md96_s5": (2, 32, 5, 12, 96, 5.0),
+    }
+    for name, (b, dl, hl, wl, md, sigma) in cases_head2.items():
+        cost = (sigma * torch.randn(b, 1, dl, hl, wl, generator=g2)).requires_grad_(True)
+        disp = rm.Disp(md)(cost)
+        gd = torch.randn(disp.shape, generator=g2) * (torch.rand(disp.shape, generator=g2) < 0.3).float()
+        disp.backward(gd)
+        p = torch.softmax(torch.randn(b, md, 3 * hl, 3 * wl, generator=g2), dim=1).contiguous()
+        reg = rm.DisparityRegression(md)(p)
+        np.savez_compressed(
+            os.path.join(HERE, name + ".npz"),
+            cost=cost.detach().numpy(), maxdisp=md, disp=disp.detach().numpy(),
+            gdisp=gd.numpy(), gcost=cost.grad.numpy(), p=p.numpy(), reg=reg.numpy(),
+        )
+        print(name, tuple(disp.shape))
+
+    # ---- next rows: the reference's own ConvBR_3d layers ----------------------
+    # stem3d0 = ConvBR_3d(2C, C, 3, 1, 1) on the volume built by Network.forward (rag_model.py:234,341,375-383) in
+    # eval mode, and last_3_3d = ConvBR_3d(C, 1, 3, 1, 1, bn=False, relu=False) (rag_model.py:269).
+    from automl.operations_3d import ConvBR_3d
+
+    torch.manual_seed(99)
+    c, hf, wf, md = 12, 5, 12, 24
+    x = torch.randn(1, c, hf, wf, generator=g2)
+    y = torch.randn(1, c, hf, wf, generator=g2)
+    stem = ConvBR_3d(2 * c, c, 3, 1, 1).eval()
+    with torch.no_grad():
+        stem.bn.running_mean.copy_(0.3 * torch.randn(c, generator=g2))
+        stem.bn.running_var.copy_(0.5 + torch.rand(c, generator=g2))
+        stem.bn.weight.copy_(0.5 + torch.rand(c, generator=g2))
+        stem.bn.bias.copy_(0.2 * torch.randn(c, generator=g2))
+        vol = _ref_cost_volume(rm, x, y, md)
+        out = stem(vol)
+    np.savez_compressed(
+        os.path.join(HERE, "stem_b1_c12_h5_w12_md24.npz"), x=x.numpy(), y=y.numpy(), maxdisp=md,
+        weight=stem.conv.weight.detach().numpy(), bn_weight=stem.bn.weight.detach().numpy(), bn_bias=stem.bn.bias.detach().numpy(),
+        bn_mean=stem.bn.running_mean.numpy(), bn_var=stem.bn.running_var.numpy(), bn_eps=stem.bn.eps, out=out.numpy(),
+    )
+    print("stem", tuple(out.shape))
+    last = ConvBR_3d(c, 1, 3, 1, 1, bn=False, relu=False).eval()
+    feat = torch.randn(1, c, 18, 9, 12, generator=g2)
+    with torch.no_grad():
+        mat = last(feat)
+    np.savez_compressed(os.path.join(HERE, "last3_b1_c12_d18_h9_w12.npz"), feat=feat.numpy(),
+                        weight=last.conv.weight.detach().numpy(), out=mat.numpy())
+    print("last_3_3d", tuple(mat.shape))
+
 
 if __name__ == "__main__":
     main()

@@ -163,3 +163,25 @@ def test_network_forward_with_fused_stem():
             ConvBR_3d.forward = old_fwd
             N._FUSE_STEM = old_flag
     assert (out - ref).abs().max().item() <= 2e-4
+
+
+def test_golden_from_the_reference_layer():
+    """tests/golden/stem_*.npz: the reference's Network.forward volume fed to its own ConvBR_3d(2C, C, 3, 1, 1) in
+    eval mode (CPU, fp32)."""
+    import glob
+    import os
+
+    import numpy as np
+
+    from rag_b200.fused_stem import cv_stem_forward
+    from tests.conftest import GOLDEN
+
+    paths = sorted(glob.glob(os.path.join(GOLDEN, "stem_*.npz")))
+    assert paths
+    for path in paths:
+        z = np.load(path)
+        t = lambda k: torch.from_numpy(np.asarray(z[k], dtype=np.float32)).cuda()  # noqa: E731
+        scale = t("bn_weight") * torch.rsqrt(t("bn_var") + float(z["bn_eps"]))
+        shift = t("bn_bias") - t("bn_mean") * scale
+        out = cv_stem_forward(t("x"), t("y"), t("weight"), scale, shift, True, int(z["maxdisp"])).cpu().numpy()
+        assert np.abs(out - z["out"]).max() <= 1e-5 * np.abs(z["out"]).max()

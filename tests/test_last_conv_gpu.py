@@ -90,3 +90,21 @@ def test_errors_are_loud():
         conv3d_c1_forward(torch.zeros(1, 4, 4, 4, 8), torch.zeros(1, 4, 3, 3, 3))                                  # CPU tensors
     with pytest.raises(RuntimeError):
         conv3d_c1_forward(torch.zeros(1, 4, 4, 4, 8, device="cuda"), torch.zeros(2, 4, 3, 3, 3, device="cuda"))   # not 1 output channel
+
+
+def test_golden_from_the_reference_layer():
+    """tests/golden/last3_*.npz: the reference's own ConvBR_3d(12, 1, 3, 1, 1, bn=False, relu=False) run on CPU."""
+    import glob
+    import os
+
+    import numpy as np
+
+    from rag_b200.last_conv import conv3d_c1_forward
+    from tests.conftest import GOLDEN
+
+    paths = sorted(glob.glob(os.path.join(GOLDEN, "last3_*.npz")))
+    assert paths
+    for path in paths:
+        z = np.load(path)
+        out = conv3d_c1_forward(torch.from_numpy(z["feat"]).cuda(), torch.from_numpy(z["weight"]).cuda()).cpu().numpy()
+        assert np.abs(out - z["out"]).max() <= 4e-6 * np.abs(z["out"]).max()
