@@ -187,7 +187,7 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
     const bool st_a = store_lane && has_a, st_b = store_lane && has_b;
     float2 pg[4] = {f2b(0.f), f2b(0.f), f2b(0.f), f2b(0.f)};   // "B" bin part of the previous k-block, per pixel
     float pgS = 0.f;
-    const float2 one = f2b(1.f), two = f2b(2.f), neg1 = f2b(-1.f);
+    const float2 neg1 = f2b(-1.f);
     float kf = (float)(3 * jb0 + 1);
 
     // full-res bin 0 (lambda1 == 0) sits exactly on low-res bin 0 and feeds cell 0 only: its share enters
@@ -196,9 +196,15 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
     float s0iS = 0.f;
     if (jb0 == 0 && j0 == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s0i[i] = mul2(dAb[0], mul2(ex2_2(a[i]), fma2(dsp[i], neg1, f2b(0.f))));
-        s0iS = dAb[0].x * (ex2_approx(aS) * (0.f - dspS));
+        for (int i = 0; i < 4; ++i) s0i[i] = mul2(gneg[i], mul2(dAb[0], mul2(ex2_2(a[i]), fma2(dsp[i], neg1, f2b(0.f)))));
+        s0iS = gnegS * (dAb[0].x * (ex2_approx(aS) * (0.f - dspS)));
     }
+    // the upstream factor -g/sum is folded into (k - disp): gdk = gneg*k - gneg*disp, so the bin terms come out
+    // already scaled (two multiplications per pixel pair and k-block fewer)
+    float2 ngd[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ngd[i] = mul2(mul2(gneg[i], dsp[i]), neg1);
+    const float ngdS = -(gnegS * dspS);
 
     for (int jb = jb0; jb < j1; ++jb) {
         if (wp < wlast) wp += 2 * kBwCols;   // upper bin min(jb+1, Dl-1)
@@ -213,25 +219,24 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float2 dlt = fma2(a[i], neg1, t[i]);
-            const float2 dk = fma2(dsp[i], neg1, kfb);           // k1 - disp
+            const float2 dk = fma2(gneg[i], kfb, ngd[i]);        // gneg * (k1 - disp)
+            const float2 dk1 = add2(dk, gneg[i]), dk2 = add2(dk1, gneg[i]);
             const float2 u1 = mul2(ex2_2(fma2(l1, dlt, a[i])), dk);
-            const float2 u2 = mul2(ex2_2(fma2(l2, dlt, a[i])), add2(dk, one));
-            const float2 u3 = mul2(ex2_2(fma2(l3, dlt, a[i])), add2(dk, two));
-            const float2 s0 = fma2(a3, u3, fma2(a2, u2, fma2(a1, u1, s0i[i])));
-            const float2 s1 = fma2(b3, u3, fma2(b2, u2, mul2(b1, u1)));
-            g0[i] = mul2(gneg[i], s0); g1[i] = mul2(gneg[i], s1);
+            const float2 u2 = mul2(ex2_2(fma2(l2, dlt, a[i])), dk1);
+            const float2 u3 = mul2(ex2_2(fma2(l3, dlt, a[i])), dk2);
+            g0[i] = fma2(a3, u3, fma2(a2, u2, fma2(a1, u1, s0i[i])));
+            g1[i] = fma2(b3, u3, fma2(b2, u2, mul2(b1, u1)));
             a[i] = t[i];
             s0i[i] = f2b(0.f);
         }
         {
             const float dlt = tS - aS;
-            const float dk = kf - dspS;
+            const float dk = __fmaf_rn(gnegS, kf, ngdS);
             const float u1 = ex2_approx(__fmaf_rn(l1.x, dlt, aS)) * dk;
-            const float u2 = ex2_approx(__fmaf_rn(l2.x, dlt, aS)) * (dk + 1.f);
-            const float u3 = ex2_approx(__fmaf_rn(l3.x, dlt, aS)) * (dk + 2.f);
-            const float s0 = __fmaf_rn(a3.x, u3, __fmaf_rn(a2.x, u2, __fmaf_rn(a1.x, u1, s0iS)));
-            const float s1 = __fmaf_rn(b3.x, u3, __fmaf_rn(b2.x, u2, b1.x * u1));
-            g0S = gnegS * s0; g1S = gnegS * s1;
+            const float u2 = ex2_approx(__fmaf_rn(l2.x, dlt, aS)) * (dk + gnegS);
+            const float u3 = ex2_approx(__fmaf_rn(l3.x, dlt, aS)) * ((dk + gnegS) + gnegS);
+            g0S = __fmaf_rn(a3.x, u3, __fmaf_rn(a2.x, u2, __fmaf_rn(a1.x, u1, s0iS)));
+            g1S = __fmaf_rn(b3.x, u3, __fmaf_rn(b2.x, u2, b1.x * u1));
             aS = tS;
             s0iS = 0.f;
         }
