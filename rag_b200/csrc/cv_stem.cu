@@ -222,11 +222,34 @@ cv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, con
 //     disparity row, so the LF vector lives in registers, the RF read is one LDS.128 through a pointer
 //     that moves 16 bytes per step, and no index arithmetic is left in the loop.
 // Needs Wf % 4 == 0.  Same shared-memory layout otherwise.
+//
+// The conv weights are regrouped ONCE per launch by a tiny kernel into the layout phase 1 reads
+// ([o][side][c][kh][20]: the nine (kd,kw) weights duplicated as (w,w) pairs + padding) instead of by every one
+// of the B*O*Hf CTAs (div/mod address arithmetic and scattered loads: 9 % of the samples).  Four slots, handed
+// out round-robin, so launches with different weights can overlap.
+constexpr int kStemWSlots = 4, kStemWMaxO = 32, kStemWPerO = 2 * 12 * 3 * 20;
+__device__ float g_stem_w[kStemWSlots][kStemWMaxO * kStemWPerO];
+
+__global__ void __launch_bounds__(256)
+stem_regroup_kernel(const float* __restrict__ w, int C, int slot) {
+    const int o = blockIdx.x;
+    for (int i = threadIdx.x; i < 2 * C * 3 * 20; i += 256) {
+        const int t2 = i % 20, kh = (i / 20) % 3, c = (i / 60) % C, side = i / (60 * C);
+        const int t = t2 >> 1;
+        float v = 0.f;
+        if (t < 9) {
+            const int kd = t / 3, kw = t % 3;
+            v = __ldg(w + ((((size_t)o * 2 * C + side * C + c) * 3 + kd) * 3 + kh) * 3 + kw);
+        }
+        g_stem_w[slot][o * kStemWPerO + i] = v;
+    }
+}
+
 template <int C>
 __global__ void __launch_bounds__(512, 2)
 cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w,
                     const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                    float* __restrict__ out, int O, int Df, int Hf, int Wf) {
+                    float* __restrict__ out, int O, int Df, int Hf, int Wf, int wslot) {
     extern __shared__ __align__(16) float stem_smem[];
     const int Wp = Wf + 2 * kStemPad;
     float* wsm = stem_smem;                       // [side][c][kh][20]: 9 (kd,kw) weights duplicated (w,w) + pad
@@ -262,15 +285,20 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
         }
     }
 
-    for (int i = tid; i < 2 * C * 3 * 20; i += NT) {
-        const int t2 = i % 20, kh = (i / 20) % 3, c = (i / 60) % C, side = i / (60 * C);
-        const int t = t2 >> 1;
-        float v = 0.f;
-        if (t < 9) {
-            const int kd = t / 3, kw = t % 3;
-            v = __ldg(w + ((((size_t)o * 2 * C + side * C + c) * 3 + kd) * 3 + kh) * 3 + kw);
+    if (wslot >= 0) {                              // weights already regrouped by stem_regroup_kernel: plain vector copy
+        const float4* src = reinterpret_cast<const float4*>(g_stem_w[wslot] + o * kStemWPerO);
+        for (int i = tid; i < 2 * C * 3 * 20 / 4; i += NT) reinterpret_cast<float4*>(wsm)[i] = src[i];
+    } else {
+        for (int i = tid; i < 2 * C * 3 * 20; i += NT) {
+            const int t2 = i % 20, kh = (i / 20) % 3, c = (i / 60) % C, side = i / (60 * C);
+            const int t = t2 >> 1;
+            float v = 0.f;
+            if (t < 9) {
+                const int kd = t / 3, kw = t % 3;
+                v = __ldg(w + ((((size_t)o * 2 * C + side * C + c) * 3 + kd) * 3 + kh) * 3 + kw);
+            }
+            wsm[i] = v;
         }
-        wsm[i] = v;
     }
     for (int i = tid; i < 33 * 2 * kStemPad; i += NT) {
         const int row = i / (2 * kStemPad), k = i - row * (2 * kStemPad);
@@ -462,7 +490,14 @@ int cv_stem_fwd(const float* x, const float* y, const float* w, const float* sca
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             if (e != cudaSuccess) return fail((int)e, "cv_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         }
-        kern<<<dim3(Hf, O, B), nt, smem2, st>>>(x, y, w, scale, shift, relu, out, O, Df, Hf, Wf);
+        static std::atomic<unsigned> ticket{0};
+        int wslot = -1;
+        if (O <= kStemWMaxO) {
+            wslot = (int)(ticket.fetch_add(1) % (unsigned)kStemWSlots);
+            stem_regroup_kernel<<<O, 256, 0, st>>>(w, C, wslot);
+            if (int e = check_launch("cv_stem_fwd(regroup)")) return e;
+        }
+        kern<<<dim3(Hf, O, B), nt, smem2, st>>>(x, y, w, scale, shift, relu, out, O, Df, Hf, Wf, wslot);
     } else if (variant == 1) {
         auto kern = cv_stem_fwd_kernel<12>;
         if (smem > 48 * 1024) {
