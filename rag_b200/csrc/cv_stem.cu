@@ -369,8 +369,10 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
             }
         }
     }
+    // j-major order: which of the nine taps of a band element survive the mask depends only on j = w - d + 2, so
+    // with one j per warp the tap branches of stem_taps are warp-uniform (1, 3, 6, 8 taps for j = 0..3)
     for (int i = tid; i < 5 * Df; i += NT) {
-        const int d = i / 5, j = i - d * 5;
+        const int j = i / Df, d = i - j * Df;
         const int col = j < 4 ? d - 2 + j : Wf - 1;
         const float v = (col >= 0 && col < Wf) ? stem_taps(maps, Wp, Df, Wf, d, col) : 0.f;
         if (j < 4) band[d * 4 + j] = v; else lastcol[d] = v;
