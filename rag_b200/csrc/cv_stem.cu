@@ -224,18 +224,17 @@ cv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, con
 // Needs Wf % 4 == 0.  Same shared-memory layout otherwise.
 //
 // The conv weights are regrouped ONCE per launch by a tiny kernel into the layout phase 1 reads
-// ([o][side][c][kh][20]: the nine (kd,kw) weights duplicated as (w,w) pairs + padding) instead of by every one
+// ([o][side][c][kh][12]: the nine (kd,kw) weights + padding) instead of by every one
 // of the B*O*Hf CTAs (div/mod address arithmetic and scattered loads: 9 % of the samples).  Four slots, handed
 // out round-robin, so launches with different weights can overlap.
-constexpr int kStemWSlots = 4, kStemWMaxO = 32, kStemWPerO = 2 * 12 * 3 * 20;
+constexpr int kStemWSlots = 4, kStemWMaxO = 32, kStemWPerO = 2 * 12 * 3 * 12;
 __device__ float g_stem_w[kStemWSlots][kStemWMaxO * kStemWPerO];
 
 __global__ void __launch_bounds__(256)
 stem_regroup_kernel(const float* __restrict__ w, int C, int slot) {
     const int o = blockIdx.x;
-    for (int i = threadIdx.x; i < 2 * C * 3 * 20; i += 256) {
-        const int t2 = i % 20, kh = (i / 20) % 3, c = (i / 60) % C, side = i / (60 * C);
-        const int t = t2 >> 1;
+    for (int i = threadIdx.x; i < 2 * C * 3 * 12; i += 256) {
+        const int t = i % 12, kh = (i / 12) % 3, c = (i / 36) % C, side = i / (36 * C);
         float v = 0.f;
         if (t < 9) {
             const int kd = t / 3, kw = t % 3;
@@ -252,8 +251,8 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
                     float* __restrict__ out, int O, int Df, int Hf, int Wf, int wslot) {
     extern __shared__ __align__(16) float stem_smem[];
     const int Wp = Wf + 2 * kStemPad;
-    float* wsm = stem_smem;                       // [side][c][kh][20]: 9 (kd,kw) weights duplicated (w,w) + pad
-    float* maps = wsm + 2 * C * 3 * 20;
+    float* wsm = stem_smem;                       // [side][c][kh][12]: 9 (kd,kw) weights + pad
+    float* maps = wsm + 2 * C * 3 * 12;
     float* LF = maps + 18 * Wp;
     float* RF = LF + 3 * Wp;
     float* band = RF + 12 * Wp;
@@ -287,11 +286,10 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
 
     if (wslot >= 0) {                              // weights already regrouped by stem_regroup_kernel: plain vector copy
         const float4* src = reinterpret_cast<const float4*>(g_stem_w[wslot] + o * kStemWPerO);
-        for (int i = tid; i < 2 * C * 3 * 20 / 4; i += NT) reinterpret_cast<float4*>(wsm)[i] = src[i];
+        for (int i = tid; i < 2 * C * 3 * 12 / 4; i += NT) reinterpret_cast<float4*>(wsm)[i] = src[i];
     } else {
-        for (int i = tid; i < 2 * C * 3 * 20; i += NT) {
-            const int t2 = i % 20, kh = (i / 20) % 3, c = (i / 60) % C, side = i / (60 * C);
-            const int t = t2 >> 1;
+        for (int i = tid; i < 2 * C * 3 * 12; i += NT) {
+            const int t = i % 12, kh = (i / 12) % 3, c = (i / 36) % C, side = i / (36 * C);
             float v = 0.f;
             if (t < 9) {
                 const int kd = t / 3, kw = t % 3;
@@ -315,7 +313,7 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
 #pragma unroll
             for (int c = 0; c < kStemStages - 1; ++c) { fetch_c(src, c, c); __pipeline_commit(); }
         }
-        const float4* wp = reinterpret_cast<const float4*>(wsm + side * C * 60);
+        const float4* wp = reinterpret_cast<const float4*>(wsm + side * C * 36);
         float2 acc[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) acc[i] = make_float2(0.f, 0.f);
@@ -332,14 +330,15 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
                 const float2 v = kh == 0 ? v0 : kh == 1 ? v1 : v2;
-                const float4 q0 = wp[kh * 5 + 0], q1 = wp[kh * 5 + 1], q2 = wp[kh * 5 + 2], q3 = wp[kh * 5 + 3], q4 = wp[kh * 5 + 4];
-                acc[0] = __ffma2_rn(make_float2(q0.x, q0.y), v, acc[0]); acc[1] = __ffma2_rn(make_float2(q0.z, q0.w), v, acc[1]);
-                acc[2] = __ffma2_rn(make_float2(q1.x, q1.y), v, acc[2]); acc[3] = __ffma2_rn(make_float2(q1.z, q1.w), v, acc[3]);
-                acc[4] = __ffma2_rn(make_float2(q2.x, q2.y), v, acc[4]); acc[5] = __ffma2_rn(make_float2(q2.z, q2.w), v, acc[5]);
-                acc[6] = __ffma2_rn(make_float2(q3.x, q3.y), v, acc[6]); acc[7] = __ffma2_rn(make_float2(q3.z, q3.w), v, acc[7]);
-                acc[8] = __ffma2_rn(make_float2(q4.x, q4.y), v, acc[8]);
+                // nine (kd,kw) weights of (c,kh) in three vectors; the packed FMA broadcasts the scalar weight
+                const float4 q0 = wp[kh * 3 + 0], q1 = wp[kh * 3 + 1], q2 = wp[kh * 3 + 2];
+                acc[0] = __ffma2_rn(make_float2(q0.x, q0.x), v, acc[0]); acc[1] = __ffma2_rn(make_float2(q0.y, q0.y), v, acc[1]);
+                acc[2] = __ffma2_rn(make_float2(q0.z, q0.z), v, acc[2]); acc[3] = __ffma2_rn(make_float2(q0.w, q0.w), v, acc[3]);
+                acc[4] = __ffma2_rn(make_float2(q1.x, q1.x), v, acc[4]); acc[5] = __ffma2_rn(make_float2(q1.y, q1.y), v, acc[5]);
+                acc[6] = __ffma2_rn(make_float2(q1.z, q1.z), v, acc[6]); acc[7] = __ffma2_rn(make_float2(q1.w, q1.w), v, acc[7]);
+                acc[8] = __ffma2_rn(make_float2(q2.x, q2.x), v, acc[8]);
             }
-            wp += 15;
+            wp += 9;
         }
         float* dst = maps + (side * 9) * Wp + kStemPad + col;
 #pragma unroll
@@ -486,7 +485,7 @@ int cv_stem_fwd(const float* x, const float* y, const float* w, const float* sca
         if (k < 1) k = 1;
         int nt = k * Wv;
         if (nt < 128) nt = ((128 + Wv - 1) / Wv) * Wv;
-        const size_t smem2 = ((size_t)2 * C * 60 + (size_t)33 * (Wf + 2 * kStemPad) + (size_t)4 * Df + ((Df + 3) & ~3)) * sizeof(float) +
+        const size_t smem2 = ((size_t)2 * C * 36 + (size_t)33 * (Wf + 2 * kStemPad) + (size_t)4 * Df + ((Df + 3) & ~3)) * sizeof(float) +
                              (size_t)kStemStages * 3 * nt * sizeof(float2);
         if (smem2 > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
