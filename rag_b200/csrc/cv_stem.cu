@@ -346,7 +346,9 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
     }
     __syncthreads();
 
-    // ---- phase 2 (as in the first kernel) ----
+    // ---- phase 2 (as in the first kernel), with the folded BatchNorm applied to the rows once instead of to
+    // every output: LF' = sc*LF + sh, RF' = sc*RF, so that out = relu?(LF' + RF') ----
+    const float sc = scale ? __ldg(scale + o) : 1.f, sh = shift ? __ldg(shift + o) : 0.f;
     for (int col = tid; col < Wf; col += NT) {
         float S[3], T[3];
 #pragma unroll
@@ -360,10 +362,11 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
         const float rf[3] = {T[1] + T[2], T[0] + T[1] + T[2], T[0] + T[1]};
 #pragma unroll
         for (int cls = 0; cls < 3; ++cls) {
-            LF[cls * Wp + kStemPad + col] = lf[cls];
+            LF[cls * Wp + kStemPad + col] = __fmaf_rn(lf[cls], sc, sh);
+            const float rfs = rf[cls] * sc;
 #pragma unroll
             for (int s2 = 0; s2 < 4; ++s2) {
-                if (col + s2 < Wf) RF[(cls * 4 + s2) * Wp + kStemPad + col + s2] = rf[cls];
+                if (col + s2 < Wf) RF[(cls * 4 + s2) * Wp + kStemPad + col + s2] = rfs;
                 if (col < s2) RF[(cls * 4 + s2) * Wp + kStemPad + col] = 0.f;
             }
         }
@@ -382,11 +385,11 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
     // Main pass is branch-free: every element is LF + RF (masked to 0 where w - d <= -3, i.e. all taps masked);
     // the 5 border elements per disparity row (diagonal band, last column) are patched afterwards from the
     // tap-by-tap tables.
-    const float sc = scale ? __ldg(scale + o) : 1.f, sh = shift ? __ldg(shift + o) : 0.f;
-    auto finish = [&](float v) {
+    auto finish = [&](float v) {                   // border elements (unscaled tap sums)
         v = __fmaf_rn(v, sc, sh);
         return relu ? fmaxf(v, 0.f) : v;
     };
+    auto act = [&](float v) { return relu ? fmaxf(v, 0.f) : v; };   // main pass: rows are already scaled
     const int Wv = Wf >> 2;
     const int rpp = NT / Wv;                       // rows per pass (NT is a multiple of Wv)
     const int d0 = tid / Wv, wv = tid - d0 * Wv, w0 = wv << 2;
@@ -408,10 +411,10 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
                 // RF copy (d & 3) at vector offset w0 - 4*(d >> 2); for u0 < 0 this reads the zero pad / garbage that is masked below
                 const int ro = max(w0 - (d & ~3), -kStemPad);
                 const float4 rf = *reinterpret_cast<const float4*>(RF + (cls * 4 + (d & 3)) * Wp + kStemPad + ro);
-                v.x = u0 + 0 >= -2 ? finish(lf.x + rf.x) : zero_val;
-                v.y = u0 + 1 >= -2 ? finish(lf.y + rf.y) : zero_val;
-                v.z = u0 + 2 >= -2 ? finish(lf.z + rf.z) : zero_val;
-                v.w = u0 + 3 >= -2 ? finish(lf.w + rf.w) : zero_val;
+                v.x = u0 + 0 >= -2 ? act(lf.x + rf.x) : zero_val;
+                v.y = u0 + 1 >= -2 ? act(lf.y + rf.y) : zero_val;
+                v.z = u0 + 2 >= -2 ? act(lf.z + rf.z) : zero_val;
+                v.w = u0 + 3 >= -2 ? act(lf.w + rf.w) : zero_val;
             }
             st_stream(reinterpret_cast<float4*>(op), v);
         }
