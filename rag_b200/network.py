@@ -79,7 +79,9 @@ def install(rag_model=None, mdenas_basicmodel=None, operations_3d=None, fuse_ste
     ``fuse_stem=True`` (needs ``operations_3d`` = the imported ``automl.operations_3d``) additionally makes
     ``ConvBR_3d.forward`` fusion-aware and lets the patched forwards skip materialising the volume: the
     first Matching-Net layer (rag_model.py:341) then runs as csrc/cv_stem.cu in inference; training and
-    any non-matching layer geometry fall back to the materialised volume automatically.  NOTE: only the
+    any non-matching layer geometry fall back to the materialised volume automatically.  The same rebinding
+    sends ``last_3_3d`` (a bias-free Conv3d C -> 1, 3x3x3 without BN/ReLU, rag_model.py:269) through
+    csrc/last_conv.cu when no gradient is wanted (rag_b200/last_conv.py).  NOTE: only the
     growable ``Network`` starts its Matching Net with a ConvBR_3d on the raw volume in all configurations;
     the search supernet (``BasicNetwork``/``AutoMatching``) keeps the materialised volume."""
     global _FUSE_STEM
