@@ -334,19 +334,19 @@ int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, cons
                   int B, int Dl, int Hl, int Wl, int D, int variant, cudaStream_t st) {
     if (!cost || !gdisp || !disp || !stats || !gcost) return fail(RAG_E_NULL, "disp_head_bwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 2) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 3) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
     if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_bwd: variant %d needs maxdisp == 3*Dl", variant);
-    if (variant == 2 && !scratch) return fail(RAG_E_NULL, "disp_head_bwd: variant 2 needs a scratch buffer");
-    if (variant == -1) variant = x3 ? (scratch ? 2 : 1) : 0;
-    if (variant == 2) {
+    if (variant >= 2 && !scratch) return fail(RAG_E_NULL, "disp_head_bwd: variant %d needs a scratch buffer", variant);
+    if (variant == -1) variant = x3 ? (scratch ? 3 : 1) : 0;
+    if (variant >= 2) {   // 3 = one exp2 per pixel and k-block (default), 2 = three
         const int nJ = (Dl + kBwJ - 1) / kBwJ;
         const int strips = (Wl + 30) / 31;
         const int n_tasks = (Hl + 1) * nJ;
         dim3 grid(strips, (n_tasks + 3) / 4, B);
         const size_t smem = (size_t)3 * (D + 3) * sizeof(float2) + (size_t)4 * kBwWin * sizeof(float);
-        auto kern = head_bwd_x3w_kernel;
+        auto kern = variant == 3 ? head_bwd_x3w_kernel<true> : head_bwd_x3w_kernel<false>;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "disp_head_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

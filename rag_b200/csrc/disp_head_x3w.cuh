@@ -1,4 +1,4 @@
-// x3 disparity-head backward, second generation (default when a scratch buffer is supplied).
+// x3 disparity-head backward, second generation (default when a scratch buffer is supplied: <CUBE = true>).
 //
 // Same maths as head_bwd_x3_kernel (disp_head_x3.cuh): deterministic, atomics-free transpose of the
 // upsample applied to -g p_k (k - disp), p_k rebuilt from cost_lr and the forward's stats.  What the
@@ -25,6 +25,15 @@ constexpr int kBwBins = kBwJ + 2;        // low-res bins a task reads
 constexpr int kBwCols = 34;              // window width: 32 block columns + 1 + pad
 constexpr int kBwWin = kBwBins * 2 * kBwCols;
 
+//
+// CUBE (default): the three full-res bins of a k-block come from ONE exp2 per pixel instead of three.  With
+// c_j = 2^(e_j/3) (e_j = relative exponent of low-res bin j) and PyTorch's lambdas (0, ~1/3, ~2/3),
+//   2^e(3j+1) = c_j^3,   2^e(3j+2) = c_j^2 c_j+1 (1 + kap2 du),   2^e(3j+3) = c_j c_j+1^2 (1 + kap3 du),
+// du = (e_j+1 - e_j)/3, kap_q = 3 ln2 (lambda_fp32 - q/3): the first-order term restores the reference's
+// fp32 lambdas (|kap du| < 2e-4 wherever the bin matters, so the second order is < 2e-8).  The profile of
+// the three-exp2 form had the XU pipe 45 % and the FMA pipe 56 % busy with the issue slots at 63 %: the
+// MUFU bursts (27 per k-block, 8 clk each) were what the four warps of a scheduler queued on.
+template <bool CUBE>
 __global__ void __launch_bounds__(128, 4)
 head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gdisp, const float* __restrict__ disp,
                     const float* __restrict__ stats, float* __restrict__ gcost, float* __restrict__ scratch,
@@ -43,6 +52,13 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
             const int jb = k == 0 ? 0 : (k - 1) / 3;
             wa = (t0 == jb ? l0 : 0.f) + (t1 == jb ? l1 : 0.f);
             wb = (t0 == jb + 1 ? l0 : 0.f) + (t1 == jb + 1 ? l1 : 0.f);
+            if (CUBE) {
+                // lambda - fl(q/3) is exact in fp32 (Sterbenz); fl(1/3) - 1/3 = 2^-25/3, fl(2/3) - 2/3 = 2^-24/3
+                const int q = k == 0 ? 0 : (k - 1) % 3;
+                const float third = q == 1 ? 0.333333343267440796f : 0.666666686534881592f;
+                const float resid = q == 1 ? 9.934107e-9f : 1.9868214e-8f;
+                l1 = (q != 0 && t1 > t0) ? 2.0794415416798357f * ((l1 - third) + resid) : 0.f;
+            }
         }
         lzb[k] = f2b(l1); dAb[k] = f2b(wa); dBb[k] = f2b(wb);
     }
@@ -76,16 +92,23 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
     {
         const int nb = min(j1, Dl - 1) - jb0 + 1;
         const int gc0 = min(max(c_first + lane, 0), Wl - 1);
-        const int gc1 = min(max(c_first + 32 + lane, 0), Wl - 1);     // lanes 0,1 also fetch u = 32, 33
+        const int gc32 = min(max(c_first + 32, 0), Wl - 1), gc33 = min(max(c_first + 33, 0), Wl - 1);
+        // lanes 0,1 fetch the two extra columns in a second pass, so that every copy is one running pointer
+        const float* s0 = base + (size_t)jb0 * plane + (size_t)ah.lo0 * Wl + gc0;
+        const float* s1 = base + (size_t)jb0 * plane + (size_t)ah.lo1 * Wl + gc0;
+        float* d = win + lane;
+#pragma unroll 2
         for (int q = 0; q < nb; ++q) {
-            const float* s0 = base + (size_t)(jb0 + q) * plane + (size_t)ah.lo0 * Wl;
-            const float* s1 = base + (size_t)(jb0 + q) * plane + (size_t)ah.lo1 * Wl;
-            float* d = win + q * 2 * kBwCols;
-            __pipeline_memcpy_async(d + lane, s0 + gc0, 4);
-            __pipeline_memcpy_async(d + kBwCols + lane, s1 + gc0, 4);
-            if (lane < 2) {
-                __pipeline_memcpy_async(d + 32 + lane, s0 + gc1, 4);
-                __pipeline_memcpy_async(d + kBwCols + 32 + lane, s1 + gc1, 4);
+            __pipeline_memcpy_async(d, s0, 4);
+            __pipeline_memcpy_async(d + kBwCols, s1, 4);
+            s0 += plane; s1 += plane; d += 2 * kBwCols;
+        }
+        if (lane < 4) {
+            const float* s2 = base + (size_t)jb0 * plane + (size_t)((lane & 2) ? ah.lo1 : ah.lo0) * Wl + ((lane & 1) ? gc33 : gc32);
+            float* d2 = win + ((lane & 2) ? kBwCols : 0) + 32 + (lane & 1);
+            for (int q = 0; q < nb; ++q) {
+                __pipeline_memcpy_async(d2, s2, 4);
+                s2 += plane; d2 += 2 * kBwCols;
             }
         }
         __pipeline_commit();
@@ -107,7 +130,7 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
                 const int i = ph * 3 + pw;
                 const size_t o = (size_t)ah.idx[ph] * W + aw.idx[pw];   // clamped -> always a real pixel
                 const bool ok = ah.valid[ph] && aw.valid[pw];
-                m9[i] = -__ldg(sm + o);
+                m9[i] = -__ldg(sm + o) * (CUBE ? 0.333333343267440796f : 1.f);   // CUBE works on exponent / 3
                 d9[i] = __ldg(dp + o);
                 g9[i] = ok ? -__ldg(gd + o) * __ldg(sm + img + o) : 0.f;
                 gabs = fmaxf(gabs, fabsf(g9[i]));
@@ -142,7 +165,8 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
     float2 h0b[3], h1b[3], hAb[3], hBb[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        h0b[i] = f2b(ah.l0[i] * kX3NegLog2e); h1b[i] = f2b(ah.l1[i] * kX3NegLog2e);
+        constexpr float ks = CUBE ? kX3NegLog2e / 3.0f : kX3NegLog2e;
+        h0b[i] = f2b(ah.l0[i] * ks); h1b[i] = f2b(ah.l1[i] * ks);
         hAb[i] = f2b(ah.wa[i]); hBb[i] = f2b(ah.wb[i]);
     }
     const float2 h0p = f2(h0b[0].x, h0b[1].x), h1p = f2(h1b[0].x, h1b[1].x);
@@ -185,19 +209,28 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
     float* ga = gout + (size_t)j0 * plane + (size_t)max(rb, 0) * Wl + c;
     float* gb = sout + (size_t)j0 * plane + (size_t)min(rb + 1, Hl - 1) * Wl + c;
     const bool st_a = store_lane && has_a, st_b = store_lane && has_b;
-    float2 pg[4] = {f2b(0.f), f2b(0.f), f2b(0.f), f2b(0.f)};   // "B" bin part of the previous k-block, per pixel
-    float pgS = 0.f;
     const float2 neg1 = f2b(-1.f);
     float kf = (float)(3 * jb0 + 1);
 
-    // full-res bin 0 (lambda1 == 0) sits exactly on low-res bin 0 and feeds cell 0 only: its share enters
-    // k-block 0's "A" sums as an initial value
-    float2 s0i[4] = {f2b(0.f), f2b(0.f), f2b(0.f), f2b(0.f)};
-    float s0iS = 0.f;
+    // "B" bin part of the previous k-block, per pixel.  Full-res bin 0 (lambda1 == 0) sits exactly on low-res
+    // bin 0 and feeds cell 0 only: its share is the initial value (cell 0 = k-block 0's "A" part + this)
+    float2 pg[4] = {f2b(0.f), f2b(0.f), f2b(0.f), f2b(0.f)};
+    float pgS = 0.f;
+    // CUBE: c = 2^(a) with a = exponent / 3 of the k-block's lower bin, and its square, carried across k-blocks
+    float2 ca[4];
+    float caS = 0.f;
+    if (CUBE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ca[i] = ex2_2(a[i]);
+        caS = ex2_approx(aS);
+    }
     if (jb0 == 0 && j0 == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) s0i[i] = mul2(gneg[i], mul2(dAb[0], mul2(ex2_2(a[i]), fma2(dsp[i], neg1, f2b(0.f)))));
-        s0iS = gnegS * (dAb[0].x * (ex2_approx(aS) * (0.f - dspS)));
+        for (int i = 0; i < 4; ++i) {
+            const float2 e0 = CUBE ? mul2(mul2(ca[i], ca[i]), ca[i]) : ex2_2(a[i]);
+            pg[i] = mul2(gneg[i], mul2(dAb[0], mul2(e0, fma2(dsp[i], neg1, f2b(0.f)))));
+        }
+        pgS = gnegS * (dAb[0].x * ((CUBE ? caS * caS * caS : ex2_approx(aS)) * (0.f - dspS)));
     }
     // the upstream factor -g/sum is folded into (k - disp): gdk = gneg*k - gneg*disp, so the bin terms come out
     // already scaled (two multiplications per pixel pair and k-block fewer)
@@ -206,46 +239,78 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
     for (int i = 0; i < 4; ++i) ngd[i] = mul2(mul2(gneg[i], dsp[i]), neg1);
     const float ngdS = -(gnegS * dspS);
 
+#pragma unroll 2
     for (int jb = jb0; jb < j1; ++jb) {
         if (wp < wlast) wp += 2 * kBwCols;   // upper bin min(jb+1, Dl-1)
         blend(wp, t, tS);
-        const float2 l1 = lp[0], l2 = lp[1], l3 = lp[2];
-        const float2 a1 = ap[0], a2 = ap[1], a3 = ap[2];
-        const float2 b1 = bp[0], b2 = bp[1], b3 = bp[2];
+        const float2 l1 = CUBE ? f2b(0.f) : lp[0], l2 = lp[1], l3 = lp[2];   // CUBE: (-, kap2, kap3)
+        const float2 a1 = CUBE ? f2b(1.f) : ap[0], a2 = ap[1], a3 = ap[2];
+        const float2 b1 = CUBE ? f2b(0.f) : bp[0], b2 = bp[1], b3 = bp[2];
         lp += 3; ap += 3; bp += 3;
         const float2 kfb = f2b(kf);
         float2 g0[4], g1[4];
         float g0S, g1S;
+        if (CUBE) {
+            // the centre bin k1 = 3 jb + 1 has lambda1 == 0 exactly (it IS low-res bin jb): weight 1 into cell jb,
+            // none into cell jb + 1, so its term starts the "A" chain together with the previous k-block's "B" part
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 dlt = fma2(a[i], neg1, t[i]);
-            const float2 dk = fma2(gneg[i], kfb, ngd[i]);        // gneg * (k1 - disp)
-            const float2 dk1 = add2(dk, gneg[i]), dk2 = add2(dk1, gneg[i]);
-            const float2 u1 = mul2(ex2_2(fma2(l1, dlt, a[i])), dk);
-            const float2 u2 = mul2(ex2_2(fma2(l2, dlt, a[i])), dk1);
-            const float2 u3 = mul2(ex2_2(fma2(l3, dlt, a[i])), dk2);
-            g0[i] = fma2(a3, u3, fma2(a2, u2, fma2(a1, u1, s0i[i])));
-            g1[i] = fma2(b3, u3, fma2(b2, u2, mul2(b1, u1)));
-            a[i] = t[i];
-            s0i[i] = f2b(0.f);
-        }
-        {
-            const float dlt = tS - aS;
-            const float dk = __fmaf_rn(gnegS, kf, ngdS);
-            const float u1 = ex2_approx(__fmaf_rn(l1.x, dlt, aS)) * dk;
-            const float u2 = ex2_approx(__fmaf_rn(l2.x, dlt, aS)) * (dk + gnegS);
-            const float u3 = ex2_approx(__fmaf_rn(l3.x, dlt, aS)) * ((dk + gnegS) + gnegS);
-            g0S = __fmaf_rn(a3.x, u3, __fmaf_rn(a2.x, u2, __fmaf_rn(a1.x, u1, s0iS)));
-            g1S = __fmaf_rn(b3.x, u3, __fmaf_rn(b2.x, u2, b1.x * u1));
-            aS = tS;
-            s0iS = 0.f;
+            for (int i = 0; i < 4; ++i) {
+                const float2 ct = ex2_2(t[i]);
+                const float2 du = fma2(a[i], neg1, t[i]);
+                const float2 x = mul2(ca[i], ct), c2 = mul2(ca[i], ca[i]);
+                const float2 dk = fma2(gneg[i], kfb, ngd[i]);        // gneg * (k1 - disp)
+                const float2 dk1 = add2(dk, gneg[i]), dk2 = add2(dk1, gneg[i]);
+                const float2 q2 = mul2(x, ca[i]), q3 = mul2(x, ct);
+                const float2 u2 = mul2(fma2(q2, mul2(l2, du), q2), dk1);
+                const float2 u3 = mul2(fma2(q3, mul2(l3, du), q3), dk2);
+                g0[i] = fma2(a3, u3, fma2(a2, u2, fma2(mul2(c2, ca[i]), dk, pg[i])));
+                g1[i] = fma2(b3, u3, mul2(b2, u2));
+                a[i] = t[i]; ca[i] = ct;
+            }
+            {
+                const float ct = ex2_approx(tS);
+                const float du = tS - aS;
+                const float x = caS * ct;
+                const float dk = __fmaf_rn(gnegS, kf, ngdS);
+                const float q2 = x * caS, q3 = x * ct;
+                const float u2 = __fmaf_rn(q2, l2.x * du, q2) * (dk + gnegS);
+                const float u3 = __fmaf_rn(q3, l3.x * du, q3) * ((dk + gnegS) + gnegS);
+                g0S = __fmaf_rn(a3.x, u3, __fmaf_rn(a2.x, u2, __fmaf_rn(caS * caS * caS, dk, pgS)));
+                g1S = __fmaf_rn(b3.x, u3, b2.x * u2);
+                aS = tS; caS = ct;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 dlt = fma2(a[i], neg1, t[i]);
+                const float2 dk = fma2(gneg[i], kfb, ngd[i]);        // gneg * (k1 - disp)
+                const float2 dk1 = add2(dk, gneg[i]), dk2 = add2(dk1, gneg[i]);
+                const float2 u1 = mul2(ex2_2(fma2(l1, dlt, a[i])), dk);
+                const float2 u2 = mul2(ex2_2(fma2(l2, dlt, a[i])), dk1);
+                const float2 u3 = mul2(ex2_2(fma2(l3, dlt, a[i])), dk2);
+                g0[i] = fma2(a3, u3, fma2(a2, u2, mul2(a1, u1)));
+                g1[i] = fma2(b3, u3, fma2(b2, u2, mul2(b1, u1)));
+                a[i] = t[i];
+            }
+            {
+                const float dlt = tS - aS;
+                const float dk = __fmaf_rn(gnegS, kf, ngdS);
+                const float u1 = ex2_approx(__fmaf_rn(l1.x, dlt, aS)) * dk;
+                const float u2 = ex2_approx(__fmaf_rn(l2.x, dlt, aS)) * (dk + gnegS);
+                const float u3 = ex2_approx(__fmaf_rn(l3.x, dlt, aS)) * ((dk + gnegS) + gnegS);
+                g0S = __fmaf_rn(a3.x, u3, __fmaf_rn(a2.x, u2, a1.x * u1));
+                g1S = __fmaf_rn(b3.x, u3, __fmaf_rn(b2.x, u2, b1.x * u1));
+                aS = tS;
+            }
         }
         kf += 3.f;
         // cell jb = this k-block's "A" bin part + the previous k-block's "B" bin part: the spatial transpose is
         // linear, so the two parts are added per pixel first and transposed ONCE
+        if (!CUBE) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) g0[i] = add2(g0[i], pg[i]);
-        g0S += pgS;
+            for (int i = 0; i < 4; ++i) g0[i] = add2(g0[i], pg[i]);
+            g0S += pgS;
+        }
         if (jb >= j0) {
             float vA, vB;
             transpose(g0, g0S, vA, vB);
