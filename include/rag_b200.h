@@ -74,10 +74,12 @@ RAG_API int rag_disp_head_fwd(const float* cost_lr, float* disp, float* stats,
                       int B, int Dl, int Hl, int Wl, int maxdisp, void* stream);
 
 /* Gradient of the head w.r.t. cost_lr (replaces autograd through interpolate/softmin/mul/sum;
- * PyTorch's CUDA trilinear backward uses atomicAdd -- this is a deterministic gather).
+ * PyTorch's CUDA trilinear backward accumulates up to 125 atomicAdds per element in arrival order
+ * -- this one is bitwise deterministic: every element of gcost_lr receives exactly TWO contributions,
+ * added into the zeroed buffer with red.global.add; two addends commute, so arrival order cannot matter).
  * gdisp, disp [B,3Hl,3Wl]; stats [B,2,3Hl,3Wl] from the forward; gcost_lr [B,1,Dl,Hl,Wl].
- * scratch: nullable caller-owned work buffer of the same size as gcost_lr ([B,1,Dl,Hl,Wl], contents
- * undefined on return); when given (and maxdisp == 3*Dl) the faster two-buffer kernel is used. */
+ * scratch: may be NULL.  Only the A/B variants 2 and 3 of rag_disp_head_bwd_v use it (a caller-owned
+ * work buffer of the same size as gcost_lr, contents undefined on return). */
 RAG_API int rag_disp_head_bwd(const float* cost_lr, const float* gdisp, const float* disp,
                       const float* stats, float* gcost_lr, float* scratch,
                       int B, int Dl, int Hl, int Wl, int maxdisp, void* stream);

@@ -334,25 +334,30 @@ int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, cons
                   int B, int Dl, int Hl, int Wl, int D, int variant, cudaStream_t st) {
     if (!cost || !gdisp || !disp || !stats || !gcost) return fail(RAG_E_NULL, "disp_head_bwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 3) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 4) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
     if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_bwd: variant %d needs maxdisp == 3*Dl", variant);
-    if (variant >= 2 && !scratch) return fail(RAG_E_NULL, "disp_head_bwd: variant %d needs a scratch buffer", variant);
-    if (variant == -1) variant = x3 ? (scratch ? 3 : 1) : 0;
-    if (variant >= 2) {   // 3 = one exp2 per pixel and k-block (default), 2 = three
+    if ((variant == 2 || variant == 3) && !scratch) return fail(RAG_E_NULL, "disp_head_bwd: variant %d needs a scratch buffer", variant);
+    if (variant == -1) variant = x3 ? 4 : 0;
+    if (variant >= 2) {   // 4 (default) = one exp2 per pixel and k-block, parts added in place; 3 = same with scratch + combine; 2 = three exp2
         const int nJ = (Dl + kBwJ - 1) / kBwJ;
         const int strips = (Wl + 30) / 31;
         const int n_tasks = (Hl + 1) * nJ;
         dim3 grid(strips, (n_tasks + 3) / 4, B);
         const size_t smem = (size_t)3 * (D + 3) * sizeof(float2) + (size_t)4 * kBwWin * sizeof(float);
-        auto kern = variant == 3 ? head_bwd_x3w_kernel<true> : head_bwd_x3w_kernel<false>;
+        auto kern = variant == 4 ? head_bwd_x3w_kernel<true, true> : variant == 3 ? head_bwd_x3w_kernel<true, false> : head_bwd_x3w_kernel<false, false>;
+        if (variant == 4) {   // two commutative contributions per element into a zeroed buffer (see the kernel's header)
+            cudaError_t e = cudaMemsetAsync(gcost, 0, (size_t)B * Dl * Hl * Wl * sizeof(float), st);
+            if (e != cudaSuccess) return fail((int)e, "disp_head_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
+        }
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "disp_head_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         }
         kern<<<grid, 128, smem, st>>>(cost, gdisp, disp, stats, gcost, scratch, Dl, Hl, Wl, sd, nJ, n_tasks);
         if (int e = check_launch("disp_head_bwd(main)")) return e;
+        if (variant == 4) return 0;
         const size_t n = (size_t)B * Dl * Hl * Wl;
         const size_t n4 = (aligned(gcost, 16) && aligned(scratch, 16)) ? n / 4 : 0;
         const size_t work = n4 > 0 ? n4 : 1;

@@ -33,7 +33,12 @@ constexpr int kBwWin = kBwBins * 2 * kBwCols;
 // fp32 lambdas (|kap du| < 2e-4 wherever the bin matters, so the second order is < 2e-8).  The profile of
 // the three-exp2 form had the XU pipe 45 % and the FMA pipe 56 % busy with the issue slots at 63 %: the
 // MUFU bursts (27 per k-block, 8 clk each) were what the four warps of a scheduler queued on.
-template <bool CUBE>
+//
+// RED: both parts are added straight into a ZEROED gcost with red.global.add.f32 -- no scratch buffer, no
+// combine kernel.  Every element receives exactly two contributions (its row's "A" part and the row
+// above's "B" part); 0 + a + b and 0 + b + a are the same fp32 value (addition is commutative and 0 + a is
+// exact), so the result does not depend on the order the two arrive in: still bitwise deterministic.
+template <bool CUBE, bool RED>
 __global__ void __launch_bounds__(128, 4)
 head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gdisp, const float* __restrict__ disp,
                     const float* __restrict__ stats, float* __restrict__ gcost, float* __restrict__ scratch,
@@ -143,7 +148,7 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
         mnegS = m9[8]; gnegS = g9[8]; dspS = d9[8];
     }
     float* gout = gcost + (size_t)b * Dl * plane;
-    float* sout = scratch + (size_t)b * Dl * plane;
+    float* sout = (RED ? gcost : scratch) + (size_t)b * Dl * plane;
     const bool store_lane = lane >= 1 && lane_on;
     const bool has_a = rb >= 0;                // cell row rb exists
     const bool has_b = rb + 1 <= Hl - 1;       // cell row rb+1 exists
@@ -151,7 +156,7 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
     // sparse ground truth: no upstream gradient anywhere in the warp's 32 blocks -> zeros, no exp2 work
     if (!__any_sync(0xffffffffu, gabs != 0.f)) {
         __pipeline_wait_prior(0);
-        if (store_lane)
+        if (store_lane && !RED)
             for (int jb = j0; jb < j1; ++jb) {
                 if (has_a) gout[(size_t)jb * plane + (size_t)rb * Wl + c] = 0.f;
                 if (has_b) sout[(size_t)jb * plane + (size_t)(rb + 1) * Wl + c] = 0.f;
@@ -314,8 +319,13 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
         if (jb >= j0) {
             float vA, vB;
             transpose(g0, g0S, vA, vB);
-            if (st_a) *ga = vA;
-            if (st_b) *gb = vB;
+            if (RED) {
+                if (st_a) atomicAdd(ga, vA);
+                if (st_b) atomicAdd(gb, vB);
+            } else {
+                if (st_a) *ga = vA;
+                if (st_b) *gb = vB;
+            }
             ga += plane; gb += plane;
         }
 #pragma unroll

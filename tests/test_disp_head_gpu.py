@@ -117,7 +117,7 @@ def test_backward_parity(F_, case):
         gd[0, 0, 0] = 1.0
     _, gref = O.disp_head_grad_ref(cost, gd, md)
     _, g64 = O.disp_head_grad_f64(cost[:, 0].numpy(), gd.numpy(), md)
-    variants = [None, 0] + ([1, 2, 3] if md == 3 * dl else [])
+    variants = [None, 0] + ([1, 2, 3, 4] if md == 3 * dl else [])
     for vf in ([None, 0] if md != 3 * dl else [None, 0, 1, 2, 3] + ([4, 5, 6, 7, 9, 10, 11] if wl % 4 == 0 else [])):
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=vf)
         for v in variants:
@@ -160,7 +160,7 @@ def test_large_magnitude_costs_exercise_the_rescale_path(F_, sigma):
         tol = 2e-3 if sigma <= 30.0 else 1e-2
         assert np.abs(out - d64)[clear].max() <= tol, f"variant {v}: {np.abs(out - d64)[clear].max()}"
         assert torch.isfinite(stats).all()
-        for vb in (0, 1, 2, 3):
+        for vb in (0, 1, 2, 3, 4):
             gc = F_.disp_head_backward(cost.cuda(), gd.cuda(), disp, stats, md, variant=vb).cpu().numpy()
             assert np.isfinite(gc).all(), f"fwd {v} bwd {vb}"
             if sigma <= 30.0:
@@ -178,7 +178,7 @@ def test_backward_with_spatially_coherent_zero_gradient(F_):
     _, g64 = O.disp_head_grad_f64(cost[:, 0].numpy(), gd.numpy(), md)
     disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True)
     out0 = F_.disp_head_backward(cost.cuda(), gd.cuda(), disp, stats, md, variant=0)
-    for v in (1, 2, 3):
+    for v in (1, 2, 3, 4):
         out1 = F_.disp_head_backward(cost.cuda(), gd.cuda(), disp, stats, md, variant=v)
         assert maxnorm_rel(out1.cpu().numpy()[:, 0], g64) <= TOL_GRAD
         assert maxnorm_rel(out1.cpu().numpy(), out0.cpu().numpy()) <= TOL_GRAD
@@ -195,7 +195,7 @@ def test_backward_deterministic_and_vs_cuda_autograd(F_):
     g1 = cost.grad.clone()
     cost.grad = None
     F_.disp_head(cost, 192).backward(gd)
-    assert torch.equal(g1, cost.grad)          # bitwise repeatable (no atomics)
+    assert torch.equal(g1, cost.grad)          # bitwise repeatable (two commutative contributions per element)
     _, gref = O.disp_head_grad_ref(cost.detach(), gd, 192)   # PyTorch CUDA autograd (atomicAdd, fp32)
     assert maxnorm_rel(g1.cpu().numpy(), gref.cpu().numpy()) <= 2 * TOL_GRAD
 
@@ -261,3 +261,19 @@ def test_module_hygiene(F_):
         assert m(x).shape == (1, 12, 18)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 64, 4, 6))  # CPU tensor: no fallback
+
+
+def test_backward_red_variant_is_bitwise_deterministic(F_):
+    """Variant 4 adds the two row parts of every element into a zeroed buffer with red.global.add: two
+    commutative contributions, so the result must not depend on arrival order -- bitwise equal run to run and
+    equal to the scratch + combine variant (which adds the same two numbers) up to the sign of a zero."""
+    g = gen(404)
+    b, dl, hl, wl, md = 2, 64, 40, 96, 192
+    cost = randn((b, 1, dl, hl, wl), g).cuda()
+    gd = sparse_grad((b, 3 * hl, 3 * wl), g).cuda()
+    disp, stats = F_.disp_head_forward(cost, md, want_stats=True)
+    ref = F_.disp_head_backward(cost, gd, disp, stats, md, variant=3)
+    outs = [F_.disp_head_backward(cost, gd, disp, stats, md, variant=4) for _ in range(5)]
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
+    assert torch.equal(outs[0], ref)     # torch.equal treats -0.0 == +0.0

@@ -144,7 +144,7 @@ def main():
                 print("head_fwd variant", v, "skipped:", e)
     if want("head_bwd"):
         disp, stats = F_.disp_head_forward(cost_lr, md, True)
-        for v in (3, 2, 1, 0):
+        for v in (4, 3, 2, 1, 0):
             try:
                 it = a.iters if v >= 1 else 2
                 med, best = timeit(lambda: F_.disp_head_backward(cost_lr, gd, disp, stats, md, variant=v), it, flush)
