@@ -284,17 +284,17 @@ static bool cv_lean_ok(const float* x, const float* y, const float* cost, int Wf
     return Wf % 4 == 0 && Wf <= 2048 && aligned(x, 16) && aligned(y, 16) && aligned(cost, 16);
 }
 
-template <int NT = 256, int VPT = 2>
+template <int NT = 256, int VPT = 2, int ST = 0>
 static int launch_cv_fwd_lean(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
                               int per_sm, int dchunk, cudaStream_t st, size_t smem_floor = 0, bool dyn = false) {
     const int Wv = Wf / 4, Df4 = (Df + 3) & ~3;
     const size_t row_bytes = (size_t)16 * (Df4 + Wf + 4);          // four images of one row
     int R = std::min(Hf, (NT * VPT) / Wv);
-    while (R > 1 && R * row_bytes > 64 * 1024) --R;
+    while (R > 1 && R * row_bytes > (NT * VPT > 512 ? 100 : 64) * 1024) --R;
     const size_t smem = std::max(R * row_bytes, smem_floor);
     if (smem > 200 * 1024) return fail(RAG_E_SHAPE, "cost_volume_fwd(lean): Df=%d Wf=%d do not fit shared memory", Df, Wf);
     static std::atomic<unsigned> ticket{0};
-    auto kern = dyn ? cv_fwd_lean_kernel<NT, VPT, true> : cv_fwd_lean_kernel<NT, VPT, false>;
+    auto kern = dyn ? cv_fwd_lean_kernel<NT, VPT, true, ST> : cv_fwd_lean_kernel<NT, VPT, false, ST>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     // the L1/shared split of an SM cannot change while CTAs are resident: ask for the largest shared-memory
     // carve-out so that this kernel and the disparity head (which does the same) can share an SM
@@ -337,13 +337,19 @@ static int launch_cv_fwd_tma(const float* x, const float* y, float* cost, int B,
 int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
                     int variant, cudaStream_t st) {
     if (int e = check_cv_args(x, y, cost, B, C, Df, Hf, Wf)) return e;
-    if (variant < -1 || variant > 32) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 36) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
     if (variant == -1) variant = cv_lean_ok(x, y, cost, Wf) ? RAG_CV_FWD_LEAN : 0;
     if (variant >= 18) {   // lean thread-stationary kernel, persistent: 18 = 2 CTAs/SM, 19 = 1, 20 = 3, 21 = 4
         if (!cv_lean_ok(x, y, cost, Wf))
             return fail(RAG_E_VARIANT, "cost_volume_fwd: lean variants need Wf %% 4 == 0, Wf <= 2048 and 16-byte aligned pointers");
         // 22-25: 16-disparity chunks per item; 22 = 2 CTAs/SM, 23 = 1, 24 = 4, 25 = one CTA per item (not persistent)
         // 31 / 32: as 29 with 128 threads x 4 vectors / 512 threads x 1 vector per thread
+        // 33 / 34: as 29 with plain / write-through stores instead of st.global.cs (A/B of the store flavour)
+        // 35 / 36: as 29 with twice the rows per tile (512 x 2 / 256 x 4 vectors per thread)
+        if (variant == 35) return launch_cv_fwd_lean<512, 2>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
+        if (variant == 36) return launch_cv_fwd_lean<256, 4>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
+        if (variant == 33) return launch_cv_fwd_lean<256, 2, 1>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
+        if (variant == 34) return launch_cv_fwd_lean<256, 2, 2>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
         if (variant == 31) return launch_cv_fwd_lean<128, 4>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
         if (variant == 32) return launch_cv_fwd_lean<512, 1>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
         // 28-30: persistent with in-order (atomic counter) item hand-out, 16-disparity chunks: 2 / 1 / 4 CTAs per SM

@@ -29,7 +29,15 @@ __device__ unsigned int g_cv_ctr[64][2];
 // work on neighbouring rows / disparity chunks (a static stride lets them drift apart and costs 12 % of
 // the HBM write bandwidth); !DYN: item = blockIdx.x + k * gridDim.x (one item per CTA when the grid covers
 // all items).
-template <int NT, int VPT, bool DYN>
+// ST: store flavour of the output stream (0 = st.global.cs, 1 = plain st.global, 2 = st.global.wt)
+template <int ST>
+__device__ __forceinline__ void cv_store(float4* p, float4 v) {
+    if (ST == 0) __stcs(p, v);
+    else if (ST == 1) *p = v;
+    else __stwt(p, v);
+}
+
+template <int NT, int VPT, bool DYN, int ST = 0>
 __global__ void __launch_bounds__(NT)
 cv_fwd_lean_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ cost,
                    int BC, int C, int Df, int Hf, int Wf, int R, int n_tiles, int dchunk, int n_dchunks, int slot) {
@@ -126,7 +134,7 @@ cv_fwd_lean_kernel(const float* __restrict__ x, const float* __restrict__ y, flo
 #pragma unroll
             for (int i = 0; i < VPT; ++i) {
                 if (on[i]) {
-                    __stcs(reinterpret_cast<float4*>(pR[i]), *reinterpret_cast<const float4*>(src[i] + s * YS - d4));
+                    cv_store<ST>(reinterpret_cast<float4*>(pR[i]), *reinterpret_cast<const float4*>(src[i] + s * YS - d4));
                     float4 m = xv[i];
                     if (d > dA[i]) {
                         m.x = t0[i] + 0 >= d ? m.x : 0.f;
@@ -134,7 +142,7 @@ cv_fwd_lean_kernel(const float* __restrict__ x, const float* __restrict__ y, flo
                         m.z = t0[i] + 2 >= d ? m.z : 0.f;
                         m.w = t0[i] + 3 >= d ? m.w : 0.f;
                     }
-                    __stcs(reinterpret_cast<float4*>(pL[i]), m);
+                    cv_store<ST>(reinterpret_cast<float4*>(pL[i]), m);
                 }
                 pL[i] += plane;
                 pR[i] += plane;

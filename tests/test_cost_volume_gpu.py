@@ -57,7 +57,7 @@ def test_forward_bit_exact(F_, shape):
     ref = O.cost_volume_ref(x, y, md)
     df = int(md / 3)
     tma = (11, 12, 13, 14) if (wf % 4 == 0 and df % 4 == 0 and df <= wf) else ()
-    for variant in (None, 0, 1, 2, 3) + ((4, 8, 9, 10, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32) if wf % 4 == 0 else ()) + tma:
+    for variant in (None, 0, 1, 2, 3) + ((4, 8, 9, 10, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36) if wf % 4 == 0 else ()) + tma:
         out = F_.cost_volume_forward(x.cuda(), y.cuda(), int(md / 3), variant=variant)
         assert torch.equal(out.cpu(), ref), f"variant {variant}"
 

@@ -39,7 +39,7 @@ def test_cost_volume_guards(L, shape):
     g = gen(1)
     x, y = randn((b, c, hf, wf), g).cuda(), randn((b, c, hf, wf), g).cuda()
     n = b * 2 * c * df * hf * wf
-    variants = [0, 1, 2, 3] + ([4, 8, 9, 10, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32] if wf % 4 == 0 else []) + ([11, 12, 13, 14] if (wf % 4 == 0 and df % 4 == 0 and df <= wf) else [])
+    variants = [0, 1, 2, 3] + ([4, 8, 9, 10, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36] if wf % 4 == 0 else []) + ([11, 12, 13, 14] if (wf % 4 == 0 and df % 4 == 0 and df <= wf) else [])
     for v in variants:
         buf, out = window(n)
         assert L.rag_cost_volume_fwd_v(x.data_ptr(), y.data_ptr(), out.data_ptr(), b, c, df, hf, wf, v, st()) == 0

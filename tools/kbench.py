@@ -82,7 +82,7 @@ def main():
         return not a.only or k in a.only.split(",")
 
     if want("cv_fwd"):
-        for v in (0, 29, 32):
+        for v in (0, 29, 35, 36, 32):
             med, best = timeit(lambda: F_.cost_volume_forward(x, y, df, variant=v), a.iters, flush)
             report("cv_fwd", v, med, best, vol_bytes)
         # torch baseline for scale: a plain device copy of the same number of bytes
