@@ -64,7 +64,7 @@ def test_head_guards(L, shape):
     cl = randn((b, 1, dl, hl, wl), g).cuda()
     npx = b * 9 * hl * wl
     x3 = md == 3 * dl
-    fv = [0] + ([1, 2, 3] if x3 else []) + ([4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14] if x3 and wl % 4 == 0 else [])
+    fv = [0] + ([1, 2, 3] if x3 else []) + ([4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16] if x3 and wl % 4 == 0 else [])
     for v in fv:
         bd, disp = window(npx)
         bs, stats = window(2 * npx)
@@ -74,14 +74,16 @@ def test_head_guards(L, shape):
         assert not (disp == CANARY).any() and not (stats == CANARY).any(), f"head_fwd variant {v} left outputs unwritten"
     gd = randn((b, 3 * hl, 3 * wl), g).cuda()
     nv = b * dl * hl * wl
-    for v in [0] + ([1, 2] if x3 else []):
+    for v in [0] + ([1, 2, 3, 4] if x3 else []):
         bg, gcl = window(nv)
         bsc, scr = window(nv)
         assert L.rag_disp_head_bwd_v(cl.data_ptr(), gd.data_ptr(), disp.data_ptr(), stats.data_ptr(), gcl.data_ptr(), scr.data_ptr(), b, dl, hl, wl, md, v, st()) == 0
         torch.cuda.synchronize()
         assert intact(bg, nv) and intact(bsc, nv), f"head_bwd variant {v}"
-        if v == 2:
-            assert not (scr == CANARY).any(), "head_bwd variant 2 left scratch elements unwritten"
+        if v in (2, 3):
+            assert not (scr == CANARY).any(), f"head_bwd variant {v} left scratch elements unwritten"
+        else:
+            assert (scr == CANARY).all(), f"head_bwd variant {v} must not touch the scratch buffer"
         assert not (gcl == CANARY).any(), f"head_bwd variant {v} left outputs unwritten"
     bu, up = window(b * md * 9 * hl * wl)
     assert L.rag_upsample_trilinear(cl.data_ptr(), up.data_ptr(), b, dl, hl, wl, md, 1, st()) == 0
