@@ -46,6 +46,10 @@ namespace rag {
 // the 2^24 threshold of the older kernels the whole-warp rescale path ran so often on large-magnitude costs
 // that the kernel took 0.39 ms instead of 0.17 ms at sigma = 20.)
 constexpr float kX3rTau = 32.0f;
+// When ANY pixel of the warp crosses kX3rTau the whole warp walks the rescale path anyway, so every pixel
+// whose new bin beats its reference by more than kX3rPiggy re-anchors on that occasion: its next crossing
+// moves further away at no extra cost (the reference lands exactly on a bin, so nothing is lost in precision).
+constexpr float kX3rPiggy = 4.0f;
 
 struct X3rPair {                          // per pixel pair
     float2 c[2];                          // ping-pong: c_j and (after the step) c_{j+1}
@@ -248,7 +252,7 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
         constexpr int cur = decltype(cur_tag)::value;
         fold();
         auto fix = [&](float& tt, float& aa, float& mn, float& cc, float& c2, float& ps, float& q, int slot, bool hi_lane) {
-            if (tt > kX3rTau) {
+            if (tt > kX3rPiggy) {
                 const float f = ex2_approx(-tt), f3 = ex2_approx(-3.f * tt);
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
@@ -265,7 +269,7 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
             fix(t[i].x, a[i].x, mneg[i].x, st[i].c[cur].x, st[i].c2.x, st[i].ps.x, st[i].q.x, 4 * i, false);
             fix(t[i].y, a[i].y, mneg[i].y, st[i].c[cur].y, st[i].c2.y, st[i].ps.y, st[i].q.y, 4 * i, true);
         }
-        if (tS > kX3rTau) {
+        if (tS > kX3rPiggy) {
             const float f = ex2_approx(-tS), f3 = ex2_approx(-3.f * tS);
             float2 d = mytot[16 * NT], n = mytot[17 * NT];
             d.x *= f3; d.y *= f3; n.x *= f3; n.y *= f3;
