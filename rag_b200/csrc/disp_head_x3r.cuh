@@ -250,30 +250,34 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     // `cur` = which half of the c ping-pong holds c_j.
     auto rescale = [&](auto cur_tag, float2 (&t)[4], float& tS, float2 (&a)[4], float& aS) {
         constexpr int cur = decltype(cur_tag)::value;
-        fold();
-        auto fix = [&](float& tt, float& aa, float& mn, float& cc, float& c2, float& ps, float& q, int slot, bool hi_lane) {
+        // the running group sums (registers) and the chunk totals (shared memory; the lo words only exist with
+        // TWOSUM) are both scaled in place -- no fold, so an event costs ~160 instead of ~270 instructions
+        auto fix = [&](float& tt, float& aa, float& mn, float& cc, float& c2, float& ps, float& q, float& gs, float& gt,
+                       int slot, bool hi_lane) {
             if (tt > kX3rPiggy) {
                 const float f = ex2_approx(-tt), f3 = ex2_approx(-3.f * tt);
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
+                for (int s = 0; s < 4; s += (TWOSUM ? 1 : 2)) {
                     float2 v = mytot[(slot + s) * NT];
                     if (hi_lane) v.y *= f3; else v.x *= f3;
                     mytot[(slot + s) * NT] = v;
                 }
+                gs *= f3; gt *= f3;
                 cc *= f; ps *= f; q *= f; c2 = cc * cc;
                 mn -= tt; aa -= tt; tt = 0.f;
             }
         };
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            fix(t[i].x, a[i].x, mneg[i].x, st[i].c[cur].x, st[i].c2.x, st[i].ps.x, st[i].q.x, 4 * i, false);
-            fix(t[i].y, a[i].y, mneg[i].y, st[i].c[cur].y, st[i].c2.y, st[i].ps.y, st[i].q.y, 4 * i, true);
+            fix(t[i].x, a[i].x, mneg[i].x, st[i].c[cur].x, st[i].c2.x, st[i].ps.x, st[i].q.x, st[i].S.x, st[i].T.x, 4 * i, false);
+            fix(t[i].y, a[i].y, mneg[i].y, st[i].c[cur].y, st[i].c2.y, st[i].ps.y, st[i].q.y, st[i].S.y, st[i].T.y, 4 * i, true);
         }
         if (tS > kX3rPiggy) {
             const float f = ex2_approx(-tS), f3 = ex2_approx(-3.f * tS);
             float2 d = mytot[16 * NT], n = mytot[17 * NT];
             d.x *= f3; d.y *= f3; n.x *= f3; n.y *= f3;
             mytot[16 * NT] = d; mytot[17 * NT] = n;
+            so.S *= f3; so.T *= f3;
             so.c[cur] *= f; so.ps *= f; so.q *= f; so.c2 = so.c[cur] * so.c[cur];
             mnegS -= tS; aS -= tS; tS = 0.f;
         }
