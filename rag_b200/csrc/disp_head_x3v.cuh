@@ -128,7 +128,7 @@ head_fwd_x3v_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     const float2 h0p = f2(hs0[0], hs0[1]), h1p = f2(hs1[0], hs1[1]);
 
     float2 mneg[4], ea[4], eb[4];   // ea/eb: ping-pong relative exponents (lower / upper bin of the k-block)
-    float mnegS, eaS, ebS;
+    float mnegS = 0.f, eaS = 0.f, ebS = 0.f;
     X3vAcc acc;
     const float kc = 0.5f * (float)D;
     float2 kf1 = f2b(1.f - kc), kf2 = f2b(2.f - kc), kf3 = f2b(3.f - kc);
