@@ -38,6 +38,8 @@ constexpr int kBwWin = kBwBins * 2 * kBwCols;
 // combine kernel.  Every element receives exactly two contributions (its row's "A" part and the row
 // above's "B" part); 0 + a + b and 0 + b + a are the same fp32 value (addition is commutative and 0 + a is
 // exact), so the result does not depend on the order the two arrive in: still bitwise deterministic.
+// (red.global.add.f32 flushes subnormal addends and sums to zero, as PyTorch's own atomicAdd backward does;
+// against the scratch + combine variant the result differs at most by that and by the sign of a zero.)
 template <bool CUBE, bool RED>
 __global__ void __launch_bounds__(128, 4)
 head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gdisp, const float* __restrict__ disp,
