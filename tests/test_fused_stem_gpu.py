@@ -176,7 +176,7 @@ def test_golden_from_the_reference_layer():
     from rag_b200.fused_stem import cv_stem_forward
     from tests.conftest import GOLDEN
 
-    paths = sorted(glob.glob(os.path.join(GOLDEN, "stem_*.npz")))
+    paths = sorted(glob.glob(os.path.join(GOLDEN, "stem_b*.npz")))
     assert paths
     for path in paths:
         z = np.load(path)

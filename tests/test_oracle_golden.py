@@ -108,3 +108,38 @@ def test_stage_oracle_matches_reference():
     z = np.load(os.path.join(GOLDEN, "stage_h10_w14.npz"))
     out = O.normalize_pad_ref(z["img"], int(z["top_pad"]), int(z["right_pad"]))
     np.testing.assert_allclose(out, z["out"], rtol=0, atol=1e-6)
+
+
+def _bn(d, training):
+    mean = torch.from_numpy(d["bn_mean0" if training else "bn_mean"].copy())
+    var = torch.from_numpy(d["bn_var0" if training else "bn_var"].copy())
+    return dict(weight=torch.from_numpy(d["bn_weight"]).requires_grad_(training), bias=torch.from_numpy(d["bn_bias"]).requires_grad_(training),
+                mean=mean, var=var, eps=float(d["bn_eps"]), momentum=float(d["bn_momentum"]) if training else 0.1)
+
+
+def test_stem_and_last_conv_oracle_match_the_reference_layers():
+    """stem3d0 on the reference-built volume (eval) and last_3_3d: the reference's own ConvBR_3d outputs."""
+    d = np.load(os.path.join(GOLDEN, "stem_b1_c12_h5_w12_md24.npz"))
+    out = O.stem_ref(torch.from_numpy(d["x"]), torch.from_numpy(d["y"]), torch.from_numpy(d["weight"]), _bn(d, False), int(d["maxdisp"]))
+    np.testing.assert_allclose(out.numpy(), d["out"], rtol=1e-5, atol=1e-6)
+    d = np.load(os.path.join(GOLDEN, "last3_b1_c12_d18_h9_w12.npz"))
+    out = O.last_conv_ref(torch.from_numpy(d["feat"]), torch.from_numpy(d["weight"]))
+    np.testing.assert_allclose(out.numpy(), d["out"], rtol=1e-5, atol=1e-6)
+
+
+def test_training_mode_stem_oracle_matches_reference_forward_backward_and_running_stats():
+    """The pin for the next round's fused training path: batch-statistics BatchNorm,
+    gradients w.r.t. both feature maps, the conv weight and the BN affine parameters, running stats after the step."""
+    d = np.load(os.path.join(GOLDEN, "trainstem_b2_c12_h5_w12_md24.npz"))
+    x = torch.from_numpy(d["x"]).requires_grad_(True)
+    y = torch.from_numpy(d["y"]).requires_grad_(True)
+    w = torch.from_numpy(d["weight"]).requires_grad_(True)
+    bn = _bn(d, True)
+    out = O.stem_ref(x, y, w, bn, int(d["maxdisp"]), training=True)
+    np.testing.assert_allclose(out.detach().numpy(), d["out"], rtol=1e-5, atol=1e-6)
+    out.backward(torch.from_numpy(d["gout"]))
+    for got, name in ((x.grad, "gx"), (y.grad, "gy"), (w.grad, "gweight"), (bn["weight"].grad, "gbn_weight"), (bn["bias"].grad, "gbn_bias")):
+        ref = d[name]
+        assert np.abs(got.numpy() - ref).max() <= 1e-5 * np.abs(ref).max(), name
+    np.testing.assert_allclose(bn["mean"].numpy(), d["bn_mean1"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(bn["var"].numpy(), d["bn_var1"], rtol=1e-6, atol=1e-7)
