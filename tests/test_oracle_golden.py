@@ -143,3 +143,24 @@ def test_training_mode_stem_oracle_matches_reference_forward_backward_and_runnin
         assert np.abs(got.numpy() - ref).max() <= 1e-5 * np.abs(ref).max(), name
     np.testing.assert_allclose(bn["mean"].numpy(), d["bn_mean1"], rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(bn["var"].numpy(), d["bn_var1"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("shape", [(1, 12, 5, 12, 24), (2, 3, 4, 9, 15), (1, 2, 3, 6, 30)], ids=str)
+def test_volume_free_stem_algebra(shape):
+    """The algebra the fused stem kernel rests on: tap sums over 18 row maps, and LF + RF
+    where every tap is valid, equal the 3-D convolution of the materialised volume (fp64, incl. Df > Wf)."""
+    b, c, hf, wf, md = shape
+    g = torch.Generator().manual_seed(hf * wf)
+    x = torch.randn(b, c, hf, wf, generator=g)
+    y = torch.randn(b, c, hf, wf, generator=g)
+    w = torch.randn(5, 2 * c, 3, 3, 3, generator=g)
+    vol = O.cost_volume_ref(x, y, md)
+    want = torch.nn.functional.conv3d(vol.double(), w.double(), None, 1, 1).numpy()
+    for collapsed in (False, True):
+        got = O.stem_volume_free_f64(x.numpy(), y.numpy(), w.numpy(), md, collapsed=collapsed)
+        assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max()), f"collapsed={collapsed}"
+    d = np.load(os.path.join(GOLDEN, "stem_b1_c12_h5_w12_md24.npz"))
+    z = O.stem_volume_free_f64(d["x"], d["y"], d["weight"], int(d["maxdisp"]))
+    sc = d["bn_weight"] / np.sqrt(d["bn_var"] + float(d["bn_eps"]))
+    out = np.maximum(z * sc[None, :, None, None, None] + (d["bn_bias"] - d["bn_mean"] * sc)[None, :, None, None, None], 0)
+    np.testing.assert_allclose(out, d["out"], rtol=1e-5, atol=2e-6)      # the reference's own (fp32) layer output
