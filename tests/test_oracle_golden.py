@@ -164,3 +164,19 @@ def test_volume_free_stem_algebra(shape):
     sc = d["bn_weight"] / np.sqrt(d["bn_var"] + float(d["bn_eps"]))
     out = np.maximum(z * sc[None, :, None, None, None] + (d["bn_bias"] - d["bn_mean"] * sc)[None, :, None, None, None], 0)
     np.testing.assert_allclose(out, d["out"], rtol=1e-5, atol=2e-6)      # the reference's own (fp32) layer output
+
+
+def test_stem_batch_moments_from_rows_match_the_training_golden():
+    """Batch statistics of the stem convolution from the LF/RF rows (window sums, no volume): equal to the moments of
+    z itself, and to the batch mean / variance the reference's BatchNorm3d used in train() (running-stat update)."""
+    d = np.load(os.path.join(GOLDEN, "trainstem_b2_c12_h5_w12_md24.npz"))
+    md = int(d["maxdisp"])
+    s1, s2, n = O.stem_batch_moments_f64(d["x"], d["y"], d["weight"], md)
+    z = O.stem_volume_free_f64(d["x"], d["y"], d["weight"], md)
+    np.testing.assert_allclose(s1, z.sum(axis=(0, 2, 3, 4)), rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(s2, (z ** 2).sum(axis=(0, 2, 3, 4)), rtol=1e-12)
+    mean = s1 / n
+    var_unbiased = (s2 / n - mean ** 2) * n / (n - 1)
+    mom = float(d["bn_momentum"])
+    np.testing.assert_allclose((1 - mom) * d["bn_mean0"] + mom * mean, d["bn_mean1"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose((1 - mom) * d["bn_var0"] + mom * var_unbiased, d["bn_var1"], rtol=1e-5, atol=1e-6)
