@@ -180,3 +180,18 @@ def test_stem_batch_moments_from_rows_match_the_training_golden():
     mom = float(d["bn_momentum"])
     np.testing.assert_allclose((1 - mom) * d["bn_mean0"] + mom * mean, d["bn_mean1"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose((1 - mom) * d["bn_var0"] + mom * var_unbiased, d["bn_var1"], rtol=1e-5, atol=1e-6)
+
+
+def test_volume_free_stem_backward_matches_the_training_golden():
+    """gx, gy, gweight of the training-mode stem from 2-D triangular / diagonal sums of the conv-output gradient
+    (no volume, no volume gradient) against the reference's autograd through the materialised volume."""
+    d = np.load(os.path.join(GOLDEN, "trainstem_b2_c12_h5_w12_md24.npz"))
+    md = int(d["maxdisp"])
+    z = torch.from_numpy(O.stem_volume_free_f64(d["x"], d["y"], d["weight"], md)).requires_grad_(True)
+    out = torch.nn.functional.relu(torch.nn.functional.batch_norm(
+        z, None, None, torch.from_numpy(d["bn_weight"]).double(), torch.from_numpy(d["bn_bias"]).double(), True, 0.1, float(d["bn_eps"])))
+    out.backward(torch.from_numpy(d["gout"]).double())
+    gx, gy, gw = O.stem_backward_volume_free_f64(d["x"], d["y"], d["weight"], z.grad.numpy(), md)
+    for got, name in ((gx, "gx"), (gy, "gy"), (gw, "gweight")):
+        ref = d[name]
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max(), (name, np.abs(got - ref).max() / np.abs(ref).max())
