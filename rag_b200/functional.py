@@ -132,7 +132,7 @@ def disp_head_backward(cost_lr, gdisp, disp, stats, maxdisp: int, variant: int |
     if gcost.numel() == 0:
         return gcost
     L = _cabi.lib()
-    # work buffer for the two-buffer kernel (same size as the gradient; the caller owns all memory)
+    # work buffer of the scratch + combine A/B variants only (the default adds both parts in place)
     scratch = torch.empty_like(cost_lr) if (maxdisp == 3 * dl and variant in (2, 3)) else None
     sp = scratch.data_ptr() if scratch is not None else None
     with torch.cuda.device(cost_lr.device):
