@@ -101,6 +101,19 @@ RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int 
  * one batch with the disparity head of another, rag_b200.pipeline.OverlappedPath): launch the cost
  * volume FIRST with RAG_CV_FWD_SHARED -- a persistent grid of one 512-thread CTA per SM whose store
  * stream leaves most of the SM to the FP32-bound head -- then the head with its default variant. */
+/* Variant ids (-1 = the default the plain entry points use; ids outside a range return RAG_E_VARIANT):
+ *   rag_cost_volume_fwd_v  0-3   first generation (items dealt to threads; any width / alignment)
+ *                          4-10  occupancy and static persistent experiments
+ *                          11-15 TMA bulk-store kernel (cp.async.bulk shared->global); 16/17 write half the output (probes)
+ *                          18-27 lean thread-stationary kernel, static grids / one CTA per item
+ *                          28-32 lean kernel, persistent with in-order item hand-out (29 = default, 32 = SM sharing)
+ *                          33-36 store flavour (plain, .wt) and taller-tile A/B of 29
+ *   rag_cost_volume_bwd_v  0/2 = 128-bit vector kernel (default when Wf % 4 == 0), 1 = scalar, 3 = high-occupancy build
+ *   rag_disp_head_fwd_v    0 = any (Dl, maxdisp); 1-3 x3 kernels; 4-9 shared-memory tiled generations;
+ *                          10 = default (cube-root form), 11-13 its correction / summation A/B, 14-16 smem-capped
+ *   rag_disp_head_bwd_v    0 = any ratio gather; 1 = first x3 kernel; 2/3 = block-row tasks with scratch + combine
+ *                          (three / one exp2 per k-block); 4 = default (one exp2, parts added in place)
+ *   rag_cv_stem_fwd_v      0 = direct (any shape); 1 = collapsed, scalar; 2 = default (packed phase 1)            */
 #define RAG_CV_FWD_LEAN 29    /* default when Wf % 4 == 0: persistent, one 256-thread CTA per SM           */
 #define RAG_CV_FWD_SHARED 32  /* same kernel, one 512-thread CTA per SM: best when sharing SMs with the head */
 RAG_API int rag_cost_volume_fwd_v(const float* x, const float* y, float* cost,
