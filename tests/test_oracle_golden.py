@@ -195,3 +195,14 @@ def test_volume_free_stem_backward_matches_the_training_golden():
     for got, name in ((gx, "gx"), (gy, "gy"), (gw, "gweight")):
         ref = d[name]
         assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max(), (name, np.abs(got - ref).max() / np.abs(ref).max())
+
+
+def test_training_step_of_the_stem_volume_free_end_to_end():
+    """Forward (batch-statistics BatchNorm + ReLU) and every gradient of the stem from the volume-free pieces alone."""
+    d = np.load(os.path.join(GOLDEN, "trainstem_b2_c12_h5_w12_md24.npz"))
+    out, gx, gy, gw, gg, gb, _ = O.stem_train_volume_free_f64(d["x"], d["y"], d["weight"], d["bn_weight"], d["bn_bias"],
+                                                              float(d["bn_eps"]), d["gout"], int(d["maxdisp"]))
+    np.testing.assert_allclose(out, d["out"], rtol=1e-5, atol=2e-6)
+    for got, name in ((gx, "gx"), (gy, "gy"), (gw, "gweight"), (gg, "gbn_weight"), (gb, "gbn_bias")):
+        ref = d[name]
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max(), (name, np.abs(got - ref).max() / np.abs(ref).max())
