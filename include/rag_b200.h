@@ -153,6 +153,13 @@ RAG_API int rag_cv_stem_fwd(const float* x, const float* y, const float* w, cons
 RAG_API int rag_cv_stem_fwd_v(const float* x, const float* y, const float* w, const float* scale, const float* shift,
                       int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, int variant, void* stream);
 
+/* Batch statistics of that convolution for a training-mode BatchNorm3d, again without the volume or the conv
+ * output (first piece of the training path): moments [B,Hf,O,2] DOUBLE, per (b,h,o) row
+ * (sum z, sum z^2) over its Df x Wf outputs z = conv3d(cost_volume(x, y), w)[b,o,:,h,:]; the caller sums the rows
+ * (mean = S1/n, biased var = S2/n - mean^2, n = B*Df*Hf*Wf).  Needs C == 12, O <= 32, Df >= 3, Wf % 4 == 0. */
+RAG_API int rag_cv_stem_moments(const float* x, const float* y, const float* w, double* moments,
+                        int B, int C, int O, int Df, int Hf, int Wf, void* stream);
+
 /* The Matching Net's last layer, the producer of the head's input (inference):
  * `self.last_3_3d[i](...)` = ConvBR_3d(C, 1, 3, 1, 1, bn=False, relu=False), src/models/rag_model.py:269,361-365,
  * i.e. a bias-free Conv3d C -> 1, 3x3x3, stride 1, zero padding 1 (src/automl/operations_3d.py:31-47):

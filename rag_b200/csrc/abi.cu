@@ -17,6 +17,7 @@ int loss_metrics_sums(const float*, const float*, double*, double*, int, int, in
 int smooth_l1_bwd(const float*, const float*, const double*, const float*, float*, int, int, int, float, cudaStream_t);
 int normalize_pad(const uint8_t*, float*, int, int, int, int, int, cudaStream_t);
 int cv_stem_fwd(const float*, const float*, const float*, const float*, const float*, int, float*, int, int, int, int, int, int, int, cudaStream_t);
+int cv_stem_moments(const float*, const float*, const float*, double*, int, int, int, int, int, int, cudaStream_t);
 int conv3d_c1_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 }  // namespace rag
 
@@ -83,6 +84,10 @@ RAG_API int rag_smooth_l1_bwd(const float* est, const float* gt, const double* s
 RAG_API int rag_cv_stem_fwd(const float* x, const float* y, const float* w, const float* scale, const float* shift,
                     int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, void* stream) {
     return cv_stem_fwd(x, y, w, scale, shift, relu, out, B, C, O, Df, Hf, Wf, -1, ST(stream));
+}
+RAG_API int rag_cv_stem_moments(const float* x, const float* y, const float* w, double* moments, int B, int C, int O, int Df, int Hf, int Wf,
+                                void* stream) {
+    return cv_stem_moments(x, y, w, moments, B, C, O, Df, Hf, Wf, ST(stream));
 }
 RAG_API int rag_cv_stem_fwd_v(const float* x, const float* y, const float* w, const float* scale, const float* shift,
                       int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, int variant, void* stream) {

@@ -229,6 +229,7 @@ cv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, con
 // out round-robin, so launches with different weights can overlap.
 constexpr int kStemWSlots = 4, kStemWMaxO = 32, kStemWPerO = 2 * 12 * 3 * 12;
 __device__ float g_stem_w[kStemWSlots][kStemWMaxO * kStemWPerO];
+static std::atomic<unsigned> g_stem_ticket{0};   // host side: next weight slot (shared by every launcher below)
 
 __global__ void __launch_bounds__(256)
 stem_regroup_kernel(const float* __restrict__ w, int C, int slot) {
@@ -244,11 +245,14 @@ stem_regroup_kernel(const float* __restrict__ w, int C, int slot) {
     }
 }
 
-template <int C, bool RELU>
+// MOMENTS: instead of streaming the output, reduce (sum z, sum z^2) of this CTA's Df x Wf conv outputs (scale/shift
+// ignored) into moments[((b*Hf + h)*O + o)*2 + {0,1}] in fp64 -- the batch-statistics pass of a training-mode
+// BatchNorm that never sees the volume or the conv output (oracle.stem_batch_moments_f64).
+template <int C, bool RELU, bool MOMENTS = false>
 __global__ void __launch_bounds__(512, 2)
 cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w,
                     const float* __restrict__ scale, const float* __restrict__ shift,
-                    float* __restrict__ out, int O, int Df, int Hf, int Wf, int wslot) {
+                    float* __restrict__ out, int O, int Df, int Hf, int Wf, int wslot, double* __restrict__ moments) {
     extern __shared__ __align__(16) float stem_smem[];
     const int Wp = Wf + 2 * kStemPad;
     float* wsm = stem_smem;                       // [side][c][kh][12]: 9 (kd,kw) weights + pad
@@ -348,7 +352,7 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
 
     // ---- phase 2 (as in the first kernel), with the folded BatchNorm applied to the rows once instead of to
     // every output: LF' = sc*LF + sh, RF' = sc*RF, so that out = relu?(LF' + RF') ----
-    const float sc = scale ? __ldg(scale + o) : 1.f, sh = shift ? __ldg(shift + o) : 0.f;
+    const float sc = (!MOMENTS && scale) ? __ldg(scale + o) : 1.f, sh = (!MOMENTS && shift) ? __ldg(shift + o) : 0.f;
     for (int col = tid; col < Wf; col += NT) {
         float S[3], T[3];
 #pragma unroll
@@ -380,6 +384,46 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
         if (j < 4) band[d * 4 + j] = v; else lastcol[d] = v;
     }
     __syncthreads();
+
+    if constexpr (MOMENTS) {
+        // z(d, w) by the same rule as the output pass: 0 left of the band, the tap tables on the band and in the last
+        // column, LF + RF (class by d) elsewhere.  fp64 from the first addition on: the sums feed a variance.
+        double s1 = 0.0, s2 = 0.0;
+        for (int col = tid; col < Wf; col += NT) {
+            for (int d = 0; d < Df; ++d) {
+                const int u = col - d;
+                float z;
+                if (u <= -3) z = 0.f;
+                else if (u <= 1) z = band[d * 4 + (u + 2)];
+                else if (col == Wf - 1) z = lastcol[d];
+                else {
+                    const int cls = d == 0 ? 0 : (d == Df - 1 ? 2 : 1);
+                    z = LF[cls * Wp + kStemPad + col] + RF[(cls * 4) * Wp + kStemPad + u];
+                }
+                s1 += (double)z;
+                s2 += (double)z * (double)z;
+            }
+        }
+        // block reduction in a fixed order (deterministic) without warp collectives: the block size need not be a
+        // multiple of 32
+        __shared__ double red1[512], red2[512];
+        red1[tid] = s1; red2[tid] = s2;
+        __syncthreads();
+        if (tid < 32) {
+            double a = 0.0, b2 = 0.0;
+            for (int i = tid; i < NT; i += 32) { a += red1[i]; b2 += red2[i]; }
+            red1[tid] = a; red2[tid] = b2;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0.0, b2 = 0.0;
+            const int nred = NT < 32 ? NT : 32;
+            for (int i = 0; i < nred; ++i) { a += red1[i]; b2 += red2[i]; }
+            double* m = moments + (((size_t)b * Hf + h) * O + o) * 2;
+            m[0] = a; m[1] = b2;
+        }
+        return;
+    }
 
     // ---- phase 3: thread keeps its 4-column group; rows d = d0, d0 + rows_per_pass, ... ----
     // Main pass is branch-free: every element is LF + RF (masked to 0 where w - d <= -3, i.e. all taps masked);
@@ -487,6 +531,34 @@ cv_stem_direct_kernel(const float* __restrict__ x, const float* __restrict__ y, 
     out[(size_t)b * n + idx] = relu ? fmaxf(v, 0.f) : v;
 }
 
+// Batch moments of the stem convolution: moments [B,Hf,O,2] fp64 = per (b,h,o) row (sum z, sum z^2) over Df x Wf.
+int cv_stem_moments(const float* x, const float* y, const float* w, double* moments, int B, int C, int O, int Df, int Hf, int Wf,
+                    cudaStream_t st) {
+    if (!x || !y || !w || !moments) return fail(RAG_E_NULL, "cv_stem_moments: null pointer");
+    if (B <= 0 || O <= 0 || Df <= 0 || Hf <= 0 || Wf <= 0 || B > 65535 || O > 65535)
+        return fail(RAG_E_SHAPE, "cv_stem_moments: bad shape B=%d C=%d O=%d Df=%d Hf=%d Wf=%d", B, C, O, Df, Hf, Wf);
+    const int Wv = Wf / 4;
+    if (!(C == 12 && Df >= 3 && Wf >= 8 && Wf % 4 == 0 && Wv <= 512 && O <= kStemWMaxO && aligned(x, 8) && aligned(y, 8)))
+        return fail(RAG_E_SHAPE, "cv_stem_moments: needs C == 12, O <= %d, Df >= 3, Wf >= 8, Wf %% 4 == 0, Wf <= 2048 and 8-byte aligned features", kStemWMaxO);
+    int k = 384 / Wv;
+    if (k < 1) k = 1;
+    int nt = k * Wv;
+    if (nt < 128) nt = ((128 + Wv - 1) / Wv) * Wv;
+    const size_t smem2 = ((size_t)2 * C * 36 + (size_t)33 * (Wf + 2 * kStemPad) + (size_t)4 * Df + ((Df + 3) & ~3)) * sizeof(float) +
+                         (size_t)kStemStages * 3 * nt * sizeof(float2);
+    if (smem2 > 200 * 1024) return fail(RAG_E_SHAPE, "cv_stem_moments: Wf=%d too wide for shared memory", Wf);
+    auto kern = cv_stem_fwd2_kernel<12, false, true>;
+    if (smem2 > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return fail((int)e, "cv_stem_moments: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    const int wslot = (int)(g_stem_ticket.fetch_add(1) % (unsigned)kStemWSlots);
+    stem_regroup_kernel<<<O, 256, 0, st>>>(w, C, wslot);
+    if (int e = check_launch("cv_stem_moments(regroup)")) return e;
+    kern<<<dim3(Hf, O, B), nt, smem2, st>>>(x, y, w, nullptr, nullptr, nullptr, O, Df, Hf, Wf, wslot, moments);
+    return check_launch("cv_stem_moments");
+}
+
 int cv_stem_fwd(const float* x, const float* y, const float* w, const float* scale, const float* shift, int relu,
                 float* out, int B, int C, int O, int Df, int Hf, int Wf, int variant, cudaStream_t st) {
     if (!x || !y || !w || !out) return fail(RAG_E_NULL, "cv_stem_fwd: null pointer");
@@ -514,14 +586,13 @@ int cv_stem_fwd(const float* x, const float* y, const float* w, const float* sca
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             if (e != cudaSuccess) return fail((int)e, "cv_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         }
-        static std::atomic<unsigned> ticket{0};
         int wslot = -1;
         if (O <= kStemWMaxO) {
-            wslot = (int)(ticket.fetch_add(1) % (unsigned)kStemWSlots);
+            wslot = (int)(g_stem_ticket.fetch_add(1) % (unsigned)kStemWSlots);
             stem_regroup_kernel<<<O, 256, 0, st>>>(w, C, wslot);
             if (int e = check_launch("cv_stem_fwd(regroup)")) return e;
         }
-        kern<<<dim3(Hf, O, B), nt, smem2, st>>>(x, y, w, scale, shift, out, O, Df, Hf, Wf, wslot);
+        kern<<<dim3(Hf, O, B), nt, smem2, st>>>(x, y, w, scale, shift, out, O, Df, Hf, Wf, wslot, nullptr);
     } else if (variant == 1) {
         auto kern = cv_stem_fwd_kernel<12>;
         if (smem > 48 * 1024) {

@@ -67,6 +67,29 @@ def cv_stem_forward(x, y, weight, scale=None, shift=None, relu=False, maxdisp=19
     return out
 
 
+def cv_stem_batch_stats(x, y, weight, maxdisp=192):
+    """Per-channel batch (mean, biased variance, count) of conv3d(cost_volume(x, y), weight, padding=1) -- what a
+    training-mode BatchNorm3d after the stem normalises with -- computed from the collapsed row maps: neither the
+    volume nor the convolution output is formed (csrc/cv_stem.cu, MOMENTS)."""
+    _require(x, "x"), _require(y, "y"), _require(weight, "weight")
+    if x.dim() != 4 or x.shape != y.shape:
+        raise RuntimeError("rag_b200: fused stem wants x,y of identical [B,C,Hf,Wf] shape")
+    b, c, hf, wf = x.shape
+    o = weight.shape[0]
+    if tuple(weight.shape) != (o, 2 * c, 3, 3, 3):
+        raise RuntimeError(f"rag_b200: fused stem wants a [O,{2 * c},3,3,3] weight, got {tuple(weight.shape)}")
+    df = int(maxdisp / 3)
+    x, y, weight = x.contiguous(), y.contiguous(), weight.contiguous()
+    rows = torch.empty((b, hf, o, 2), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _cabi.lib().rag_cv_stem_moments(x.data_ptr(), y.data_ptr(), weight.data_ptr(), rows.data_ptr(), b, c, o, df, hf, wf, _stream(x))
+    _cabi.check(rc, "rag_cv_stem_moments")
+    s = rows.sum(dim=(0, 1))                      # fixed-order fp64 reduction of B*Hf row pairs per channel
+    n = b * df * hf * wf
+    mean = s[:, 0] / n
+    return mean, s[:, 1] / n - mean * mean, n
+
+
 def _fusable(conv: nn.Conv3d, vol: VirtualCostVolume) -> bool:
     return (isinstance(conv, nn.Conv3d) and conv.bias is None and conv.kernel_size == (3, 3, 3) and conv.stride == (1, 1, 1)
             and conv.padding == (1, 1, 1) and conv.dilation == (1, 1, 1) and conv.groups == 1

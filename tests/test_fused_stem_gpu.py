@@ -185,3 +185,57 @@ def test_golden_from_the_reference_layer():
         shift = t("bn_bias") - t("bn_mean") * scale
         out = cv_stem_forward(t("x"), t("y"), t("weight"), scale, shift, True, int(z["maxdisp"])).cpu().numpy()
         assert np.abs(out - z["out"]).max() <= 1e-5 * np.abs(z["out"]).max()
+
+
+def _torch_moments(x, y, w, md):
+    """fp64 moments of the fp32 (TF32 off) convolution of the materialised volume, per output channel."""
+    from rag_b200.functional import cost_volume
+
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        z = F.conv3d(cost_volume(x, y, md), w, None, 1, 1).double()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    return z.mean(dim=(0, 2, 3, 4)), z.var(dim=(0, 2, 3, 4), unbiased=False), z.numel() // z.shape[1]
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 12, 24), (1, 7, 40, 48), (3, 4, 36, 192), (2, 6, 416, 96)], ids=str)
+def test_batch_stats_without_the_volume(shape):
+    """First piece of the training path: the batch mean / variance a training-mode BatchNorm3d
+    after the stem would use, from the collapsed row maps, against the moments of the real convolution output."""
+    from rag_b200.fused_stem import cv_stem_batch_stats
+
+    b, hf, wf, md = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(b, 12, hf, wf, generator=g).cuda()
+    y = torch.randn(b, 12, hf, wf, generator=g).cuda()
+    w = (torch.randn(12, 24, 3, 3, 3, generator=g) * 0.1).cuda()
+    mean, var, n = cv_stem_batch_stats(x, y, w, md)
+    rmean, rvar, rn = _torch_moments(x, y, w, md)
+    assert n == rn
+    std = rvar.sqrt()
+    assert ((mean - rmean).abs() <= 1e-5 * std + 1e-7).all(), (mean - rmean).abs().max().item()
+    assert ((var - rvar).abs() <= 1e-5 * rvar).all(), ((var - rvar).abs() / rvar).max().item()
+    m2, v2, _ = cv_stem_batch_stats(x, y, w, md)
+    assert torch.equal(mean, m2) and torch.equal(var, v2)          # fixed-order reduction: bitwise repeatable
+
+
+def test_batch_stats_match_the_reference_running_stat_update():
+    """tests/golden/trainstem_*.npz: the reference's ConvBR_3d in train() updated its running statistics from the batch
+    moments (momentum 0.1, unbiased variance); ours must reproduce that update."""
+    import os
+
+    import numpy as np
+
+    from rag_b200.fused_stem import cv_stem_batch_stats
+    from tests.conftest import GOLDEN
+
+    z = np.load(os.path.join(GOLDEN, "trainstem_b2_c12_h5_w12_md24.npz"))
+    x, y, w = (torch.from_numpy(z[k]).cuda() for k in ("x", "y", "weight"))
+    mean, var, n = cv_stem_batch_stats(x, y, w, int(z["maxdisp"]))
+    mom = float(z["bn_momentum"])
+    mean1 = (1 - mom) * torch.from_numpy(z["bn_mean0"]).double() + mom * mean.cpu()
+    var1 = (1 - mom) * torch.from_numpy(z["bn_var0"]).double() + mom * var.cpu() * n / (n - 1)
+    np.testing.assert_allclose(mean1.numpy(), z["bn_mean1"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(var1.numpy(), z["bn_var1"], rtol=1e-5, atol=1e-6)
