@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RAG_B200_ABI_VERSION 6
+#define RAG_B200_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
