@@ -39,6 +39,8 @@ def test_argument_errors_without_gpu():
     assert b"null" in lib.rag_last_error()
     assert lib.rag_disp_head_fwd(None, None, None, 1, 1, 1, 1, 3, None) == -1
     assert lib.rag_loss_metrics_scratch(480, 960) > 0
+    assert lib.rag_cv_stem_moments(None, None, None, None, 1, 12, 12, 8, 4, 8, None) == -1       # null pointers
+    assert lib.rag_disp_head_bwd(None, None, None, None, None, None, 1, 1, 1, 1, 3, None) == -1
     with pytest.raises(RuntimeError, match="code -1"):
         _cabi.check(-1, "x")
 
@@ -71,6 +73,15 @@ def test_modules_are_stateless_and_cpu_inputs_raise():
         Disp(192)(torch.zeros(1, 1, 64, 2, 2))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         DisparityRegression(192)(torch.zeros(1, 192, 2, 2))
+    from rag_b200.fused_stem import cv_stem_batch_stats, cv_stem_forward
+    from rag_b200.last_conv import conv3d_c1_forward
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cv_stem_forward(torch.zeros(1, 12, 3, 8), torch.zeros(1, 12, 3, 8), torch.zeros(12, 24, 3, 3, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cv_stem_batch_stats(torch.zeros(1, 12, 3, 8), torch.zeros(1, 12, 3, 8), torch.zeros(12, 24, 3, 3, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        conv3d_c1_forward(torch.zeros(1, 12, 3, 3, 8), torch.zeros(1, 12, 3, 3, 3))
 
 
 def test_product_never_imports_oracle():
