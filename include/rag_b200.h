@@ -13,7 +13,13 @@
  *     default stream) on the calling thread's current device; no host synchronisation;
  *   - return value: 0 on success; <0 argument error (RAG_E_*); >0 a cudaError_t.  The text
  *     of the last error on the calling thread is rag_last_error().  No exceptions cross the ABI;
- *   - re-entrant and thread-safe: no mutable global state except the thread-local error text.
+ *   - re-entrant and thread-safe.  The library keeps NO mutable state of its own that a launch depends on:
+ *     work counters and regrouped weights live in caller-owned workspaces (rag_cost_volume_fwd_ws,
+ *     rag_cv_stem_fwd); the thread-local error text and the launch counter are bookkeeping only.  The single
+ *     exception is rag_conv3d_c1_fwd, whose weights must sit in constant memory: its eight per-device weight
+ *     slots are ordered across streams with events (never rewritten under a running reader) and it refuses a
+ *     capturing stream with RAG_E_CAPTURE.  Every other entry point may be stream-captured and the captured
+ *     graphs replayed concurrently with eager launches.
  *
  * Shapes: B batch (stereo pairs), C feature channels (12 in the reference), Hf,Wf = H/3,W/3,
  * Df = int(maxdisp/3) low-res disparity bins, D = maxdisp full-res bins.
@@ -21,13 +27,14 @@
 #ifndef RAG_B200_H
 #define RAG_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define RAG_B200_ABI_VERSION 7
+#define RAG_B200_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
@@ -40,6 +47,7 @@ extern "C" {
 #define RAG_E_SHAPE (-2)    /* a dimension is <= 0 or out of the supported range */
 #define RAG_E_ALIGN (-3)    /* a pointer is not 4-byte (16-byte where stated) aligned */
 #define RAG_E_VARIANT (-4)  /* unknown kernel variant id                        */
+#define RAG_E_CAPTURE (-5)  /* the stream is being captured and this entry point cannot be (rag_conv3d_c1_fwd) */
 
 RAG_API int rag_abi_version(void);
 RAG_API const char* rag_last_error(void);
@@ -52,9 +60,17 @@ RAG_API uint64_t rag_launch_count(void);
  * src/automl/mdenas_basicmodel.py:83-91 (BasicNetwork.forward):
  *   cost[b,   c, d,h,w] = x[b,c,h,w]   if w >= d else 0
  *   cost[b, C+c, d,h,w] = y[b,c,h,w-d] if w >= d else 0          d in [0,Df)
- * x,y [B,C,Hf,Wf]; cost [B,2C,Df,Hf,Wf].  Bit-exact copy. */
+ * x,y [B,C,Hf,Wf]; cost [B,2C,Df,Hf,Wf].  Bit-exact copy.  Stateless: one CTA per work item. */
 RAG_API int rag_cost_volume_fwd(const float* x, const float* y, float* cost,
                         int B, int C, int Df, int Hf, int Wf, void* stream);
+/* Same result through the persistent kernel (one CTA per SM taking its work items IN ORDER from a counter: 3 %
+ * faster at B=8 480x960, and the form that can share the SMs with the disparity head on a second stream).
+ * workspace: caller-owned DEVICE buffer of RAG_CV_FWD_WORKSPACE_BYTES, 8-byte aligned, private to this launch
+ * until it completes; the library zeroes it on `stream` before the kernel (one memset node: graph-capturable).
+ * NULL workspace = rag_cost_volume_fwd. */
+#define RAG_CV_FWD_WORKSPACE_BYTES 16
+RAG_API int rag_cost_volume_fwd_ws(const float* x, const float* y, float* cost,
+                           int B, int C, int Df, int Hf, int Wf, void* workspace, void* stream);
 
 /* Gradient of the above (replaces the 128 chained CopySlices autograd nodes the reference
  * loop creates).  gx[b,c,h,w] = sum_d gcost[b,c,d,h,w] (d<=w), gy[b,c,h,w] = sum_d
@@ -78,7 +94,7 @@ RAG_API int rag_disp_head_fwd(const float* cost_lr, float* disp, float* stats,
  * -- this one is bitwise deterministic: every element of gcost_lr receives exactly TWO contributions,
  * added into the zeroed buffer with red.global.add; two addends commute, so arrival order cannot matter).
  * gdisp, disp [B,3Hl,3Wl]; stats [B,2,3Hl,3Wl] from the forward; gcost_lr [B,1,Dl,Hl,Wl].
- * scratch: may be NULL.  Only the A/B variants 2 and 3 of rag_disp_head_bwd_v use it (a caller-owned
+ * scratch: may be NULL.  Only the A/B variant 2 of rag_disp_head_bwd_v uses it (a caller-owned
  * work buffer of the same size as gcost_lr, contents undefined on return). */
 RAG_API int rag_disp_head_bwd(const float* cost_lr, const float* gdisp, const float* disp,
                       const float* stats, float* gcost_lr, float* scratch,
@@ -96,28 +112,25 @@ RAG_API int rag_disparity_regression_bwd(const float* gout, float* gp, int B, in
 RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int Dl, int Hl, int Wl,
                            int maxdisp, int fma_index, void* stream);
 
-/* ---- variants (tuning / A-B measurement only; the functions above pick the default) --------
- * Two ids matter to callers that overlap the two kernels of the path on two streams (the cost volume of
- * one batch with the disparity head of another, rag_b200.pipeline.OverlappedPath): launch the cost
- * volume FIRST with RAG_CV_FWD_SHARED -- a persistent grid of one 512-thread CTA per SM whose store
- * stream leaves most of the SM to the FP32-bound head -- then the head with its default variant. */
-/* Variant ids (-1 = the default the plain entry points use; ids outside a range return RAG_E_VARIANT):
- *   rag_cost_volume_fwd_v  0-3   first generation (items dealt to threads; any width / alignment)
- *                          4-10  occupancy and static persistent experiments
- *                          11-15 TMA bulk-store kernel (cp.async.bulk shared->global); 16/17 write half the output (probes)
- *                          18-27 lean thread-stationary kernel, static grids / one CTA per item
- *                          28-32 lean kernel, persistent with in-order item hand-out (29 = default, 32 = SM sharing)
- *                          33-36 store flavour (plain, .wt) and taller-tile A/B of 29
- *   rag_cost_volume_bwd_v  0/2 = 128-bit vector kernel (default when Wf % 4 == 0), 1 = scalar, 3 = high-occupancy build
- *   rag_disp_head_fwd_v    0 = any (Dl, maxdisp); 1-3 x3 kernels; 4-9 shared-memory tiled generations;
- *                          10 = default (cube-root form), 11-13 its correction / summation A/B, 14-16 smem-capped
- *   rag_disp_head_bwd_v    0 = any ratio gather; 1 = first x3 kernel; 2/3 = block-row tasks with scratch + combine
- *                          (three / one exp2 per k-block); 4 = default (one exp2, parts added in place)
- *   rag_cv_stem_fwd_v      0 = direct (any shape); 1 = collapsed, scalar; 2 = default (packed phase 1)            */
-#define RAG_CV_FWD_LEAN 29    /* default when Wf % 4 == 0: persistent, one 256-thread CTA per SM           */
-#define RAG_CV_FWD_SHARED 32  /* same kernel, one 512-thread CTA per SM: best when sharing SMs with the head */
+/* ---- variants (A/B measurement and fallbacks; the functions above pick the default) ----------
+ * Variant ids (-1 = the default; ids outside a range return RAG_E_VARIANT):
+ *   rag_cost_volume_fwd_v  0 = any width / alignment (items dealt to threads); 1 = lean thread-stationary kernel, one CTA
+ *                          per item (default without a workspace when Wf % 4 == 0); 2 = lean persistent, 256 threads, one
+ *                          CTA per SM (default with a workspace); 3 = lean persistent, 512 threads (SM sharing);
+ *                          4 = TMA bulk-store kernel (cp.async.bulk shared->global).  2-4 need the workspace.
+ *   rag_cost_volume_bwd_v  0 = 128-bit vector kernel (default when Wf % 4 == 0), 1 = scalar (any width)
+ *   rag_disp_head_fwd_v    0 = any (Dl, maxdisp); 1 = first x3 kernel (any width); 2 = cube-root tiled kernel (default when
+ *                          maxdisp == 3*Dl and Wl % 4 == 0); 3 = as 2 with the lambda correction at every step + TwoSum totals
+ *   rag_disp_head_bwd_v    0 = any-ratio gather; 1 = block-row tasks, parts added in place (default when maxdisp == 3*Dl);
+ *                          2 = same with scratch + combine kernel
+ *   rag_cv_stem_fwd_v      0 = direct (any shape); 1 = collapsed, scalar; 2 = default (packed phase 1)
+ * Callers that overlap the two kernels of the path on two streams (the cost volume of one batch with the disparity head
+ * of another, rag_b200.pipeline.OverlappedPath) launch the cost volume FIRST with RAG_CV_FWD_SHARED -- a persistent grid
+ * of one 512-thread CTA per SM whose store stream leaves most of the SM to the FP32-bound head. */
+#define RAG_CV_FWD_LEAN 2     /* default with a workspace: persistent, one 256-thread CTA per SM                  */
+#define RAG_CV_FWD_SHARED 3   /* same kernel, one 512-thread CTA per SM: best when sharing SMs with the head        */
 RAG_API int rag_cost_volume_fwd_v(const float* x, const float* y, float* cost,
-                          int B, int C, int Df, int Hf, int Wf, int variant, void* stream);
+                          int B, int C, int Df, int Hf, int Wf, void* workspace, int variant, void* stream);
 RAG_API int rag_cost_volume_bwd_v(const float* gcost, float* gx, float* gy,
                           int B, int C, int Df, int Hf, int Wf, int variant, void* stream);
 RAG_API int rag_disp_head_fwd_v(const float* cost_lr, float* disp, float* stats,
@@ -147,25 +160,30 @@ RAG_API int rag_smooth_l1_bwd(const float* est, const float* gt, const double* s
  *   out = relu?( scale[o] * conv3d(cost_volume(x, y), w)[o] + shift[o] )
  * x,y [B,C,Hf,Wf]; w [O,2C,3,3,3] (Conv3d.weight, bias-free); scale/shift [O] = eval-mode BatchNorm folded
  * (gamma/sqrt(var+eps), beta - mean*scale), NULL = identity; out [B,O,Df,Hf,Wf].  fp32 accumulation
- * (cuDNN's default for this layer is TF32).  Forward only: training keeps the materialised path. */
+ * (cuDNN's default for this layer is TF32).
+ * workspace (nullable): caller-owned DEVICE buffer of rag_cv_stem_workspace_bytes(C, O) bytes, 16-byte aligned, private
+ * to this launch until it completes; the weights are regrouped into it once per launch instead of by every CTA. */
+RAG_API size_t rag_cv_stem_workspace_bytes(int C, int O);
 RAG_API int rag_cv_stem_fwd(const float* x, const float* y, const float* w, const float* scale, const float* shift,
-                    int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, void* stream);
+                    int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, void* workspace, void* stream);
 RAG_API int rag_cv_stem_fwd_v(const float* x, const float* y, const float* w, const float* scale, const float* shift,
-                      int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, int variant, void* stream);
+                      int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, void* workspace, int variant, void* stream);
 
 /* Batch statistics of that convolution for a training-mode BatchNorm3d, again without the volume or the conv
  * output (first piece of the training path): moments [B,Hf,O,2] DOUBLE, per (b,h,o) row
  * (sum z, sum z^2) over its Df x Wf outputs z = conv3d(cost_volume(x, y), w)[b,o,:,h,:]; the caller sums the rows
- * (mean = S1/n, biased var = S2/n - mean^2, n = B*Df*Hf*Wf).  Needs C == 12, O <= 32, Df >= 3, Wf % 4 == 0. */
+ * (mean = S1/n, biased var = S2/n - mean^2, n = B*Df*Hf*Wf).  Needs C == 12, Df >= 3, Wf % 4 == 0.
+ * workspace: as for rag_cv_stem_fwd (nullable). */
 RAG_API int rag_cv_stem_moments(const float* x, const float* y, const float* w, double* moments,
-                        int B, int C, int O, int Df, int Hf, int Wf, void* stream);
+                        int B, int C, int O, int Df, int Hf, int Wf, void* workspace, void* stream);
 
 /* The Matching Net's last layer, the producer of the head's input (inference):
  * `self.last_3_3d[i](...)` = ConvBR_3d(C, 1, 3, 1, 1, bn=False, relu=False), src/models/rag_model.py:269,361-365,
  * i.e. a bias-free Conv3d C -> 1, 3x3x3, stride 1, zero padding 1 (src/automl/operations_3d.py:31-47):
  *   out[b,0,d,h,w] = sum_{c,kd,kh,kw} w[0,c,kd,kh,kw] * in[b,c,d+kd-1,h+kh-1,w+kw-1]
  * in [B,C,D,H,W]; w [1,C,3,3,3] (Conv3d.weight); out [B,1,D,H,W].  fp32 accumulation (cuDNN's default for
- * this layer is TF32).  Needs W % 4 == 0 and 16-byte aligned in/out.  Forward only. */
+ * this layer is TF32).  Needs W % 4 == 0, C <= 64, B*ceil(D/16) <= 65535 and 16-byte aligned in/out.  Forward only.
+ * Not capturable (RAG_E_CAPTURE on a capturing stream): see the conventions at the top of this file. */
 RAG_API int rag_conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int D, int H, int W, void* stream);
 
 /* Eval-time input staging: uint8 HWC image -> ImageNet-normalised fp32 CHW, zero-padded on the

@@ -12,7 +12,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _f = C.POINTER(C.c_float)
 _d = C.POINTER(C.c_double)
@@ -32,16 +32,18 @@ SIGNATURES = {
     "rag_disparity_regression_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rag_disparity_regression_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "rag_upsample_trilinear": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "rag_cost_volume_fwd_v": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "rag_cost_volume_fwd_ws": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rag_cost_volume_fwd_v": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "rag_cost_volume_bwd_v": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rag_disp_head_fwd_v": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rag_disp_head_bwd_v": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rag_loss_metrics_scratch": (_i, [_i, _i]),
     "rag_loss_metrics_sums": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, C.c_float, _vp]),
     "rag_smooth_l1_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.c_float, _vp]),
-    "rag_cv_stem_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "rag_cv_stem_fwd_v": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "rag_cv_stem_moments": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "rag_cv_stem_workspace_bytes": (C.c_size_t, [_i, _i]),
+    "rag_cv_stem_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "rag_cv_stem_fwd_v": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "rag_cv_stem_moments": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "rag_conv3d_c1_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rag_normalize_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }

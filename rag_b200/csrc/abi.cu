@@ -5,7 +5,7 @@ namespace rag {
 thread_local char g_last_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 
-int cost_volume_fwd(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+int cost_volume_fwd(const float*, const float*, float*, int, int, int, int, int, void*, int, cudaStream_t);
 int cost_volume_bwd(const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
 int upsample_trilinear(const float*, float*, int, int, int, int, int, int, cudaStream_t);
 int disp_head_fwd(const float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
@@ -16,8 +16,9 @@ int loss_metrics_scratch(int, int);
 int loss_metrics_sums(const float*, const float*, double*, double*, int, int, int, float, cudaStream_t);
 int smooth_l1_bwd(const float*, const float*, const double*, const float*, float*, int, int, int, float, cudaStream_t);
 int normalize_pad(const uint8_t*, float*, int, int, int, int, int, cudaStream_t);
-int cv_stem_fwd(const float*, const float*, const float*, const float*, const float*, int, float*, int, int, int, int, int, int, int, cudaStream_t);
-int cv_stem_moments(const float*, const float*, const float*, double*, int, int, int, int, int, int, cudaStream_t);
+int cv_stem_fwd(const float*, const float*, const float*, const float*, const float*, int, float*, int, int, int, int, int, int, float*, int, cudaStream_t);
+size_t cv_stem_workspace_bytes(int, int);
+int cv_stem_moments(const float*, const float*, const float*, double*, int, int, int, int, int, int, float*, cudaStream_t);
 int conv3d_c1_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 }  // namespace rag
 
@@ -25,7 +26,7 @@ using namespace rag;
 #define ST(s) static_cast<cudaStream_t>(s)
 
 // default variants (picked from the measurements in profiles/)
-static constexpr int kCvFwdDefault = -1;    // -1 = lean persistent kernel when Wf % 4 == 0 and pointers are 16-byte aligned, cv_fwd_kernel otherwise
+static constexpr int kCvFwdDefault = -1;    // -1 = lean kernel when Wf % 4 == 0 and pointers are 16-byte aligned (persistent with a workspace), cv_fwd_kernel otherwise
 static constexpr int kCvBwdDefault = 0;
 static constexpr int kHeadFwdDefault = -1;  // -1 = x3 kernel when maxdisp == 3*Dl, generic otherwise
 static constexpr int kHeadBwdDefault = -1;
@@ -37,7 +38,10 @@ RAG_API const char* rag_last_error(void) { return g_last_error; }
 RAG_API uint64_t rag_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 RAG_API int rag_cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf, void* stream) {
-    return cost_volume_fwd(x, y, cost, B, C, Df, Hf, Wf, kCvFwdDefault, ST(stream));
+    return cost_volume_fwd(x, y, cost, B, C, Df, Hf, Wf, nullptr, kCvFwdDefault, ST(stream));
+}
+RAG_API int rag_cost_volume_fwd_ws(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf, void* workspace, void* stream) {
+    return cost_volume_fwd(x, y, cost, B, C, Df, Hf, Wf, workspace, kCvFwdDefault, ST(stream));
 }
 RAG_API int rag_cost_volume_bwd(const float* gcost, float* gx, float* gy, int B, int C, int Df, int Hf, int Wf, void* stream) {
     return cost_volume_bwd(gcost, gx, gy, B, C, Df, Hf, Wf, kCvBwdDefault, ST(stream));
@@ -59,8 +63,8 @@ RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int 
     return upsample_trilinear(cost_lr, out, B, Dl, Hl, Wl, maxdisp, fma_index, ST(stream));
 }
 
-RAG_API int rag_cost_volume_fwd_v(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf, int variant, void* stream) {
-    return cost_volume_fwd(x, y, cost, B, C, Df, Hf, Wf, variant, ST(stream));
+RAG_API int rag_cost_volume_fwd_v(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf, void* workspace, int variant, void* stream) {
+    return cost_volume_fwd(x, y, cost, B, C, Df, Hf, Wf, workspace, variant, ST(stream));
 }
 RAG_API int rag_cost_volume_bwd_v(const float* gcost, float* gx, float* gy, int B, int C, int Df, int Hf, int Wf, int variant, void* stream) {
     return cost_volume_bwd(gcost, gx, gy, B, C, Df, Hf, Wf, variant, ST(stream));
@@ -81,17 +85,18 @@ RAG_API int rag_smooth_l1_bwd(const float* est, const float* gt, const double* s
                       int B, int H, int W, float maxdisp, void* stream) {
     return smooth_l1_bwd(est, gt, sums, gloss, gest, B, H, W, maxdisp, ST(stream));
 }
+RAG_API size_t rag_cv_stem_workspace_bytes(int C, int O) { return cv_stem_workspace_bytes(C, O); }
 RAG_API int rag_cv_stem_fwd(const float* x, const float* y, const float* w, const float* scale, const float* shift,
-                    int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, void* stream) {
-    return cv_stem_fwd(x, y, w, scale, shift, relu, out, B, C, O, Df, Hf, Wf, -1, ST(stream));
+                    int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, void* workspace, void* stream) {
+    return cv_stem_fwd(x, y, w, scale, shift, relu, out, B, C, O, Df, Hf, Wf, static_cast<float*>(workspace), -1, ST(stream));
 }
 RAG_API int rag_cv_stem_moments(const float* x, const float* y, const float* w, double* moments, int B, int C, int O, int Df, int Hf, int Wf,
-                                void* stream) {
-    return cv_stem_moments(x, y, w, moments, B, C, O, Df, Hf, Wf, ST(stream));
+                        void* workspace, void* stream) {
+    return cv_stem_moments(x, y, w, moments, B, C, O, Df, Hf, Wf, static_cast<float*>(workspace), ST(stream));
 }
 RAG_API int rag_cv_stem_fwd_v(const float* x, const float* y, const float* w, const float* scale, const float* shift,
-                      int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, int variant, void* stream) {
-    return cv_stem_fwd(x, y, w, scale, shift, relu, out, B, C, O, Df, Hf, Wf, variant, ST(stream));
+                      int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, void* workspace, int variant, void* stream) {
+    return cv_stem_fwd(x, y, w, scale, shift, relu, out, B, C, O, Df, Hf, Wf, static_cast<float*>(workspace), variant, ST(stream));
 }
 RAG_API int rag_conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int D, int H, int W, void* stream) {
     return conv3d_c1_fwd(in, w, out, B, C, D, H, W, ST(stream));

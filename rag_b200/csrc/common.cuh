@@ -32,7 +32,18 @@ inline int check_launch(const char* what) {
 
 inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the current device (148 on a B200; smaller under MIG), queried once per device
+inline int num_sms() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
 
 // ---- device side ---------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -131,25 +131,6 @@ cv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* _
     cv_fwd_unit<V, NT>(x, y, cost, C, Df, Hf, Wf, R, dchunk, tile, blockIdx.x - tile * n_dchunks, blockIdx.y, blockIdx.z, smem);
 }
 
-// Persistent form: a fixed number of CTAs (a multiple of the SM count) walks the work units.  Used when the
-// kernel has to SHARE every SM with the disparity-head kernel on a second stream (rag_b200.pipeline): a
-// resident footprint of exactly k CTAs per SM leaves the rest of the register file / shared memory free.
-template <int V, int NT>
-__global__ void __launch_bounds__(NT)
-cv_fwd_persistent_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ cost,
-                         int B, int C, int Df, int Hf, int Wf, int R, int dchunk, int n_dchunks, int n_tiles) {
-    extern __shared__ __align__(16) float smem[];
-    const int per_bc = n_tiles * n_dchunks;
-    const long long total = (long long)B * C * per_bc;
-    for (long long u = blockIdx.x; u < total; u += gridDim.x) {
-        const int bc = (int)(u / per_bc);
-        const int rem = (int)(u - (long long)bc * per_bc);
-        const int tile = rem / n_dchunks;
-        cv_fwd_unit<V, NT>(x, y, cost, C, Df, Hf, Wf, R, dchunk, tile, rem - tile * n_dchunks, bc % C, bc / C, smem);
-        __syncthreads();   // the staging buffers are reused by the next unit
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
@@ -246,28 +227,27 @@ static int check_cv_args(const void* a, const void* b_, const void* c, int B, in
     if (B <= 0 || C <= 0 || Df <= 0 || Hf <= 0 || Wf <= 0)
         return fail(RAG_E_SHAPE, "cost_volume: non-positive dimension B=%d C=%d Df=%d Hf=%d Wf=%d", B, C, Df, Hf, Wf);
     if (B > 65535 || C > 65535) return fail(RAG_E_SHAPE, "cost_volume: B and C must be <= 65535");
+    // the kernels index (b*2C + c) and the item count B*C*tiles*chunks in 32-bit int
+    if ((long long)2 * B * C >= (1LL << 31) || (long long)B * C * Hf * ((Df + 15) / 16) >= (1LL << 31))
+        return fail(RAG_E_SHAPE, "cost_volume: 2*B*C and B*C*Hf*ceil(Df/16) must be < 2^31");
     if ((size_t)Df * Hf * Wf >= ((size_t)1 << 31) || Wf > 65535)
         return fail(RAG_E_SHAPE, "cost_volume: Df*Hf*Wf must be < 2^31 and Wf <= 65535");
     if (!aligned(a, 4) || !aligned(b_, 4) || !aligned(c, 4)) return fail(RAG_E_ALIGN, "cost_volume: pointers must be 4-byte aligned");
     return RAG_OK;
 }
 
+// any width / alignment: items (d, vector) dealt to threads, 16-disparity chunks, 36 KB tiles
 template <int V, int NT>
-static int launch_cv_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
-                         int variant, size_t smem_floor, cudaStream_t st) {
-    // variant: 0 -> 16-disparity chunks, 36 KB tiles; 1 -> 32-disparity chunks; 2 -> whole sweep per CTA;
-    //          3 -> 16-disparity chunks, 72 KB tiles
-    int dchunk = variant == 1 ? 32 : variant == 2 ? Df : 16;
-    dchunk = ((dchunk + V - 1) / V) * V;
+static int launch_cv_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf, cudaStream_t st) {
+    int dchunk = ((16 + V - 1) / V) * V;
     const int n_dchunks = (Df + dchunk - 1) / dchunk;
-    const size_t budget = variant == 3 ? 72 * 1024 : 36 * 1024;
+    const size_t budget = 36 * 1024;
     int R = (int)(budget / ((size_t)(V + 1) * 4 * Wf + (size_t)2 * (Wf / V)));
     R = R < 1 ? 1 : (R > Hf ? Hf : R);
     // prefer an R that divides Hf (no ragged last tile) when one is close
     for (int r = R; r >= (R * 3) / 4 && r >= 1; --r)
         if (Hf % r == 0) { R = r; break; }
-    size_t smem = (size_t)(V + 1) * R * Wf * 4 + (size_t)R * (Wf / V) * 2;
-    if (smem < smem_floor) smem = smem_floor;   // occupancy experiments only
+    const size_t smem = (size_t)(V + 1) * R * Wf * 4 + (size_t)R * (Wf / V) * 2;
     if (smem > 200 * 1024) return fail(RAG_E_SHAPE, "cost_volume_fwd: Wf=%d too wide for one shared-memory row tile", Wf);
     auto kern = cv_fwd_kernel<V, NT>;
     if (smem > 48 * 1024) {
@@ -275,6 +255,7 @@ static int launch_cv_fwd(const float* x, const float* y, float* cost, int B, int
         if (e != cudaSuccess) return fail((int)e, "cost_volume_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
     const int n_tiles = (Hf + R - 1) / R;
+    if ((long long)n_tiles * n_dchunks > 2147483647LL) return fail(RAG_E_SHAPE, "cost_volume_fwd: grid too large");
     dim3 grid(n_tiles * n_dchunks, C, B);
     kern<<<grid, NT, smem, st>>>(x, y, cost, C, Df, Hf, Wf, R, dchunk, n_dchunks);
     return check_launch("cost_volume_fwd");
@@ -284,29 +265,43 @@ static bool cv_lean_ok(const float* x, const float* y, const float* cost, int Wf
     return Wf % 4 == 0 && Wf <= 2048 && aligned(x, 16) && aligned(y, 16) && aligned(cost, 16);
 }
 
-template <int NT = 256, int VPT = 2, int ST = 0>
+// zero the caller's work counter on the launch stream (stream-ordered before the kernel that consumes it)
+static int arm_counter(void* workspace, cudaStream_t st, const char* who) {
+    if (!aligned(workspace, 8)) return fail(RAG_E_ALIGN, "%s: workspace must be 8-byte aligned", who);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, RAG_CV_FWD_WORKSPACE_BYTES, st);
+    if (e != cudaSuccess) return fail((int)e, "%s: cudaMemsetAsync(workspace): %s", who, cudaGetErrorString(e));
+    return RAG_OK;
+}
+
+// lean thread-stationary kernel.  ctr == nullptr: one CTA per item (hardware dispatch order keeps the resident
+// CTAs on neighbouring rows; stateless).  ctr != nullptr: persistent grid of `per_sm` CTAs per SM that takes its
+// items IN ORDER from the caller's counter (3 % faster at B=8 480x960, and resident at once, which is what lets the
+// disparity head share the SMs on a second stream).
+template <int NT, int VPT>
 static int launch_cv_fwd_lean(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
-                              int per_sm, int dchunk, cudaStream_t st, size_t smem_floor = 0, bool dyn = false) {
+                              int per_sm, unsigned int* ctr, cudaStream_t st) {
     const int Wv = Wf / 4, Df4 = (Df + 3) & ~3;
     const size_t row_bytes = (size_t)16 * (Df4 + Wf + 4);          // four images of one row
     int R = std::min(Hf, (NT * VPT) / Wv);
-    while (R > 1 && R * row_bytes > (NT * VPT > 512 ? 100 : 64) * 1024) --R;
-    const size_t smem = std::max(R * row_bytes, smem_floor);
+    if (R < 1) return fail(RAG_E_SHAPE, "cost_volume_fwd(lean): Wf=%d too wide for a %d-vector tile", Wf, NT * VPT);
+    while (R > 1 && R * row_bytes > 64 * 1024) --R;
+    const size_t smem = R * row_bytes;
     if (smem > 200 * 1024) return fail(RAG_E_SHAPE, "cost_volume_fwd(lean): Df=%d Wf=%d do not fit shared memory", Df, Wf);
-    static std::atomic<unsigned> ticket{0};
-    auto kern = dyn ? cv_fwd_lean_kernel<NT, VPT, true, ST> : cv_fwd_lean_kernel<NT, VPT, false, ST>;
+    const bool dyn = ctr != nullptr;
+    auto kern = dyn ? cv_fwd_lean_kernel<NT, VPT, true> : cv_fwd_lean_kernel<NT, VPT, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     // the L1/shared split of an SM cannot change while CTAs are resident: ask for the largest shared-memory
     // carve-out so that this kernel and the disparity head (which does the same) can share an SM
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return fail((int)e, "cost_volume_fwd(lean): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const int n_tiles = (Hf + R - 1) / R;
-    if (dchunk <= 0 || dchunk > Df) dchunk = (Df + 3) & ~3;
+    const int dchunk = std::min(16, (Df + 3) & ~3);
     const int n_dchunks = (Df + dchunk - 1) / dchunk;
     const long long n_items = (long long)B * C * n_tiles * n_dchunks;
-    const int grid = (int)(per_sm > 0 ? std::min<long long>(n_items, (long long)kNumSMs * per_sm) : n_items);
-    const int slot = dyn ? (int)(ticket.fetch_add(1) % 64u) : 0;
-    kern<<<grid, NT, smem, st>>>(x, y, cost, B * C, C, Df, Hf, Wf, R, n_tiles, dchunk, n_dchunks, slot);
+    if (n_items >= (1LL << 31)) return fail(RAG_E_SHAPE, "cost_volume_fwd(lean): too many work items");
+    const int grid = (int)(dyn ? std::min<long long>(n_items, (long long)num_sms() * per_sm) : n_items);
+    if (dyn) if (int rc = arm_counter(ctr, st, "cost_volume_fwd(lean)")) return rc;
+    kern<<<grid, NT, smem, st>>>(x, y, cost, B * C, C, Df, Hf, Wf, R, n_tiles, dchunk, n_dchunks, ctr);
     return check_launch("cost_volume_fwd(lean)");
 }
 
@@ -315,100 +310,66 @@ static bool cv_tma_ok(const float* x, const float* y, const float* cost, int Df,
 }
 
 static int launch_cv_fwd_tma(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
-                             int R, int per_sm, int mode, cudaStream_t st) {
+                             unsigned int* ctr, cudaStream_t st) {
     constexpr int NT = 128;
-    R = R > Hf ? Hf : R;
+    int R = std::min(4, Hf);
+    const int per_sm = 2;
     const size_t row_floats = (size_t)Wf + 4 * (size_t)(Df + Wf + 4);
     while (R > 1 && 4 * (Df + 2 * R * row_floats) > 200 * 1024) --R;
     const size_t smem = 4 * (Df + 2 * R * row_floats);
     if (smem > 200 * 1024) return fail(RAG_E_SHAPE, "cost_volume_fwd(tma): Wf=%d too wide for shared memory", Wf);
-    auto kern = mode == 1 ? cv_fwd_tma_kernel<NT, 1> : mode == 2 ? cv_fwd_tma_kernel<NT, 2> : cv_fwd_tma_kernel<NT, 0>;
+    auto kern = cv_fwd_tma_kernel<NT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "cost_volume_fwd(tma): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    static std::atomic<unsigned> ticket{0};
     const int n_tiles = (Hf + R - 1) / R;
     const int dchunk = std::min(16, Df), n_dchunks = (Df + dchunk - 1) / dchunk;
     const long long n_items = (long long)B * C * n_tiles * n_dchunks;
-    const int grid = (int)std::min<long long>(n_items, (long long)kNumSMs * per_sm);
-    kern<<<grid, NT, smem, st>>>(x, y, cost, B, C, Df, Hf, Wf, R, n_tiles, dchunk, n_dchunks, (int)(ticket.fetch_add(1) % 64u));
+    if (n_items >= (1LL << 31)) return fail(RAG_E_SHAPE, "cost_volume_fwd(tma): too many work items");
+    const int grid = (int)std::min<long long>(n_items, (long long)num_sms() * per_sm);
+    if (int rc = arm_counter(ctr, st, "cost_volume_fwd(tma)")) return rc;
+    kern<<<grid, NT, smem, st>>>(x, y, cost, B, C, Df, Hf, Wf, R, n_tiles, dchunk, n_dchunks, ctr);
     return check_launch("cost_volume_fwd(tma)");
 }
 
+// variant: -1 = default (lean persistent when a workspace is given, lean one-CTA-per-item without, generic when the
+// lean preconditions fail); 0 = generic; 1 = lean one CTA per item; 2 = lean persistent 256 threads (needs workspace);
+// 3 = lean persistent 512 threads, RAG_CV_FWD_SHARED (needs workspace); 4 = TMA bulk-store kernel (needs workspace)
 int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
-                    int variant, cudaStream_t st) {
+                    void* workspace, int variant, cudaStream_t st) {
     if (int e = check_cv_args(x, y, cost, B, C, Df, Hf, Wf)) return e;
-    if (variant < -1 || variant > 36) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
-    if (variant == -1) variant = cv_lean_ok(x, y, cost, Wf) ? RAG_CV_FWD_LEAN : 0;
-    if (variant >= 18) {   // lean thread-stationary kernel, persistent: 18 = 2 CTAs/SM, 19 = 1, 20 = 3, 21 = 4
-        if (!cv_lean_ok(x, y, cost, Wf))
-            return fail(RAG_E_VARIANT, "cost_volume_fwd: lean variants need Wf %% 4 == 0, Wf <= 2048 and 16-byte aligned pointers");
-        // 22-25: 16-disparity chunks per item; 22 = 2 CTAs/SM, 23 = 1, 24 = 4, 25 = one CTA per item (not persistent)
-        // 31 / 32: as 29 with 128 threads x 4 vectors / 512 threads x 1 vector per thread
-        // 33 / 34: as 29 with plain / write-through stores instead of st.global.cs (A/B of the store flavour)
-        // 35 / 36: as 29 with twice the rows per tile (512 x 2 / 256 x 4 vectors per thread)
-        if (variant == 35) return launch_cv_fwd_lean<512, 2>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
-        if (variant == 36) return launch_cv_fwd_lean<256, 4>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
-        if (variant == 33) return launch_cv_fwd_lean<256, 2, 1>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
-        if (variant == 34) return launch_cv_fwd_lean<256, 2, 2>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
-        if (variant == 31) return launch_cv_fwd_lean<128, 4>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
-        if (variant == 32) return launch_cv_fwd_lean<512, 1>(x, y, cost, B, C, Df, Hf, Wf, 1, 16, st, 0, true);
-        // 28-30: persistent with in-order (atomic counter) item hand-out, 16-disparity chunks: 2 / 1 / 4 CTAs per SM
-        if (variant >= 28) return launch_cv_fwd_lean(x, y, cost, B, C, Df, Hf, Wf, variant == 28 ? 2 : variant == 29 ? 1 : 4, 16, st, 0, true);
-        // 26 / 27: as 25 with the shared-memory request padded so that only 1 / 2 CTAs fit an SM
-        if (variant >= 26) return launch_cv_fwd_lean(x, y, cost, B, C, Df, Hf, Wf, 0, 16, st, variant == 26 ? 120 * 1024 : 76 * 1024);
-        if (variant >= 22) return launch_cv_fwd_lean(x, y, cost, B, C, Df, Hf, Wf, variant == 22 ? 2 : variant == 23 ? 1 : variant == 24 ? 4 : 0, 16, st);
-        return launch_cv_fwd_lean(x, y, cost, B, C, Df, Hf, Wf, variant == 18 ? 2 : variant == 19 ? 1 : variant == 20 ? 3 : 4, 0, st);
-    }
-    if (variant >= 11) {   // TMA bulk-store kernel: 11 = R4 x 1 CTA/SM, 12 = R4 x 2, 13 = R2 x 2, 14 = R8 x 1
+    if (variant < -1 || variant > 4) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
+    unsigned int* ctr = static_cast<unsigned int*>(workspace);
+    const bool lean = cv_lean_ok(x, y, cost, Wf) && (Wf / 4) <= 512;
+    if (variant == -1) variant = lean ? (ctr ? RAG_CV_FWD_LEAN : 1) : 0;
+    if (variant >= 2 && !ctr) return fail(RAG_E_NULL, "cost_volume_fwd: variant %d needs a workspace of RAG_CV_FWD_WORKSPACE_BYTES", variant);
+    if (variant >= 1 && variant <= 3 && !lean)
+        return fail(RAG_E_VARIANT, "cost_volume_fwd: lean variants need Wf %% 4 == 0, Wf <= 2048 and 16-byte aligned pointers");
+    if (variant == 1) return launch_cv_fwd_lean<256, 2>(x, y, cost, B, C, Df, Hf, Wf, 0, nullptr, st);
+    if (variant == 2) return launch_cv_fwd_lean<256, 2>(x, y, cost, B, C, Df, Hf, Wf, 1, ctr, st);
+    if (variant == 3) return launch_cv_fwd_lean<512, 1>(x, y, cost, B, C, Df, Hf, Wf, 1, ctr, st);
+    if (variant == 4) {
         if (!cv_tma_ok(x, y, cost, Df, Wf))
-            return fail(RAG_E_VARIANT, "cost_volume_fwd: TMA variants need Wf %% 4 == 0, Df %% 4 == 0, Df <= Wf and 16-byte aligned pointers");
-        // 15 = R2 x 4 CTAs/SM; 16 / 17 = EXPERIMENTS writing only the right / left half (output incomplete)
-        const int R = (variant == 13 || variant == 15) ? 2 : variant == 14 ? 8 : 4;
-        const int per_sm = variant == 15 ? 4 : (variant == 11 || variant == 14) ? 1 : 2;
-        return launch_cv_fwd_tma(x, y, cost, B, C, Df, Hf, Wf, R, per_sm, variant == 16 ? 1 : variant == 17 ? 2 : 0, st);
-    }
-    if (variant >= 8) {   // persistent: exactly 3 (variant 8), 4 (9) or 2 (10) 128-thread CTAs per SM, ~20 KB tiles
-        if (!(Wf % 4 == 0 && aligned(x, 16) && aligned(y, 16) && aligned(cost, 16)))
-            return fail(RAG_E_VARIANT, "cost_volume_fwd: persistent variants need Wf %% 4 == 0 and 16-byte aligned pointers");
-        constexpr int V = 4, NT = 128;
-        const int per_sm = variant == 8 ? 3 : variant == 9 ? 4 : 2;
-        const int dchunk = 16, n_dchunks = (Df + dchunk - 1) / dchunk;
-        int R = (int)((20 * 1024) / ((size_t)(V + 1) * 4 * Wf + (size_t)2 * (Wf / V)));
-        R = R < 1 ? 1 : (R > Hf ? Hf : R);
-        for (int r = R; r >= (R * 3) / 4 && r >= 1; --r)
-            if (Hf % r == 0) { R = r; break; }
-        const size_t smem = (size_t)(V + 1) * R * Wf * 4 + (size_t)R * (Wf / V) * 2;
-        if (smem > 48 * 1024) return fail(RAG_E_SHAPE, "cost_volume_fwd: Wf=%d too wide for the persistent variant", Wf);
-        const int n_tiles = (Hf + R - 1) / R;
-        cv_fwd_persistent_kernel<V, NT><<<kNumSMs * per_sm, NT, smem, st>>>(x, y, cost, B, C, Df, Hf, Wf, R, dchunk, n_dchunks, n_tiles);
-        return check_launch("cost_volume_fwd(persistent)");
+            return fail(RAG_E_VARIANT, "cost_volume_fwd: the TMA variant needs Wf %% 4 == 0, Df %% 4 == 0, Df <= Wf and 16-byte aligned pointers");
+        return launch_cv_fwd_tma(x, y, cost, B, C, Df, Hf, Wf, ctr, st);
     }
     const bool a16 = aligned(x, 16) && aligned(y, 16) && aligned(cost, 16);
     const bool a8 = aligned(x, 8) && aligned(y, 8) && aligned(cost, 8);
-    if (variant >= 4) {   // occupancy experiments: 128-thread CTAs, 4: unconstrained, 5: <=4, 6: <=2, 7: 1 CTA per SM
-        if (!(Wf % 4 == 0 && a16)) return fail(RAG_E_VARIANT, "cost_volume_fwd: variants 4-7 need Wf %% 4 == 0");
-        const size_t floor_b = variant == 5 ? 50 * 1024 : variant == 6 ? 100 * 1024 : variant == 7 ? 190 * 1024 : 0;
-        return launch_cv_fwd<4, 128>(x, y, cost, B, C, Df, Hf, Wf, 0, floor_b, st);
-    }
-    if (Wf % 4 == 0 && a16) return launch_cv_fwd<4, 256>(x, y, cost, B, C, Df, Hf, Wf, variant, 0, st);
-    if (Wf % 2 == 0 && a8) return launch_cv_fwd<2, 256>(x, y, cost, B, C, Df, Hf, Wf, variant, 0, st);
-    return launch_cv_fwd<1, 256>(x, y, cost, B, C, Df, Hf, Wf, variant, 0, st);
+    if (Wf % 4 == 0 && a16) return launch_cv_fwd<4, 256>(x, y, cost, B, C, Df, Hf, Wf, st);
+    if (Wf % 2 == 0 && a8) return launch_cv_fwd<2, 256>(x, y, cost, B, C, Df, Hf, Wf, st);
+    return launch_cv_fwd<1, 256>(x, y, cost, B, C, Df, Hf, Wf, st);
 }
 
+// variant: 0 = default (128-bit vector kernel when Wf % 4 == 0 and aligned, else scalar); 1 = scalar
 int cost_volume_bwd(const float* g, float* gx, float* gy, int B, int C, int Df, int Hf, int Wf,
                     int variant, cudaStream_t st) {
     if (int e = check_cv_args(g, gx, gy, B, C, Df, Hf, Wf)) return e;
-    if (variant < 0 || variant > 3) return fail(RAG_E_VARIANT, "cost_volume_bwd: unknown variant %d", variant);
+    if (variant < 0 || variant > 1) return fail(RAG_E_VARIANT, "cost_volume_bwd: unknown variant %d", variant);
     const bool a16 = aligned(g, 16) && aligned(gx, 16) && aligned(gy, 16);
     if (variant != 1 && Wf % 4 == 0 && a16) {
         constexpr int NT = 128;
         const int PV = Hf * (Wf / 4);
         dim3 grid((PV + NT - 1) / NT, C, B);
-        // variant 3 = 12-CTA/SM build (2 disparities in flight, 40 registers): measured SLOWER than the 4-deep
-        // build at every size (profiles/r1_kbench_cv_bwd.jsonl), kept for A/B only
-        const bool hi_occ = variant == 3;
-        if (hi_occ) cv_bwd_v4_kernel<NT, 2, 12><<<grid, NT, 0, st>>>(g, gx, gy, C, Df, Hf, Wf);
-        else cv_bwd_v4_kernel<NT, 4, 1><<<grid, NT, 0, st>>>(g, gx, gy, C, Df, Hf, Wf);
+        cv_bwd_v4_kernel<NT, 4, 1><<<grid, NT, 0, st>>>(g, gx, gy, C, Df, Hf, Wf);
     } else {
         constexpr int NT = 256;
         const int PE = Hf * Wf;

@@ -21,9 +21,9 @@ namespace rag {
 
 // grid: persistent, blockIdx.x strides over items (b*C + c, row tile).  NT threads, VPT vectors per thread.
 // smem: Y[R][4][YS], YS = Df4 + Wf + 4 with Df4 = Df rounded up to a multiple of 4.
-// Work counters of the persistent form (DYN): {next item, finished CTAs} per launch slot; the last CTA of a
-// launch resets its slot, the host hands out slots round-robin.
-__device__ unsigned int g_cv_ctr[64][2];
+// Work counter of the persistent form (DYN): ONE unsigned int "next item" in a CALLER-OWNED workspace, zeroed by the
+// launcher with cudaMemsetAsync on the launch stream right before the kernel -- the library keeps no state of its
+// own, so concurrent launches, graph capture and replays cannot interfere (each launch has its own counter).
 
 // DYN: the CTAs of a persistent grid take items from an atomic counter IN ORDER, so the resident CTAs always
 // work on neighbouring rows / disparity chunks (a static stride lets them drift apart and costs 12 % of
@@ -40,7 +40,7 @@ __device__ __forceinline__ void cv_store(float4* p, float4 v) {
 template <int NT, int VPT, bool DYN, int ST = 0>
 __global__ void __launch_bounds__(NT)
 cv_fwd_lean_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ cost,
-                   int BC, int C, int Df, int Hf, int Wf, int R, int n_tiles, int dchunk, int n_dchunks, int slot) {
+                   int BC, int C, int Df, int Hf, int Wf, int R, int n_tiles, int dchunk, int n_dchunks, unsigned int* __restrict__ ctr) {
     extern __shared__ __align__(16) float cvl_smem[];
     __shared__ int s_item[2];
     const int Df4 = (Df + 3) & ~3;
@@ -79,14 +79,14 @@ cv_fwd_lean_kernel(const float* __restrict__ x, const float* __restrict__ y, flo
     };
     int item = blockIdx.x;
     if (DYN) {
-        if (tid == 0) s_item[0] = (int)atomicAdd(&g_cv_ctr[slot][0], 1u);
+        if (tid == 0) s_item[0] = (int)atomicAdd(ctr, 1u);
         __syncthreads();
         item = s_item[0];
     }
     if (item < n_items) prefetch(item);
 
     for (int k = 0; item < n_items; ++k) {
-        if (DYN && tid == 0) s_item[(k + 1) & 1] = (int)atomicAdd(&g_cv_ctr[slot][0], 1u);   // published by the barrier below
+        if (DYN && tid == 0) s_item[(k + 1) & 1] = (int)atomicAdd(ctr, 1u);   // published by the barrier below
         const int it = item / n_dchunks, dc = item - it * n_dchunks;
         const int tile = it % n_tiles, bc = it / n_tiles;
         const int d_beg = dc * dchunk, d_end = min(d_beg + dchunk, Df);   // dchunk % 4 == 0
@@ -155,14 +155,6 @@ cv_fwd_lean_kernel(const float* __restrict__ x, const float* __restrict__ y, flo
         }
         for (int s = 0; d4 + s < d_end; ++s) emit(d4, s);
         item = next;
-    }
-    if (DYN && tid == 0) {
-        // every CTA gets here after its last fetch, so the last arrival can rearm the slot
-        if (atomicAdd(&g_cv_ctr[slot][1], 1u) == gridDim.x - 1) {
-            g_cv_ctr[slot][0] = 0u;
-            g_cv_ctr[slot][1] = 0u;
-            __threadfence();
-        }
     }
 }
 

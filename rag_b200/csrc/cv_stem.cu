@@ -225,14 +225,14 @@ cv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, con
 //
 // The conv weights are regrouped ONCE per launch by a tiny kernel into the layout phase 1 reads
 // ([o][side][c][kh][12]: the nine (kd,kw) weights + padding) instead of by every one
-// of the B*O*Hf CTAs (div/mod address arithmetic and scattered loads: 9 % of the samples).  Four slots, handed
-// out round-robin, so launches with different weights can overlap.
-constexpr int kStemWSlots = 4, kStemWMaxO = 32, kStemWPerO = 2 * 12 * 3 * 12;
-__device__ float g_stem_w[kStemWSlots][kStemWMaxO * kStemWPerO];
-static std::atomic<unsigned> g_stem_ticket{0};   // host side: next weight slot (shared by every launcher below)
+// of the B*O*Hf CTAs (div/mod address arithmetic and scattered loads: 9 % of the samples).  The regrouped copy
+// lives in a CALLER-OWNED workspace (rag_cv_stem_workspace_bytes): the library keeps no state, so launches with
+// different weights on any streams, graph capture and replays cannot interfere.  Without a workspace every CTA
+// regroups its own channel's weights from `w` (the slower path).
+constexpr int kStemWPerO = 2 * 12 * 3 * 12;
 
 __global__ void __launch_bounds__(256)
-stem_regroup_kernel(const float* __restrict__ w, int C, int slot) {
+stem_regroup_kernel(const float* __restrict__ w, int C, float* __restrict__ wreg) {
     const int o = blockIdx.x;
     for (int i = threadIdx.x; i < 2 * C * 3 * 12; i += 256) {
         const int t = i % 12, kh = (i / 12) % 3, c = (i / 36) % C, side = i / (36 * C);
@@ -241,7 +241,7 @@ stem_regroup_kernel(const float* __restrict__ w, int C, int slot) {
             const int kd = t / 3, kw = t % 3;
             v = __ldg(w + ((((size_t)o * 2 * C + side * C + c) * 3 + kd) * 3 + kh) * 3 + kw);
         }
-        g_stem_w[slot][o * kStemWPerO + i] = v;
+        wreg[(size_t)o * kStemWPerO + i] = v;
     }
 }
 
@@ -252,7 +252,7 @@ template <int C, bool RELU, bool MOMENTS = false>
 __global__ void __launch_bounds__(512, 2)
 cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ w,
                     const float* __restrict__ scale, const float* __restrict__ shift,
-                    float* __restrict__ out, int O, int Df, int Hf, int Wf, int wslot, double* __restrict__ moments) {
+                    float* __restrict__ out, int O, int Df, int Hf, int Wf, const float* __restrict__ wreg, double* __restrict__ moments) {
     extern __shared__ __align__(16) float stem_smem[];
     const int Wp = Wf + 2 * kStemPad;
     float* wsm = stem_smem;                       // [side][c][kh][12]: 9 (kd,kw) weights + pad
@@ -288,8 +288,8 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
         }
     }
 
-    if (wslot >= 0) {                              // weights already regrouped by stem_regroup_kernel: plain vector copy
-        const float4* src = reinterpret_cast<const float4*>(g_stem_w[wslot] + o * kStemWPerO);
+    if (wreg != nullptr) {                         // weights already regrouped by stem_regroup_kernel: plain vector copy
+        const float4* src = reinterpret_cast<const float4*>(wreg + (size_t)o * kStemWPerO);
         for (int i = tid; i < 2 * C * 3 * 12 / 4; i += NT) reinterpret_cast<float4*>(wsm)[i] = src[i];
     } else {
         for (int i = tid; i < 2 * C * 3 * 12; i += NT) {
@@ -533,13 +533,13 @@ cv_stem_direct_kernel(const float* __restrict__ x, const float* __restrict__ y, 
 
 // Batch moments of the stem convolution: moments [B,Hf,O,2] fp64 = per (b,h,o) row (sum z, sum z^2) over Df x Wf.
 int cv_stem_moments(const float* x, const float* y, const float* w, double* moments, int B, int C, int O, int Df, int Hf, int Wf,
-                    cudaStream_t st) {
+                    float* workspace, cudaStream_t st) {
     if (!x || !y || !w || !moments) return fail(RAG_E_NULL, "cv_stem_moments: null pointer");
     if (B <= 0 || O <= 0 || Df <= 0 || Hf <= 0 || Wf <= 0 || B > 65535 || O > 65535)
         return fail(RAG_E_SHAPE, "cv_stem_moments: bad shape B=%d C=%d O=%d Df=%d Hf=%d Wf=%d", B, C, O, Df, Hf, Wf);
     const int Wv = Wf / 4;
-    if (!(C == 12 && Df >= 3 && Wf >= 8 && Wf % 4 == 0 && Wv <= 512 && O <= kStemWMaxO && aligned(x, 8) && aligned(y, 8)))
-        return fail(RAG_E_SHAPE, "cv_stem_moments: needs C == 12, O <= %d, Df >= 3, Wf >= 8, Wf %% 4 == 0, Wf <= 2048 and 8-byte aligned features", kStemWMaxO);
+    if (!(C == 12 && Df >= 3 && Wf >= 8 && Wf % 4 == 0 && Wv <= 512 && aligned(x, 8) && aligned(y, 8) && (!workspace || aligned(workspace, 16))))
+        return fail(RAG_E_SHAPE, "cv_stem_moments: needs C == 12, Df >= 3, Wf >= 8, Wf %% 4 == 0, Wf <= 2048, 8-byte aligned features and a 16-byte aligned workspace");
     int k = 384 / Wv;
     if (k < 1) k = 1;
     int nt = k * Wv;
@@ -552,16 +552,18 @@ int cv_stem_moments(const float* x, const float* y, const float* w, double* mome
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e != cudaSuccess) return fail((int)e, "cv_stem_moments: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    const int wslot = (int)(g_stem_ticket.fetch_add(1) % (unsigned)kStemWSlots);
-    stem_regroup_kernel<<<O, 256, 0, st>>>(w, C, wslot);
-    if (int e = check_launch("cv_stem_moments(regroup)")) return e;
-    kern<<<dim3(Hf, O, B), nt, smem2, st>>>(x, y, w, nullptr, nullptr, nullptr, O, Df, Hf, Wf, wslot, moments);
+    if (workspace) {
+        stem_regroup_kernel<<<O, 256, 0, st>>>(w, C, workspace);
+        if (int e = check_launch("cv_stem_moments(regroup)")) return e;
+    }
+    kern<<<dim3(Hf, O, B), nt, smem2, st>>>(x, y, w, nullptr, nullptr, nullptr, O, Df, Hf, Wf, workspace, moments);
     return check_launch("cv_stem_moments");
 }
 
 int cv_stem_fwd(const float* x, const float* y, const float* w, const float* scale, const float* shift, int relu,
-                float* out, int B, int C, int O, int Df, int Hf, int Wf, int variant, cudaStream_t st) {
+                float* out, int B, int C, int O, int Df, int Hf, int Wf, float* workspace, int variant, cudaStream_t st) {
     if (!x || !y || !w || !out) return fail(RAG_E_NULL, "cv_stem_fwd: null pointer");
+    if (workspace && !aligned(workspace, 16)) return fail(RAG_E_ALIGN, "cv_stem_fwd: workspace must be 16-byte aligned");
     if (B <= 0 || C <= 0 || O <= 0 || Df <= 0 || Hf <= 0 || Wf <= 0 || B > 65535 || O > 65535 || Hf > 2147483647 / 4)
         return fail(RAG_E_SHAPE, "cv_stem_fwd: bad shape B=%d C=%d O=%d Df=%d Hf=%d Wf=%d", B, C, O, Df, Hf, Wf);
     if ((size_t)O * Df * Hf * Wf >= ((size_t)1 << 40)) return fail(RAG_E_SHAPE, "cv_stem_fwd: output too large");
@@ -586,13 +588,11 @@ int cv_stem_fwd(const float* x, const float* y, const float* w, const float* sca
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
             if (e != cudaSuccess) return fail((int)e, "cv_stem_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         }
-        int wslot = -1;
-        if (O <= kStemWMaxO) {
-            wslot = (int)(g_stem_ticket.fetch_add(1) % (unsigned)kStemWSlots);
-            stem_regroup_kernel<<<O, 256, 0, st>>>(w, C, wslot);
+        if (workspace) {
+            stem_regroup_kernel<<<O, 256, 0, st>>>(w, C, workspace);
             if (int e = check_launch("cv_stem_fwd(regroup)")) return e;
         }
-        kern<<<dim3(Hf, O, B), nt, smem2, st>>>(x, y, w, scale, shift, out, O, Df, Hf, Wf, wslot, nullptr);
+        kern<<<dim3(Hf, O, B), nt, smem2, st>>>(x, y, w, scale, shift, out, O, Df, Hf, Wf, workspace, nullptr);
     } else if (variant == 1) {
         auto kern = cv_stem_fwd_kernel<12>;
         if (smem > 48 * 1024) {
@@ -608,5 +608,8 @@ int cv_stem_fwd(const float* x, const float* y, const float* w, const float* sca
     }
     return check_launch("cv_stem_fwd");
 }
+
+// bytes of the optional regrouped-weight workspace of cv_stem_fwd / cv_stem_moments
+size_t cv_stem_workspace_bytes(int C, int O) { return C == 12 && O > 0 ? (size_t)O * kStemWPerO * sizeof(float) : 0; }
 
 }  // namespace rag

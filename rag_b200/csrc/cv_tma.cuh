@@ -34,14 +34,13 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // grid: persistent, blockIdx.x strides over items (b, c, row tile).  128 threads.
 // smem: zeros[Df] | 2 stages x ( X[R][Wf] | Y[R][4][Df+Wf+4] )
-__device__ unsigned int g_cvt_ctr[64][2];   // {next item, finished CTAs} per launch slot (see cv_lean.cuh)
 
-// Items = (b*C + c, row tile, d-chunk), handed out IN ORDER from an atomic counter so that the resident CTAs
+// Items = (b*C + c, row tile, d-chunk), handed out IN ORDER from an atomic counter (caller-owned workspace, zeroed by the launcher; see cv_lean.cuh) so that the resident CTAs
 // write neighbouring rows of the same few disparity planes (HBM page locality).
-template <int NT, int MODE>   // MODE (experiments): 0 = full, 1 = right half only, 2 = left half only
+template <int NT>
 __global__ void __launch_bounds__(NT)
 cv_fwd_tma_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ cost,
-                  int B, int C, int Df, int Hf, int Wf, int R, int n_tiles, int dchunk, int n_dchunks, int slot) {
+                  int B, int C, int Df, int Hf, int Wf, int R, int n_tiles, int dchunk, int n_dchunks, unsigned int* __restrict__ ctr) {
     extern __shared__ __align__(128) float cvt_smem[];
     __shared__ int s_item[2];
     const int YS = Df + Wf + 4;                    // one image of one row
@@ -63,12 +62,12 @@ cv_fwd_tma_kernel(const float* __restrict__ x, const float* __restrict__ y, floa
             Y[img * YS + k] = 0.f;              // covers [0, Df+s) for every s <= 3
         }
     }
-    if (tid == 0) s_item[0] = (int)atomicAdd(&g_cvt_ctr[slot][0], 1u);
+    if (tid == 0) s_item[0] = (int)atomicAdd(ctr, 1u);
     __syncthreads();
 
     int item = s_item[0];
     for (int it_local = 0; item < n_items; ++it_local) {
-        if (tid == 0) s_item[(it_local + 1) & 1] = (int)atomicAdd(&g_cvt_ctr[slot][0], 1u);   // published by the barrier below
+        if (tid == 0) s_item[(it_local + 1) & 1] = (int)atomicAdd(ctr, 1u);   // published by the barrier below
         const int it = item / n_dchunks, dc = item - it * n_dchunks;
         const int d_beg = dc * dchunk, nd = min(dchunk, Df - d_beg);
         const int tile = it % n_tiles;
@@ -105,8 +104,7 @@ cv_fwd_tma_kernel(const float* __restrict__ x, const float* __restrict__ y, floa
             const int d = d_beg + dl;
             const int q = d >> 2, s = d & 3;
             const size_t o = (size_t)d * plane + (size_t)r * Wf;
-            if (MODE != 2) bulk_s2g(outR + o, Y + (r * 4 + s) * YS + (Df - 4 * q), (uint32_t)Wf * 4u, policy);
-            if (MODE == 1) continue;
+            bulk_s2g(outR + o, Y + (r * 4 + s) * YS + (Df - 4 * q), (uint32_t)Wf * 4u, policy);
             const float* xr = X + r * Wf;
             if (q > 0) bulk_s2g(outL + o, zeros, (uint32_t)q * 16u, policy);
             float4 m = *reinterpret_cast<const float4*>(xr + 4 * q);
@@ -121,11 +119,6 @@ cv_fwd_tma_kernel(const float* __restrict__ x, const float* __restrict__ y, floa
         item = s_item[(it_local + 1) & 1];
     }
     bulk_wait_read<0>();                             // shared memory must outlive the copies that read it
-    if (tid == 0 && atomicAdd(&g_cvt_ctr[slot][1], 1u) == gridDim.x - 1) {   // last CTA rearms the slot
-        g_cvt_ctr[slot][0] = 0u;
-        g_cvt_ctr[slot][1] = 0u;
-        __threadfence();
-    }
 }
 
 }  // namespace rag

@@ -111,12 +111,6 @@ head_fwd_generic_kernel(const float* __restrict__ cost, float* __restrict__ disp
 
 }  // namespace rag
 #include "disp_head_x3.cuh"
-#include "disp_head_x3p.cuh"
-#include "disp_head_x3c.cuh"
-#include "disp_head_x3t.cuh"
-#include "disp_head_x3tp.cuh"
-#include "disp_head_x3u.cuh"
-#include "disp_head_x3v.cuh"
 #include "disp_head_x3w.cuh"
 #include "disp_head_x3r.cuh"
 namespace rag {
@@ -243,28 +237,26 @@ int upsample_trilinear(const float* cost, float* out, int B, int Dl, int Hl, int
     return check_launch("upsample_trilinear");
 }
 
+// variant: -1 = default; 0 = any (Dl, maxdisp) (one thread per output pixel, fp64 sums); 1 = first x3 kernel (any width);
+// 2 = cube-root tiled kernel (default when maxdisp == 3*Dl, Wl % 4 == 0, 16-byte aligned input); 3 = as 2 with the
+// fp32-lambda correction at every step and TwoSum totals (most accurate, A/B)
 int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, int Hl, int Wl, int D,
                   int variant, cudaStream_t st) {
     if (!cost || !disp) return fail(RAG_E_NULL, "disp_head_fwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 16) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 3) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
     if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl", variant);
     const bool tiled_ok = x3 && (Wl % 4 == 0) && aligned(cost, 16);
-    if (variant >= 4 && !tiled_ok) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl, Wl %% 4 == 0 and 16-byte aligned cost_lr", variant);
-    if (variant == -1) variant = tiled_ok ? 10 : (x3 ? 1 : 0);
-    if (variant >= 10) {
-        // cube-root kernels; fp32-lambda correction: 10 = from the second chunk on (default), 11 = never,
-        // 12 = every step + TwoSum totals (most accurate), 13 = as 10 with TwoSum totals.
+    if (variant >= 2 && !tiled_ok) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl, Wl %% 4 == 0 and 16-byte aligned cost_lr", variant);
+    if (variant == -1) variant = tiled_ok ? 2 : (x3 ? 1 : 0);
+    if (variant >= 2) {
         // (5 block rows per CTA would fill the last wave of the 480x960 B=8 grid better, but 5 warps do not
         // spread evenly over the 4 SM sub-partitions: measured 202 us vs 165 us.)
         constexpr int warps = 4;
         dim3 grid((Wl + 31) / 32, (Hl + warps - 1) / warps, B);
-        size_t smem = (size_t)2 * 16 * (warps + 2) * kTCols * sizeof(float) + ((size_t)18 * 32 * warps + 2 * Dl) * sizeof(float2);
-        if (variant == 14) smem = std::max<size_t>(smem, 58 * 1024);   // 14 / 15 / 16 = as 10, at most 3 / 2 / 1 CTAs per SM (SM sharing)
-        if (variant == 15) smem = std::max<size_t>(smem, 80 * 1024);
-        if (variant == 16) smem = std::max<size_t>(smem, 120 * 1024);
+        const size_t smem = (size_t)2 * 16 * (warps + 2) * kTCols * sizeof(float) + ((size_t)18 * 32 * warps + 2 * Dl) * sizeof(float2);
         auto launch = [&](auto kern) -> int {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -272,52 +264,8 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
             kern<<<grid, 32 * warps, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
             return RAG_OK;
         };
-        int e = RAG_OK;
-        if (variant == 11) e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 0, false>);
-        else if (variant == 12) e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 1, true>);
-        else if (variant == 13) e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 2, true>);
-        else e = launch(head_fwd_x3r_kernel<4, 4, 16, 2, 2, false>);
+        const int e = variant == 3 ? launch(head_fwd_x3r_kernel<4, 4, 16, 2, 1, true>) : launch(head_fwd_x3r_kernel<4, 4, 16, 2, 2, false>);
         if (e) return e;
-    } else if (variant >= 7) {
-        dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
-        const size_t fixed = ((size_t)18 * 128 + 4 * Dl) * sizeof(float2);
-        const size_t smem8 = (size_t)3 * 8 * kTRows * kTCols * sizeof(float) + fixed;     // 3 stages x 8 bins
-        const size_t smem16 = (size_t)2 * 16 * kTRows * kTCols * sizeof(float) + fixed;   // 2 stages x 16 bins
-        if (variant == 7) head_fwd_x3v_kernel<4, 8, 3><<<grid, 128, smem8, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
-        if (variant == 8) head_fwd_x3v_kernel<5, 8, 3><<<grid, 128, smem8, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
-        if (variant == 9) {
-            auto kern = head_fwd_x3v_kernel<4, 16, 2>;
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem16);
-            if (e != cudaSuccess) return fail((int)e, "disp_head_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            kern<<<grid, 128, smem16, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
-        }
-    } else if (variant == 6) {
-        dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
-        const size_t smem = (size_t)kTStages * kTStageFloats * sizeof(float) + (size_t)Dl * sizeof(float4);
-        head_fwd_x3u_kernel<<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
-    } else if (variant == 5) {
-        dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
-        const size_t smem = (size_t)kTStages * kTStageFloats * sizeof(float) + ((size_t)18 * 128 + D) * sizeof(float2);
-        auto kern = head_fwd_x3tp_kernel;
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail((int)e, "disp_head_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        }
-        kern<<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
-    } else if (variant == 4) {
-        dim3 grid((Wl + 31) / 32, (Hl + 3) / 4, B);
-        const size_t smem = ((size_t)kTStages * kTStageFloats + D) * sizeof(float);
-        head_fwd_x3t_kernel<<<grid, 128, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
-    } else if (variant == 3) {
-        constexpr int NT = 128;
-        const long long n = (long long)(Hl + 1) * 3 * Wl;
-        dim3 grid((unsigned)((n + NT - 1) / NT), B);
-        head_fwd_x3c_kernel<NT><<<grid, NT, (size_t)D * sizeof(float), st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
-    } else if (variant == 2) {
-        constexpr int WARPS = 4;
-        dim3 grid((Wl + 1 + 31) / 32, (Hl + 1 + WARPS - 1) / WARPS, B);
-        const size_t smem = ((size_t)D + 20 * WARPS * 32) * sizeof(float2);
-        head_fwd_x3p_kernel<WARPS><<<grid, WARPS * 32, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
     } else if (variant == 1) {
         constexpr int WARPS = 4;
         dim3 grid((Wl + 1 + 31) / 32, (Hl + 1 + WARPS - 1) / WARPS, B);
@@ -330,24 +278,27 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
     return check_launch("disp_head_fwd");
 }
 
+// variant: -1 = default; 0 = any-ratio gather; 1 = block-row tasks, one exp2 per pixel and k-block, both parts added
+// in place with red.global.add (default when maxdisp == 3*Dl); 2 = same with the "B" part to `scratch` + a combine
+// kernel (A/B; needs scratch)
 int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, const float* stats, float* gcost, float* scratch,
                   int B, int Dl, int Hl, int Wl, int D, int variant, cudaStream_t st) {
     if (!cost || !gdisp || !disp || !stats || !gcost) return fail(RAG_E_NULL, "disp_head_bwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 4) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 2) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
     if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_bwd: variant %d needs maxdisp == 3*Dl", variant);
-    if ((variant == 2 || variant == 3) && !scratch) return fail(RAG_E_NULL, "disp_head_bwd: variant %d needs a scratch buffer", variant);
-    if (variant == -1) variant = x3 ? 4 : 0;
-    if (variant >= 2) {   // 4 (default) = one exp2 per pixel and k-block, parts added in place; 3 = same with scratch + combine; 2 = three exp2
+    if (variant == 2 && !scratch) return fail(RAG_E_NULL, "disp_head_bwd: variant 2 needs a scratch buffer");
+    if (variant == -1) variant = x3 ? 1 : 0;
+    if (variant >= 1) {
         const int nJ = (Dl + kBwJ - 1) / kBwJ;
         const int strips = (Wl + 30) / 31;
         const int n_tasks = (Hl + 1) * nJ;
         dim3 grid(strips, (n_tasks + 3) / 4, B);
         const size_t smem = (size_t)3 * (D + 3) * sizeof(float2) + (size_t)4 * kBwWin * sizeof(float);
-        auto kern = variant == 4 ? head_bwd_x3w_kernel<true, true> : variant == 3 ? head_bwd_x3w_kernel<true, false> : head_bwd_x3w_kernel<false, false>;
-        if (variant == 4) {   // two commutative contributions per element into a zeroed buffer (see the kernel's header)
+        auto kern = variant == 1 ? head_bwd_x3w_kernel<true, true> : head_bwd_x3w_kernel<true, false>;
+        if (variant == 1) {   // two commutative contributions per element into a zeroed buffer (see the kernel's header)
             cudaError_t e = cudaMemsetAsync(gcost, 0, (size_t)B * Dl * Hl * Wl * sizeof(float), st);
             if (e != cudaSuccess) return fail((int)e, "disp_head_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
         }
@@ -357,30 +308,17 @@ int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, cons
         }
         kern<<<grid, 128, smem, st>>>(cost, gdisp, disp, stats, gcost, scratch, Dl, Hl, Wl, sd, nJ, n_tasks);
         if (int e = check_launch("disp_head_bwd(main)")) return e;
-        if (variant == 4) return 0;
+        if (variant == 1) return 0;
         const size_t n = (size_t)B * Dl * Hl * Wl;
         const size_t n4 = (aligned(gcost, 16) && aligned(scratch, 16)) ? n / 4 : 0;
         const size_t work = n4 > 0 ? n4 : 1;
         head_bwd_combine_kernel<<<(unsigned)((work + 255) / 256), 256, 0, st>>>(gcost, scratch, n4, n);
         return check_launch("disp_head_bwd(combine)");
     }
-    if (variant == 1) {
-        constexpr int J = 16;
-        const int nJ = (Dl + J - 1) / J;
-        const int strips = (Wl + 30) / 31;
-        // taller row tiles recompute fewer halo rows; use them when there is enough work to fill the GPU
-        int TR = 8;
-        if ((long long)B * strips * ((Hl + TR - 1) / TR) * nJ < 4LL * 4 * kNumSMs) TR = 4;
-        const int n_tasks = ((Hl + TR - 1) / TR) * nJ;
-        dim3 grid(strips, (n_tasks + 3) / 4, B);
-        const size_t smem = (size_t)(3 * (D + 3) + 4 * J * 32) * sizeof(float);
-        head_bwd_x3_kernel<J><<<grid, 128, smem, st>>>(cost, gdisp, disp, stats, gcost, Dl, Hl, Wl, sd, TR, nJ, n_tasks);
-    } else {
-        constexpr int NT = 128;
-        const size_t nvox = (size_t)Dl * Hl * Wl;
-        dim3 grid((unsigned)((nvox + NT - 1) / NT), B);
-        head_bwd_generic_kernel<NT><<<grid, NT, 0, st>>>(cost, gdisp, disp, stats, gcost, Dl, Hl, Wl, D, sd, sh, sw);
-    }
+    constexpr int NT = 128;
+    const size_t nvox = (size_t)Dl * Hl * Wl;
+    dim3 grid((unsigned)((nvox + NT - 1) / NT), B);
+    head_bwd_generic_kernel<NT><<<grid, NT, 0, st>>>(cost, gdisp, disp, stats, gcost, Dl, Hl, Wl, D, sd, sh, sw);
     return check_launch("disp_head_bwd");
 }
 

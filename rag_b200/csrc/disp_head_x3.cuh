@@ -9,13 +9,11 @@
 //
 // All weights come from src_index<true>() -- PyTorch's fp32 lambda arithmetic -- never from 1/3, 2/3.
 #pragma once
-#include "common.cuh"
+#include "head_common.cuh"
 
 namespace rag {
 
 // blends are produced directly as log2-domain exponents: z = -log2(e) * v
-constexpr float kX3NegLog2e = -1.4426950408889634f;
-constexpr float kX3Tau = 24.0f;  // lazy-rescale threshold (log2 units)
 
 // Tables of one axis of block `blk`: lambdas of its 3 full-res indices (invalid ones clamped into
 // range) and, for the backward, the weights with which each index feeds low-res cell `blk` (wa) and
@@ -215,178 +213,6 @@ head_fwd_x3_kernel(const float* __restrict__ cost, float* __restrict__ disp, flo
                 stats[(size_t)b * 2 * img + o] = m[i];
                 stats[(size_t)b * 2 * img + img + o] = inv;
             }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// backward: deterministic, atomics-free.
-//   gcost[j,r,c] = sum_{k,h,w} Wd(j,k) Wh(r,h) Ww(c,w) * ( -g[h,w] p_k[h,w] (k - disp[h,w]) ),
-//   p_k = 2^(z_k - m) * inv  rebuilt from cost_lr and the forward's stats.
-// A warp owns 31 low-res columns (32 block columns c0-1..c0+30: lane l -> block c0-1+l, and each
-// low-res cell column gets the "A" part of its own block plus the "B" part of the block to its
-// left via one shuffle), TR low-res rows (it sweeps block rows r0-1..r0+TR-1 and carries each
-// block row's "B" part to the next row in shared memory) and a chunk of J low-res bins (k-blocks
-// j0-1..j0+J-1, the "B" part of a k-block is carried to the next in registers).  Every gcost element
-// is produced by exactly one lane with a fixed summation order.
-// grid: x = ceil(Wl/31), y = ceil(n_tasks/4), z = B; task = row_tile * nJ + bin_chunk.
-// ---------------------------------------------------------------------------------------------
-template <int J>
-__global__ void __launch_bounds__(128)
-head_bwd_x3_kernel(const float* __restrict__ cost, const float* __restrict__ gdisp, const float* __restrict__ disp,
-                   const float* __restrict__ stats, float* __restrict__ gcost,
-                   int Dl, int Hl, int Wl, float scale, int TR, int nJ, int n_tasks) {
-    extern __shared__ float x3_smem[];
-    const int D = 3 * Dl, H = 3 * Hl, W = 3 * Wl;
-    float* lz = x3_smem;            // [D+3] lambda1 of bin k (exponent interpolation)
-    float* dA = lz + (D + 3);       // [D+3] weight of bin k into low-res cell (k-1)/3
-    float* dB = dA + (D + 3);       // [D+3] weight of bin k into low-res cell (k-1)/3 + 1
-    float* carry_all = dB + (D + 3);
-    for (int k = threadIdx.x; k < D + 3; k += 128) {
-        float l0 = 0.f, l1 = 0.f, wa = 0.f, wb = 0.f;
-        if (k < D) {
-            int t0, t1;
-            src_index<true>(scale, k, Dl, t0, t1, l0, l1);
-            const int jb = k == 0 ? 0 : (k - 1) / 3;
-            wa = (t0 == jb ? l0 : 0.f) + (t1 == jb ? l1 : 0.f);
-            wb = (t0 == jb + 1 ? l0 : 0.f) + (t1 == jb + 1 ? l1 : 0.f);
-        }
-        lz[k] = l1; dA[k] = wa; dB[k] = wb;
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int task = blockIdx.y * 4 + warp;
-    if (task >= n_tasks) return;
-    float* carry = carry_all + warp * (J * 32) + lane;  // [J] per lane, stride 32
-    const int tile = task / nJ, jc = task - tile * nJ;
-    const int r0 = tile * TR, r1 = min(r0 + TR, Hl);
-    const int j0 = jc * J, j1 = min(j0 + J, Dl);
-    const int b = blockIdx.z;
-    const int c_raw = blockIdx.x * 31 + lane - 1;
-    const bool lane_on = c_raw <= Wl - 1;
-    const int c = min(c_raw, Wl - 1);
-
-    X3Axis aw;
-    x3_axis(scale, c, Wl, aw);
-    if (!lane_on) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { aw.wa[i] = 0.f; aw.wb[i] = 0.f; aw.valid[i] = false; }
-    }
-    const size_t plane = (size_t)Hl * Wl;
-    const size_t img = (size_t)H * W;
-    const float* base = cost + (size_t)b * Dl * plane;
-    const float* gd = gdisp + (size_t)b * img;
-    const float* dp = disp + (size_t)b * img;
-    const float* sm = stats + (size_t)b * 2 * img;
-    float* gout = gcost + (size_t)b * Dl * plane;
-    const int jb0 = max(j0 - 1, 0);
-
-    for (int rb = r0 - 1; rb < r1; ++rb) {
-        X3Axis ah;
-        x3_axis(scale, rb, Hl, ah);
-        float hs0[3], hs1[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { hs0[i] = ah.l0[i] * kX3NegLog2e; hs1[i] = ah.l1[i] * kX3NegLog2e; }
-        float m[9], gneg[9], dsp[9], a[9], nxt[9];
-#pragma unroll
-        for (int ph = 0; ph < 3; ++ph)
-#pragma unroll
-            for (int pw = 0; pw < 3; ++pw) {
-                const int i = ph * 3 + pw;
-                const size_t o = (size_t)ah.idx[ph] * W + aw.idx[pw];   // clamped -> always a real pixel
-                const bool ok = ah.valid[ph] && aw.valid[pw];
-                m[i] = __ldg(sm + o);
-                dsp[i] = __ldg(dp + o);
-                gneg[i] = ok ? -__ldg(gd + o) * __ldg(sm + img + o) : 0.f;
-            }
-        // Ground-truth masks are sparse and spatially coherent (no LiDAR returns in the sky, occlusions): if no
-        // pixel of the warp's 32 blocks carries an upstream gradient, the whole block row contributes zeros --
-        // skip its exp2 work but keep the carries and the stores going.
-        float gabs = 0.f;
-#pragma unroll
-        for (int i = 0; i < 9; ++i) gabs = fmaxf(gabs, fabsf(gneg[i]));
-        if (!__any_sync(0xffffffffu, gabs != 0.f)) {
-            for (int jb = max(jb0, j0); jb < j1; ++jb) {
-                const int jj = jb - j0;
-                if (rb >= r0 && lane >= 1 && lane_on) gout[(size_t)jb * plane + (size_t)rb * Wl + c] = carry[jj * 32];
-                carry[jj * 32] = 0.f;
-            }
-            continue;
-        }
-        X3Loader ld;
-        ld.init(base, Wl, plane, Dl, jb0, ah.lo0, ah.lo1, aw.lo0, aw.lo1);
-        x3_blend9_rel(ld.v, aw.l0, aw.l1, hs0, hs1, m, a);
-        ld.next();
-        float pA = 0.f, pB = 0.f;  // "B" bin-part of the previous k-block, split by row part
-
-        for (int jb = jb0; jb < j1; ++jb) {
-            x3_blend9_rel(ld.v, aw.l0, aw.l1, hs0, hs1, m, nxt);
-            ld.next();
-            const int k1 = 3 * jb + 1;
-            const float lz1 = lz[k1], lz2 = lz[k1 + 1], lz3 = lz[k1 + 2];
-            const float a1 = dA[k1], a2 = dA[k1 + 1], a3 = dA[k1 + 2];
-            const float b1 = dB[k1], b2 = dB[k1 + 1], b3 = dB[k1 + 2];
-            const float kf = (float)k1;
-            float g0[9], g1[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                const float t = nxt[i];
-                const float dlt = t - a[i];
-                const float dk = kf - dsp[i];
-                float s0 = 0.f, s1 = 0.f;
-                if (jb == 0) {  // full-res bin 0 rides with k-block 0
-                    const float u = ex2_approx(a[i]) * (dk - 1.f);
-                    s0 = dA[0] * u;
-                    s1 = dB[0] * u;
-                }
-                const float u1 = ex2_approx(__fmaf_rn(lz1, dlt, a[i])) * dk;
-                const float u2 = ex2_approx(__fmaf_rn(lz2, dlt, a[i])) * (dk + 1.f);
-                const float u3 = ex2_approx(__fmaf_rn(lz3, dlt, a[i])) * (dk + 2.f);
-                s0 = __fmaf_rn(a1, u1, s0); s1 = __fmaf_rn(b1, u1, s1);
-                s0 = __fmaf_rn(a2, u2, s0); s1 = __fmaf_rn(b2, u2, s1);
-                s0 = __fmaf_rn(a3, u3, s0); s1 = __fmaf_rn(b3, u3, s1);
-                g0[i] = gneg[i] * s0;
-                g1[i] = gneg[i] * s1;
-                a[i] = t;
-            }
-            // separable transpose of the bilinear blend: rows (A -> cell row rb, B -> rb+1), then columns
-            float v0A, v0B, v1A, v1B;
-            {
-                float tAA = 0.f, tAB = 0.f, tBA = 0.f, tBB = 0.f;
-#pragma unroll
-                for (int pw = 0; pw < 3; ++pw) {
-                    const float uA = __fmaf_rn(ah.wa[2], g0[6 + pw], __fmaf_rn(ah.wa[1], g0[3 + pw], ah.wa[0] * g0[pw]));
-                    const float uB = __fmaf_rn(ah.wb[2], g0[6 + pw], __fmaf_rn(ah.wb[1], g0[3 + pw], ah.wb[0] * g0[pw]));
-                    tAA = __fmaf_rn(aw.wa[pw], uA, tAA); tAB = __fmaf_rn(aw.wb[pw], uA, tAB);
-                    tBA = __fmaf_rn(aw.wa[pw], uB, tBA); tBB = __fmaf_rn(aw.wb[pw], uB, tBB);
-                }
-                v0A = tAA + __shfl_up_sync(0xffffffffu, tAB, 1);
-                v0B = tBA + __shfl_up_sync(0xffffffffu, tBB, 1);
-            }
-            {
-                float tAA = 0.f, tAB = 0.f, tBA = 0.f, tBB = 0.f;
-#pragma unroll
-                for (int pw = 0; pw < 3; ++pw) {
-                    const float uA = __fmaf_rn(ah.wa[2], g1[6 + pw], __fmaf_rn(ah.wa[1], g1[3 + pw], ah.wa[0] * g1[pw]));
-                    const float uB = __fmaf_rn(ah.wb[2], g1[6 + pw], __fmaf_rn(ah.wb[1], g1[3 + pw], ah.wb[0] * g1[pw]));
-                    tAA = __fmaf_rn(aw.wa[pw], uA, tAA); tAB = __fmaf_rn(aw.wb[pw], uA, tAB);
-                    tBA = __fmaf_rn(aw.wa[pw], uB, tBA); tBB = __fmaf_rn(aw.wb[pw], uB, tBB);
-                }
-                v1A = tAA + __shfl_up_sync(0xffffffffu, tAB, 1);
-                v1B = tBA + __shfl_up_sync(0xffffffffu, tBB, 1);
-            }
-            if (jb >= j0) {
-                const int jj = jb - j0;
-                const float rowA = v0A + pA;   // cell (jb, rb): own k-block's A part + previous k-block's B part
-                const float rowB = v0B + pB;   // cell (jb, rb+1)
-                if (rb >= r0) {
-                    const float out = rowA + carry[jj * 32];
-                    if (lane >= 1 && lane_on) gout[(size_t)jb * plane + (size_t)rb * Wl + c] = out;
-                }
-                carry[jj * 32] = rowB;
-            }
-            pA = v1A;
-            pB = v1B;
         }
     }
 }

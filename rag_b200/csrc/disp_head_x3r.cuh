@@ -37,7 +37,7 @@
 #pragma once
 #include <type_traits>
 
-#include "disp_head_x3v.cuh"
+#include "disp_head_x3.cuh"
 
 namespace rag {
 

@@ -16,7 +16,7 @@
 #pragma once
 #include <cuda_pipeline.h>
 
-#include "disp_head_x3p.cuh"
+#include "disp_head_x3.cuh"
 
 namespace rag {
 

@@ -16,6 +16,8 @@
 // the head that runs next.
 #include <cuda_pipeline.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace rag {
@@ -32,10 +34,23 @@ constexpr int kLcStage = kLcRows * kLcSW;                   // floats per stage 
 
 
 // Weights live in CONSTANT memory (copied there device-to-device, stream-ordered, before the launch) so that
-// the FFMAs take them as uniform-register operands instead of 27 vector registers per thread.  Eight slots,
-// handed out round-robin, so that up to eight convolutions with different weights can be in flight.
+// the FFMAs take them as uniform-register operands instead of 27 vector registers per thread (168 registers at
+// three CTAs per SM leave no room for them).  Constant memory cannot be caller-owned, so this is the ONE piece
+// of per-device state the library keeps, and it is made race-free instead of hidden: eight slots are used
+// round-robin, every launch records an event after its kernel, and the next user of a slot -- on whatever
+// stream -- first makes its stream wait for that event, so a slot is never rewritten under a kernel that reads
+// it (a cross-stream dependency appears only when a slot comes round again, eight launches later).  The
+// event chain cannot be expressed inside a stream capture: a capturing stream is refused with RAG_E_CAPTURE
+// (callers fall back to the reference's own nn.Conv3d there).
 constexpr int kLcMaxC = 64, kLcSlotsW = 8;
 __constant__ float c_lcw[kLcSlotsW][kLcMaxC * 27];
+struct LcRing {
+    std::mutex mu;
+    unsigned next = 0;
+    cudaEvent_t ev[kLcSlotsW] = {};
+    bool have[kLcSlotsW] = {};
+};
+static LcRing g_lc_ring[64];   // per device
 
 // grid: x = ceil(W/64), y = ceil(H/8), z = B * ceil(D/16); 256 threads.
 // smem: STAGES x kLcStage floats
@@ -181,17 +196,36 @@ int conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int
     // two output rows per thread (128-thread CTAs, 18 instead of 12 FMAs per shared-memory load) pay off once
     // the grid is several waves deep: 0.501 vs 0.554 ms at B=8 480x960, 0.126 vs 0.122 ms at B=4 288x576
     const long long ctas = (long long)((W + kLcWT - 1) / kLcWT) * ((H + kLcHT - 1) / kLcHT) * B * n_dt;
-    const int TH = ctas >= 4LL * 3 * kNumSMs ? 2 : 1;
+    const int TH = ctas >= 4LL * 3 * num_sms() ? 2 : 1;
     auto kern = TH == 2 ? conv3d_c1_kernel<stages, 2> : conv3d_c1_kernel<stages, 1>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    static std::atomic<unsigned> ticket{0};
-    const int wslot = (int)(ticket.fetch_add(1) % (unsigned)kLcSlotsW);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    e = cudaStreamIsCapturing(st, &cap);
+    if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaStreamIsCapturing: %s", cudaGetErrorString(e));
+    if (cap != cudaStreamCaptureStatusNone)
+        return fail(RAG_E_CAPTURE, "conv3d_c1_fwd: the stream is capturing; the constant-memory weight slots are ordered with events and cannot be captured");
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: unsupported device index");
+    LcRing& ring = g_lc_ring[dev];
+    std::lock_guard<std::mutex> lock(ring.mu);
+    const int wslot = (int)(ring.next++ % (unsigned)kLcSlotsW);
+    if (ring.have[wslot]) {
+        e = cudaStreamWaitEvent(st, ring.ev[wslot], 0);      // the previous reader of this slot has finished
+        if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaStreamWaitEvent: %s", cudaGetErrorString(e));
+    } else {
+        e = cudaEventCreateWithFlags(&ring.ev[wslot], cudaEventDisableTiming);
+        if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaEventCreate: %s", cudaGetErrorString(e));
+        ring.have[wslot] = true;
+    }
     e = cudaMemcpyToSymbolAsync(c_lcw, w, (size_t)C * 27 * sizeof(float), (size_t)wslot * kLcMaxC * 27 * sizeof(float), cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: weight copy: %s", cudaGetErrorString(e));
     dim3 grid((W + kLcWT - 1) / kLcWT, (H + kLcHT - 1) / kLcHT, B * n_dt);
     kern<<<grid, 256 / TH, smem, st>>>(in, w, out, C, D, H, W, n_dt, wslot);
-    return check_launch("conv3d_c1_fwd");
+    if (int rc = check_launch("conv3d_c1_fwd")) return rc;
+    e = cudaEventRecord(ring.ev[wslot], st);
+    if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaEventRecord: %s", cudaGetErrorString(e));
+    return RAG_OK;
 }
 
 }  // namespace rag

@@ -27,7 +27,10 @@ def _stream(t: torch.Tensor) -> int:
 # ------------------------------------------------------------------------------------------------
 # cost volume
 # ------------------------------------------------------------------------------------------------
-def cost_volume_forward(x: torch.Tensor, y: torch.Tensor, df: int, variant: int | None = None) -> torch.Tensor:
+def cost_volume_forward(x: torch.Tensor, y: torch.Tensor, df: int, variant: int | None = None, workspace: bool = True) -> torch.Tensor:
+    """``workspace=True`` (default) hands the library a fresh 16-byte device buffer for the work counter of the
+    persistent kernel (rag_cost_volume_fwd_ws; the caching allocator makes it stream-ordered and private to the
+    launch, graph-capture safe); ``workspace=False`` calls the stateless one-CTA-per-item entry point."""
     _require(x, "x"), _require(y, "y")
     if x.dim() != 4 or x.shape != y.shape:
         raise RuntimeError(f"rag_b200: cost volume wants x,y of identical [B,C,Hf,Wf] shape, got {tuple(x.shape)} and {tuple(y.shape)}")
@@ -40,10 +43,15 @@ def cost_volume_forward(x: torch.Tensor, y: torch.Tensor, df: int, variant: int 
         return cost
     L = _cabi.lib()
     with torch.cuda.device(x.device):
+        ws = torch.empty(4, dtype=torch.int32, device=x.device) if workspace else None
+        wp = ws.data_ptr() if ws is not None else None
         if variant is None:
-            rc = L.rag_cost_volume_fwd(x.data_ptr(), y.data_ptr(), cost.data_ptr(), b, c, df, hf, wf, _stream(x))
+            if ws is None:
+                rc = L.rag_cost_volume_fwd(x.data_ptr(), y.data_ptr(), cost.data_ptr(), b, c, df, hf, wf, _stream(x))
+            else:
+                rc = L.rag_cost_volume_fwd_ws(x.data_ptr(), y.data_ptr(), cost.data_ptr(), b, c, df, hf, wf, wp, _stream(x))
         else:
-            rc = L.rag_cost_volume_fwd_v(x.data_ptr(), y.data_ptr(), cost.data_ptr(), b, c, df, hf, wf, variant, _stream(x))
+            rc = L.rag_cost_volume_fwd_v(x.data_ptr(), y.data_ptr(), cost.data_ptr(), b, c, df, hf, wf, wp, variant, _stream(x))
     _cabi.check(rc, "rag_cost_volume_fwd")
     return cost
 
@@ -132,8 +140,8 @@ def disp_head_backward(cost_lr, gdisp, disp, stats, maxdisp: int, variant: int |
     if gcost.numel() == 0:
         return gcost
     L = _cabi.lib()
-    # work buffer of the scratch + combine A/B variants only (the default adds both parts in place)
-    scratch = torch.empty_like(cost_lr) if (maxdisp == 3 * dl and variant in (2, 3)) else None
+    # work buffer of the scratch + combine A/B variant only (the default adds both parts in place)
+    scratch = torch.empty_like(cost_lr) if (maxdisp == 3 * dl and variant == 2) else None
     sp = scratch.data_ptr() if scratch is not None else None
     with torch.cuda.device(cost_lr.device):
         if variant is None:

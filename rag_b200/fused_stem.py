@@ -41,6 +41,13 @@ class VirtualCostVolume:
         return cost_volume(self.x, self.y, self.maxdisp)
 
 
+def _stem_workspace(L, c, o, device):
+    """Caller-owned buffer for the regrouped weights (rag_cv_stem_workspace_bytes): fresh per launch from the caching
+    allocator, so it is stream-ordered and never shared between launches."""
+    n = int(L.rag_cv_stem_workspace_bytes(c, o))
+    return torch.empty(n // 4, dtype=torch.float32, device=device) if n else None
+
+
 def cv_stem_forward(x, y, weight, scale=None, shift=None, relu=False, maxdisp=192, variant=None) -> torch.Tensor:
     """out = relu?(scale * conv3d(cost_volume(x, y), weight, padding=1) + shift), fp32, volume never built."""
     _require(x, "x"), _require(y, "y"), _require(weight, "weight")
@@ -55,14 +62,18 @@ def cv_stem_forward(x, y, weight, scale=None, shift=None, relu=False, maxdisp=19
     out = torch.empty((b, o, df, hf, wf), dtype=torch.float32, device=x.device)
     if out.numel() == 0:
         return out
-    sp = scale.contiguous().data_ptr() if scale is not None else None
-    hp = shift.contiguous().data_ptr() if shift is not None else None
+    scale = scale.contiguous() if scale is not None else None
+    shift = shift.contiguous() if shift is not None else None
+    sp = scale.data_ptr() if scale is not None else None
+    hp = shift.data_ptr() if shift is not None else None
     L = _cabi.lib()
     with torch.cuda.device(x.device):
+        ws = _stem_workspace(L, c, o, x.device)
+        wp = ws.data_ptr() if ws is not None else None
         if variant is None:
-            rc = L.rag_cv_stem_fwd(x.data_ptr(), y.data_ptr(), weight.data_ptr(), sp, hp, int(relu), out.data_ptr(), b, c, o, df, hf, wf, _stream(x))
+            rc = L.rag_cv_stem_fwd(x.data_ptr(), y.data_ptr(), weight.data_ptr(), sp, hp, int(relu), out.data_ptr(), b, c, o, df, hf, wf, wp, _stream(x))
         else:
-            rc = L.rag_cv_stem_fwd_v(x.data_ptr(), y.data_ptr(), weight.data_ptr(), sp, hp, int(relu), out.data_ptr(), b, c, o, df, hf, wf, variant, _stream(x))
+            rc = L.rag_cv_stem_fwd_v(x.data_ptr(), y.data_ptr(), weight.data_ptr(), sp, hp, int(relu), out.data_ptr(), b, c, o, df, hf, wf, wp, variant, _stream(x))
     _cabi.check(rc, "rag_cv_stem_fwd")
     return out
 
@@ -81,8 +92,11 @@ def cv_stem_batch_stats(x, y, weight, maxdisp=192):
     df = int(maxdisp / 3)
     x, y, weight = x.contiguous(), y.contiguous(), weight.contiguous()
     rows = torch.empty((b, hf, o, 2), dtype=torch.float64, device=x.device)
+    L = _cabi.lib()
     with torch.cuda.device(x.device):
-        rc = _cabi.lib().rag_cv_stem_moments(x.data_ptr(), y.data_ptr(), weight.data_ptr(), rows.data_ptr(), b, c, o, df, hf, wf, _stream(x))
+        ws = _stem_workspace(L, c, o, x.device)
+        rc = L.rag_cv_stem_moments(x.data_ptr(), y.data_ptr(), weight.data_ptr(), rows.data_ptr(), b, c, o, df, hf, wf,
+                                   ws.data_ptr() if ws is not None else None, _stream(x))
     _cabi.check(rc, "rag_cv_stem_moments")
     s = rows.sum(dim=(0, 1))                      # fixed-order fp64 reduction of B*Hf row pairs per channel
     n = b * df * hf * wf
@@ -105,8 +119,8 @@ def stem_forward(self, x):
         if self.relu:
             x = F.relu(x, inplace=True)
         return x
-    needs_grad = torch.is_grad_enabled() and (x.x.requires_grad or x.y.requires_grad or self.conv.weight.requires_grad
-                                              or (self.use_bn and self.bn.weight is not None and self.bn.weight.requires_grad))
+    needs_grad = torch.is_grad_enabled() and (x.x.requires_grad or x.y.requires_grad
+                                              or any(p.requires_grad for p in self.parameters()))
     bn_batch_stats = self.use_bn and (self.bn.training or not self.bn.track_running_stats)
     if needs_grad or not _fusable(self.conv, x):
         return stem_forward(self, x.materialize())          # the reference's path on the materialised volume

@@ -36,13 +36,22 @@ def conv3d_c1_forward(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
 
 
 def qualifies(conv: nn.Module, x: torch.Tensor) -> bool:
-    """True when ``conv(x)`` is the layer the kernel implements and no gradient is wanted."""
-    return (isinstance(conv, nn.Conv3d) and conv.out_channels == 1 and conv.bias is None and conv.kernel_size == (3, 3, 3)
+    """True when ``conv(x)`` is the layer the kernel implements (csrc/last_conv.cu ``conv3d_c1_fwd`` preconditions: C <= 64,
+    W % 4 == 0, B*ceil(D/16) <= 65535, 16-byte aligned tensors, not inside a CUDA-graph capture) and no gradient is wanted."""
+    if not (isinstance(conv, nn.Conv3d) and conv.out_channels == 1 and conv.bias is None and conv.kernel_size == (3, 3, 3)
             and conv.stride == (1, 1, 1) and conv.padding == (1, 1, 1) and conv.dilation == (1, 1, 1) and conv.groups == 1
-            and conv.padding_mode == "zeros" and conv.weight.dtype == torch.float32
-            and isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
-            and x.shape[1] == conv.in_channels and x.shape[-1] % 4 == 0 and x.shape[2] * x.shape[3] * x.shape[4] < 2 ** 31
-            and not (torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad)))
+            and conv.padding_mode == "zeros" and conv.weight.dtype == torch.float32 and conv.weight.is_cuda
+            and conv.in_channels <= 64):
+        return False
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
+            and x.shape[1] == conv.in_channels and x.numel() > 0 and x.shape[-1] % 4 == 0
+            and x.shape[2] * x.shape[3] * x.shape[4] < 2 ** 31 and x.shape[0] * ((x.shape[2] + 15) // 16) <= 65535):
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
+        return False
+    if x.is_contiguous() and x.data_ptr() % 16:
+        return False
+    return not torch.cuda.is_current_stream_capturing()      # the constant-memory weight slots are event-ordered
 
 
 def conv_forward(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:

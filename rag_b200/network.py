@@ -24,13 +24,21 @@ from .functional import cost_volume, disp_head
 from .fused_stem import VirtualCostVolume, stem_forward
 from .modules import CostVolume, Disp, DisparityRegression  # noqa: F401  (re-exported)
 
-# set by install(..., fuse_stem=True): the patched forwards then hand the Matching Net a VirtualCostVolume
-# and its first layer (ConvBR_3d, made fusion-aware) runs cost volume + conv + BN + ReLU as one kernel
+# Process-wide default set by install(fuse_stem=...) (every install() call sets it, so a later
+# install(fuse_stem=False) switches it off again).  A network instance overrides it with the attribute
+# ``rag_b200_fuse_stem`` (True / False).  When on, the patched forwards hand the Matching Net a
+# VirtualCostVolume and its first layer (ConvBR_3d, made fusion-aware) runs cost volume + conv + BN + ReLU
+# as one kernel; this needs ConvBR_3d.forward to be the fusion-aware one (install(fuse_stem=True) once).
 _FUSE_STEM = False
+_STEM_AWARE = False      # ConvBR_3d.forward has been rebound (a VirtualCostVolume may be handed out)
+_ORIGINALS = {}          # (module object id, attribute path) -> original, for uninstall()
 
 
-def _volume(x, y, maxdisp):
-    if _FUSE_STEM:
+def _volume(self, x, y, maxdisp):
+    fuse = getattr(self, "rag_b200_fuse_stem", None)
+    if fuse is None:
+        fuse = _FUSE_STEM
+    if fuse and _STEM_AWARE:
         return VirtualCostVolume(x, y, maxdisp)
     return cost_volume(x, y, maxdisp)
 
@@ -47,7 +55,7 @@ def network_forward(self, left, right, t, task_arch=None, path=None):
     """Replacement for Network.forward (rag_model.py:369-387)."""
     x = self.feature(left, task_arch, path)
     y = self.feature(right, task_arch, path)
-    cost = _volume(x, y, self.maxdisp)              # rag_model.py:375-383
+    cost = _volume(self, x, y, self.maxdisp)        # rag_model.py:375-383
     cost = self.matching(cost, task_arch, path)
     return _head(self, cost)                        # rag_model.py:386
 
@@ -56,7 +64,7 @@ def network_search_forward(self, left, right, t, selected_ops):
     """Replacement for Network.search_forward (rag_model.py:688-706)."""
     x = self.search_feature(left, selected_ops)
     y = self.search_feature(right, selected_ops)
-    cost = _volume(x, y, self.maxdisp)              # rag_model.py:694-702
+    cost = _volume(self, x, y, self.maxdisp)        # rag_model.py:694-702
     cost = self.search_matching(cost, selected_ops, t)
     return _head(self, cost)
 
@@ -84,26 +92,46 @@ def install(rag_model=None, mdenas_basicmodel=None, operations_3d=None, fuse_ste
     csrc/last_conv.cu when no gradient is wanted (rag_b200/last_conv.py).  NOTE: only the
     growable ``Network`` starts its Matching Net with a ConvBR_3d on the raw volume in all configurations;
     the search supernet (``BasicNetwork``/``AutoMatching``) keeps the materialised volume."""
-    global _FUSE_STEM
+    global _FUSE_STEM, _STEM_AWARE
     done = {}
+
+    def bind(owner, name, value):
+        _ORIGINALS.setdefault((owner, name), getattr(owner, name))
+        setattr(owner, name, value)
+
     if fuse_stem:
         if operations_3d is None:
             raise ValueError("fuse_stem=True needs operations_3d (the reference's automl.operations_3d module)")
-        operations_3d.ConvBR_3d.forward = stem_forward
-        _FUSE_STEM = True
+        bind(operations_3d.ConvBR_3d, "forward", stem_forward)
+        _STEM_AWARE = True
         done["operations_3d"] = ["ConvBR_3d.forward"]
+    _FUSE_STEM = bool(fuse_stem)          # always (re)set: install(fuse_stem=False) after a fused install turns it off
     if rag_model is not None:
-        rag_model.Network.forward = network_forward
-        rag_model.Network.search_forward = network_search_forward
-        rag_model.Disp = Disp
-        rag_model.DisparityRegression = DisparityRegression
+        bind(rag_model.Network, "forward", network_forward)
+        bind(rag_model.Network, "search_forward", network_search_forward)
+        bind(rag_model, "Disp", Disp)
+        bind(rag_model, "DisparityRegression", DisparityRegression)
         done["rag_model"] = ["Network.forward", "Network.search_forward", "Disp", "DisparityRegression"]
     if mdenas_basicmodel is not None:
-        mdenas_basicmodel.BasicNetwork.forward = basic_network_forward
-        mdenas_basicmodel.Disp = Disp
-        mdenas_basicmodel.DisparityRegression = DisparityRegression
+        bind(mdenas_basicmodel.BasicNetwork, "forward", basic_network_forward)
+        bind(mdenas_basicmodel, "Disp", Disp)
+        bind(mdenas_basicmodel, "DisparityRegression", DisparityRegression)
         done["mdenas_basicmodel"] = ["BasicNetwork.forward", "Disp", "DisparityRegression"]
     return done
+
+
+def uninstall() -> int:
+    """Undo every install(): restore the reference's own forwards / classes.  Returns how many bindings
+    were restored.  (Tests use it to compare patched and unpatched networks in one process.)"""
+    global _FUSE_STEM, _STEM_AWARE
+    n = 0
+    for (owner, name), orig in list(_ORIGINALS.items()):
+        setattr(owner, name, orig)
+        n += 1
+    _ORIGINALS.clear()
+    _FUSE_STEM = False
+    _STEM_AWARE = False
+    return n
 
 
 class PathRouter:

@@ -13,7 +13,7 @@ import torch
 from . import functional as F_
 from .modules import CostVolume, Disp
 
-CV_FWD_SHARED = 32   # include/rag_b200.h RAG_CV_FWD_SHARED
+CV_FWD_SHARED = 3    # include/rag_b200.h RAG_CV_FWD_SHARED
 
 
 class OverlappedPath:

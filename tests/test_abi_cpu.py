@@ -39,7 +39,9 @@ def test_argument_errors_without_gpu():
     assert b"null" in lib.rag_last_error()
     assert lib.rag_disp_head_fwd(None, None, None, 1, 1, 1, 1, 3, None) == -1
     assert lib.rag_loss_metrics_scratch(480, 960) > 0
-    assert lib.rag_cv_stem_moments(None, None, None, None, 1, 12, 12, 8, 4, 8, None) == -1       # null pointers
+    assert lib.rag_cv_stem_moments(None, None, None, None, 1, 12, 12, 8, 4, 8, None, None) == -1       # null pointers
+    assert lib.rag_cost_volume_fwd_ws(None, None, None, 1, 1, 1, 1, 1, None, None) == -1
+    assert lib.rag_cv_stem_workspace_bytes(12, 12) == 12 * 2 * 12 * 3 * 12 * 4
     assert lib.rag_disp_head_bwd(None, None, None, None, None, None, 1, 1, 1, 1, 3, None) == -1
     with pytest.raises(RuntimeError, match="code -1"):
         _cabi.check(-1, "x")

@@ -154,14 +154,22 @@ def test_network_forward_with_fused_stem():
     left, right = randn((2, 3, 24, 96), g).cuda(), randn((2, 3, 24, 96), g).cuda()
     with torch.no_grad():
         ref = O.disp_head_ref(net.matching(O.cost_volume_ref(net.feature(left), net.feature(right), md)), md)
-        old_fwd, old_flag = ConvBR_3d.forward, N._FUSE_STEM
+        import types
+
+        ops3d = types.SimpleNamespace(ConvBR_3d=ConvBR_3d)
         try:
-            ConvBR_3d.forward = stem_forward
-            N._FUSE_STEM = True
+            N.install(operations_3d=ops3d, fuse_stem=True)
+            assert ConvBR_3d.forward is stem_forward
             out = N.network_forward(net, left, right, 0)
+            net.rag_b200_fuse_stem = False                      # per-instance opt-out: the materialised path
+            out_plain = N.network_forward(net, left, right, 0)
+            del net.rag_b200_fuse_stem
+            N.install(fuse_stem=False)                          # a later plain install() switches the default off
+            assert N._FUSE_STEM is False
         finally:
-            ConvBR_3d.forward = old_fwd
-            N._FUSE_STEM = old_flag
+            N.uninstall()
+        assert ConvBR_3d.forward is not stem_forward
+    assert (out_plain - ref).abs().max().item() <= 1e-4
     assert (out - ref).abs().max().item() <= 2e-4
 
 

@@ -39,16 +39,19 @@ def test_cost_volume_guards(L, shape):
     g = gen(1)
     x, y = randn((b, c, hf, wf), g).cuda(), randn((b, c, hf, wf), g).cuda()
     n = b * 2 * c * df * hf * wf
-    variants = [0, 1, 2, 3] + ([4, 8, 9, 10, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36] if wf % 4 == 0 else []) + ([11, 12, 13, 14] if (wf % 4 == 0 and df % 4 == 0 and df <= wf) else [])
+    variants = [-1, 0] + ([1, 2, 3] if wf % 4 == 0 else []) + ([4] if (wf % 4 == 0 and df % 4 == 0 and df <= wf) else [])
     for v in variants:
         buf, out = window(n)
-        assert L.rag_cost_volume_fwd_v(x.data_ptr(), y.data_ptr(), out.data_ptr(), b, c, df, hf, wf, v, st()) == 0
+        wbuf, ws = window(4)                       # the 16-byte work-counter workspace, itself behind guard bands
+        assert L.rag_cost_volume_fwd_v(x.data_ptr(), y.data_ptr(), out.data_ptr(), b, c, df, hf, wf, ws.data_ptr(), v, st()) == 0
+        torch.cuda.synchronize()
+        assert intact(wbuf, 4), f"cv_fwd variant {v} wrote outside its workspace"
         torch.cuda.synchronize()
         assert intact(buf, n), f"cv_fwd variant {v} wrote out of bounds"
         assert not (out == CANARY).any(), f"cv_fwd variant {v} left output elements unwritten"
     gc = randn((b, 2 * c, df, hf, wf), g).cuda()
     m = b * c * hf * wf
-    for v in (0, 1, 2, 3):
+    for v in (0, 1):
         bx, gx = window(m)
         by, gy = window(m)
         assert L.rag_cost_volume_bwd_v(gc.data_ptr(), gx.data_ptr(), gy.data_ptr(), b, c, df, hf, wf, v, st()) == 0
@@ -64,7 +67,7 @@ def test_head_guards(L, shape):
     cl = randn((b, 1, dl, hl, wl), g).cuda()
     npx = b * 9 * hl * wl
     x3 = md == 3 * dl
-    fv = [0] + ([1, 2, 3] if x3 else []) + ([4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16] if x3 and wl % 4 == 0 else [])
+    fv = [0] + ([1] if x3 else []) + ([2, 3] if x3 and wl % 4 == 0 else [])
     for v in fv:
         bd, disp = window(npx)
         bs, stats = window(2 * npx)
@@ -74,13 +77,13 @@ def test_head_guards(L, shape):
         assert not (disp == CANARY).any() and not (stats == CANARY).any(), f"head_fwd variant {v} left outputs unwritten"
     gd = randn((b, 3 * hl, 3 * wl), g).cuda()
     nv = b * dl * hl * wl
-    for v in [0] + ([1, 2, 3, 4] if x3 else []):
+    for v in [0] + ([1, 2] if x3 else []):
         bg, gcl = window(nv)
         bsc, scr = window(nv)
         assert L.rag_disp_head_bwd_v(cl.data_ptr(), gd.data_ptr(), disp.data_ptr(), stats.data_ptr(), gcl.data_ptr(), scr.data_ptr(), b, dl, hl, wl, md, v, st()) == 0
         torch.cuda.synchronize()
         assert intact(bg, nv) and intact(bsc, nv), f"head_bwd variant {v}"
-        if v in (2, 3):
+        if v == 2:
             assert not (scr == CANARY).any(), f"head_bwd variant {v} left scratch elements unwritten"
         else:
             assert (scr == CANARY).all(), f"head_bwd variant {v} must not touch the scratch buffer"
@@ -99,7 +102,12 @@ def test_fused_stem_guards(L):
         n = b * o * df * hf * wf
         for v in (0,) + ((1,) if (c == 12 and df >= 3) else ()) + ((2,) if (c == 12 and df >= 3 and wf % 4 == 0) else ()):
             buf, out = window(n)
-            assert L.rag_cv_stem_fwd_v(x.data_ptr(), y.data_ptr(), w.data_ptr(), None, None, 0, out.data_ptr(), b, c, o, df, hf, wf, v, st()) == 0
+            nws = int(L.rag_cv_stem_workspace_bytes(c, o)) // 4
+            wbuf, ws = window(max(nws, 4))
+            assert L.rag_cv_stem_fwd_v(x.data_ptr(), y.data_ptr(), w.data_ptr(), None, None, 0, out.data_ptr(), b, c, o, df, hf, wf,
+                                       ws.data_ptr() if nws else None, v, st()) == 0
+            torch.cuda.synchronize()
+            assert intact(wbuf, max(nws, 4)), f"cv_stem variant {v} wrote outside its workspace"
             torch.cuda.synchronize()
             assert intact(buf, n), f"cv_stem variant {v} wrote out of bounds"
             assert not (out == CANARY).any(), f"cv_stem variant {v} left outputs unwritten"

@@ -1,0 +1,291 @@
+"""The drop-in proven on the REAL reference network, on the GPU.
+
+``baseline/_ref/src`` is the unmodified reference installed by ``tools/install_ref.sh`` (git-ignored, travels to
+the GPU box).  These tests build the reference's own ``Network(genotype, device)`` and ``BasicNetwork`` on CUDA and
+compare the UNPATCHED reference forward/backward with the ``rag_b200.network.install()``-patched one on the same
+weights and inputs:
+
+* ``Network.forward``          rag_model.py:369-387      * ``Network.search_forward``  rag_model.py:688-706
+* ``BasicNetwork.forward``     mdenas_basicmodel.py:76-97
+* the growth loop around them: ``expand`` :391-522, ``select`` :709-845, ``deepcopy`` (approaches/rag.py:225) and the
+  ``state_dict`` snapshot / reload (utils.py:64-70) with the patch installed
+* ``install(fuse_stem=True)``: every ``ConvBR_3d.forward`` of the real model rebound; fused in ``eval()``,
+  materialised volume (the reference's own layers) whenever a gradient is wanted.
+
+Tolerances: disparity 1e-4 px (north_star) with the Matching Net's last layer rescaled so the matching cost has
+sigma = 1 (a random-init network emits sigma ~ 3 in train() and ~ 60-8000 in eval(): near-one-hot softmax where the
+reference's own fp32 result is not defined to 1e-4); parameter gradients 1e-4 relative in
+max-norm per tensor -- the only differing operator is the head (1e-5 vs fp64) but the reference
+side accumulates its trilinear backward with atomics in arrival order, so its own run-to-run noise is measured and
+reported next to the difference.
+"""
+import os
+import sys
+from copy import deepcopy
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refimport as R  # noqa: E402
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "src", "models")),
+                                 reason="baseline/_ref absent: run tools/install_ref.sh in the build container")]
+
+H, W = 96, 192          # image size: multiples of 6 with H/3, W/3 even down to /4 (the Matching Net's level 2)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    assert torch.cuda.is_available()
+    R.verify_manifest()                     # the travelled copy is byte-identical to what was installed
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False  # both sides run the same cuDNN layers; keep them in fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield R.import_reference()
+    torch.backends.cudnn.allow_tf32 = old_tf32
+    from rag_b200 import network as N
+
+    N.uninstall()
+
+
+def _inputs(b, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(b, 3, H, W, generator=g).cuda(), torch.randn(b, 3, H, W, generator=g).cuda(),
+            torch.randn(b, H, W, generator=g).cuda())
+
+
+def _calibrate(net, call, layers):
+    """Scale the last Matching-Net layer so the matching cost has sigma = 1 (controlled-sigma parity)."""
+    seen = {}
+    hooks = [l.register_forward_hook(lambda m, i, o: seen.__setitem__("c", o.detach())) for l in layers]
+    with torch.no_grad():
+        call()
+    for h in hooks:
+        h.remove()
+    s = seen["c"].std().item()
+    with torch.no_grad():
+        for l in layers:
+            l.conv.weight.mul_(1.0 / s)
+    return s
+
+
+def _grads(net):
+    return {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
+
+
+def _compare_grads(got, want, noise=None, tol=1e-4):
+    assert set(got) == set(want) and len(got) > 20
+    worst = 0.0
+    for n in want:
+        den = want[n].abs().max().item()
+        if den == 0.0:
+            assert got[n].abs().max().item() == 0.0, n
+            continue
+        rel = (got[n] - want[n]).abs().max().item() / den
+        allow = tol + (3 * noise.get(n, 0.0) if noise else 0.0)
+        assert rel <= allow, f"{n}: rel max-norm {rel:.3e} > {allow:.3e}"
+        worst = max(worst, rel)
+    return worst
+
+
+def _fwd_bwd(net, call, w):
+    net.zero_grad(set_to_none=True)
+    out = call()
+    (out * w).sum().backward()
+    return out.detach(), _grads(net)
+
+
+def test_network_forward_backward_patched_vs_unpatched(ref):
+    from rag_b200 import network as N
+    from rag_b200.modules import Disp
+
+    N.uninstall()
+    torch.manual_seed(0)
+    net = ref.rag_model.Network(R.make_genotype(ref, 0), "cuda").cuda().train()
+    assert type(net.disp).__module__ == "models.rag_model"
+    left, right, w = _inputs(2, 1)
+    call = lambda: net.forward(left, right, 0, net.arch_init)  # noqa: E731
+    _calibrate(net, call, [net.last_3_3d[0]])
+    bn_state = deepcopy(net.state_dict())                    # train() forwards update BN running stats: reset per run
+
+    def run():
+        net.load_state_dict(bn_state)
+        return _fwd_bwd(net, call, w)
+
+    ref_out, ref_g = run()
+    ref_out2, ref_g2 = run()                                 # the reference's own run-to-run noise (atomics)
+    noise = {n: (ref_g[n] - ref_g2[n]).abs().max().item() / max(ref_g[n].abs().max().item(), 1e-30) for n in ref_g}
+    n0 = __import__("rag_b200._cabi", fromlist=["x"]).launch_count()
+    done = N.install(ref.rag_model, ref.mdenas_basicmodel)
+    assert "Network.forward" in done["rag_model"] and ref.rag_model.Network.forward is N.network_forward
+    got_out, got_g = run()                                   # an EXISTING instance (reference Disp inside) is patched
+    assert __import__("rag_b200._cabi", fromlist=["x"]).launch_count() - n0 >= 4, "the CUDA kernels did not run"
+    err = (got_out - ref_out).abs().max().item()
+    assert err <= 1e-4, f"disparity differs from the unpatched reference by {err:.3e} px"
+    worst = _compare_grads(got_g, ref_g, noise)
+    # a network built AFTER install() carries rag_b200.Disp and loads the old weights (empty head state_dict)
+    net2 = ref.rag_model.Network(R.make_genotype(ref, 0), "cuda").cuda().train()
+    assert isinstance(net2.disp, Disp)
+    net2.load_state_dict(bn_state)
+    out2 = net2.forward(left, right, 0, net2.arch_init)
+    assert torch.equal(out2.detach(), got_out)
+    print(f"\nNetwork.forward: |disp - ref| max {err:.2e} px; worst grad rel {worst:.2e}; "
+          f"reference run-to-run grad noise max {max(noise.values()):.2e}")
+    N.uninstall()
+    assert ref.rag_model.Network.forward is not N.network_forward
+
+
+def test_growth_loop_with_patch_installed(ref):
+    """expand -> search_forward (fwd+bwd) -> select -> forward on the grown path -> deepcopy -> state_dict round trip."""
+    from rag_b200 import network as N
+
+    N.uninstall()
+    torch.manual_seed(1)
+    geno = R.make_genotype(ref, 1)
+    net = ref.rag_model.Network(geno, "cuda").cuda().train()
+    left, right, w = _inputs(1, 2)
+    net.expand(1, R.make_genotype(ref, 2), device="cuda")            # rag_model.py:391-522
+    assert len(net.p) == 18
+    gsel = torch.Generator().manual_seed(5)
+    ops = [int(torch.multinomial(p, 1, generator=gsel)) for p in net.p]   # approaches/rag.py:275
+    ops[8] = 1                                                        # the NEW stem3d0 unit consumes the volume
+    call = lambda: net.search_forward(left, right, 1, ops)            # noqa: E731
+    _calibrate(net, call, [net.last_3_3d[1]])
+    state = deepcopy(net.state_dict())
+
+    def run():
+        net.load_state_dict(state)
+        return _fwd_bwd(net, call, w)
+
+    ref_out, ref_g = run()
+    N.install(ref.rag_model, ref.mdenas_basicmodel)
+    got_out, got_g = run()
+    err = (got_out - ref_out).abs().max().item()
+    assert err <= 1e-4, f"search_forward differs by {err:.3e} px"
+    _compare_grads(got_g, ref_g, tol=2e-4)
+    # select() with the patch installed, then the grown path through Network.forward
+    net.load_state_dict(state)
+    for i in range(len(net.p)):
+        net.p[i] = torch.tensor([0.1, 0.9])                           # choose every new unit
+    arch = net.select(1)                                              # rag_model.py:709-845
+    assert arch["stem_3d0"] == [1] and net.length["stem_3d0"] == 2
+    with torch.no_grad():
+        d_new = net.forward(left, right, 1, arch)
+        d_old = net.forward(left, right, 0, net.arch_init)
+    assert d_new.shape == (1, H, W) and not torch.equal(d_new, d_old)
+    N.uninstall()
+    with torch.no_grad():
+        d_new_ref = net.forward(left, right, 1, arch)
+    # eval-free comparison: train() BatchNorm uses batch statistics, so both calls see the same numbers
+    assert (d_new - d_new_ref).abs().max().item() <= 1e-4
+    N.install(ref.rag_model, ref.mdenas_basicmodel)
+    clone = deepcopy(net)                                             # approaches/rag.py:225
+    snap = ref.utils.get_model(net)                                   # utils.py:64-66
+    assert not any(k.startswith("disp.") for k in snap)
+    ref.utils.set_model_(clone, snap)                                 # utils.py:69-70
+    with torch.no_grad():
+        net.eval(), clone.eval()
+        assert torch.equal(clone.forward(left, right, 1, arch), net.forward(left, right, 1, arch))
+    N.uninstall()
+
+
+def test_basic_network_patched_vs_unpatched(ref):
+    from rag_b200 import network as N
+
+    N.uninstall()
+    torch.manual_seed(2)
+    net = ref.mdenas_basicmodel.BasicNetwork(device="cuda").cuda().train()
+    gsel = torch.Generator().manual_seed(3)
+    fea_ops = torch.randint(0, net.num_ops, (net.num_edges,), generator=gsel)   # mdenas_search.py:101-104
+    mat_ops = torch.randint(0, net.num_ops, (net.num_edges,), generator=gsel)
+    left, right, w = _inputs(1, 4)
+    call = lambda: net.forward(left, right, fea_ops, mat_ops)  # noqa: E731
+    last = [m for n, m in net.matching.named_modules() if n.endswith("last_3")]
+    assert len(last) == 1
+    _calibrate(net, call, last)
+    state = deepcopy(net.state_dict())
+
+    def run():
+        net.load_state_dict(state)
+        return _fwd_bwd(net, call, w)
+
+    ref_out, ref_g = run()
+    N.install(ref.rag_model, ref.mdenas_basicmodel)
+    got_out, got_g = run()
+    err = (got_out - ref_out).abs().max().item()
+    assert err <= 1e-4, f"BasicNetwork.forward differs by {err:.3e} px"
+    _compare_grads(got_g, ref_g, tol=2e-4)
+    N.uninstall()
+
+
+def test_fuse_stem_on_the_real_network(ref):
+    """install(fuse_stem=True) rebinds EVERY ConvBR_3d.forward of the real model (stems, 8 cells x pre/pre-pre-process +
+    ops, last_3/6/12): eval() takes the fused stem and the hand-written last_3_3d, a wanted gradient falls back."""
+    from rag_b200 import _cabi
+    from rag_b200 import network as N
+
+    N.uninstall()
+    torch.manual_seed(3)
+    net = ref.rag_model.Network(R.make_genotype(ref, 3), "cuda").cuda().train()
+    left, right, w = _inputs(2, 6)
+    call = lambda: net.forward(left, right, 0, net.arch_init)  # noqa: E731
+    # give BatchNorm sensible running statistics (a fresh net's mean 0 / var 1 explode through 30 layers in eval())
+    for m in net.modules():
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.momentum = None                                 # cumulative average
+    with torch.no_grad():
+        for _ in range(2):
+            call()
+    net.eval()
+    s = _calibrate(net, call, [net.last_3_3d[0]])
+    assert s < 1e3
+    with torch.no_grad():
+        ref_out = call()
+    # ---- materialised (plain install) vs fused (fuse_stem=True) in eval() ----
+    N.install(ref.rag_model, ref.mdenas_basicmodel)
+    with torch.no_grad():
+        plain = call()
+    assert (plain - ref_out).abs().max().item() <= 1e-4
+    N.install(ref.rag_model, ref.mdenas_basicmodel, ref.operations_3d, fuse_stem=True)
+    assert ref.operations_3d.ConvBR_3d.forward.__module__ == "rag_b200.fused_stem"
+    n0 = _cabi.launch_count()
+    with torch.no_grad():
+        fused = call()
+    launches = _cabi.launch_count() - n0
+    assert launches == 4, f"expected weight regroup + fused stem + last_3_3d + head = 4 launches of ours, saw {launches}"
+    # the fused stem / last conv accumulate in another order than cuDNN (1e-6 relative per layer); through ~30 layers
+    # and a sigma = 1 softmax that stays well inside 1e-3 px
+    ferr = (fused - ref_out).abs().max().item()
+    assert ferr <= 1e-3, f"fused eval path differs by {ferr:.3e} px"
+    # per-instance opt-out
+    net.rag_b200_fuse_stem = False
+    n0 = _cabi.launch_count()
+    with torch.no_grad():
+        out = call()
+    assert _cabi.launch_count() - n0 == 3 and (out - ref_out).abs().max().item() <= 1e-4   # cost volume + last_3_3d + head
+    del net.rag_b200_fuse_stem
+    # ---- training: a wanted gradient must fall back to the materialised volume + the reference's own layers ----
+    net.train()
+    state = deepcopy(net.state_dict())
+    N.uninstall()
+    net.load_state_dict(state)
+    ref_o, ref_g = _fwd_bwd(net, call, w)
+    N.install(ref.rag_model, ref.mdenas_basicmodel, ref.operations_3d, fuse_stem=True)
+    net.load_state_dict(state)
+    got_o, got_g = _fwd_bwd(net, call, w)
+    assert (got_o - ref_o).abs().max().item() <= 1e-4
+    _compare_grads(got_g, ref_g, tol=2e-4)
+    # only the BatchNorm bias of stem3d0 trainable: its gradient must not be dropped
+    for p in net.parameters():
+        p.requires_grad_(False)
+    net.stem3d0[0].bn.bias.requires_grad_(True)
+    net.load_state_dict(state)
+    net.zero_grad(set_to_none=True)
+    (call() * w).sum().backward()
+    gb = net.stem3d0[0].bn.bias.grad
+    assert gb is not None and (gb - ref_g["stem3d0.0.bn.bias"]).abs().max().item() <= 2e-4 * ref_g["stem3d0.0.bn.bias"].abs().max().item()
+    N.uninstall()
+    assert ref.operations_3d.ConvBR_3d.forward.__module__ != "rag_b200.fused_stem"
