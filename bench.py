@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Contract benchmark of the RAG stereo hot path (cost volume + disparity regression) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer|train] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload infer|train|router|sweep192|sweep288] [--impl reference]
 
 A step = one pass of the hot path over one batch of synthetic stereo pairs.  Default workload
 (BASELINE.json configs[1]): inference batch 8 per GPU at DrivingStereo half-res 400x880, which the
@@ -9,17 +9,27 @@ reference pads to 480x960 at eval (dataloaders/stereo_dataset.py:95-96; its Feat
 400x880) -> features [8,12,160,320], volume [8,24,64,160,320], head input [8,1,64,160,320],
 maxdisp 192.  `--workload train` is configs[2]: fwd+bwd, batch 4 per GPU at 288x576.
 
-Prints ONE JSON line (rank 0).  Inference workloads are timed on the two-stream schedule of
-rag_b200.pipeline.OverlappedPath (the cost volume of a batch shares the SMs with the disparity head of
-another): `value` = pairs/s of K such steps with inputs resident in HBM (CUDA events,
-max over ranks); `path.serial` = the same K steps with the kernels back to back on one stream, which is also
-where the per-kernel durations and `roofline` (the dominant kernel, cost-volume forward, against the measured
-HBM peak) come from.  The training workload (fwd+bwd) is timed serially.  `e2e` = the same metric through
-rag_b200.pipeline.HostPipeline with pinned HOST buffers (H2D of the inputs and D2H of the disparity inside the
-timed region); `cpu_baseline` = the oracle port of the reference timed on this box's host cores; `next_rows`
-= the SURVEY.md section 8f rows (fused stem, last_3_3d conv) beside the headline.  `--impl reference` times the
-reference's CPU path (oracle port: the reference is pure PyTorch, so the port IS its op sequence) on the
-same config.
+Prints ONE JSON line (rank 0).  Top level:
+  value / ms_per_step   K steps of the workload on the two-stream schedule (`schedule: "overlapped"`,
+                        rag_b200.pipeline.OverlappedPath / OverlappedTrainPath: the HBM-bound volume kernels share the SMs
+                        with the FP32-bound head kernels), inputs resident in HBM, CUDA events, max over ranks;
+  value_serial          the same K steps with the kernels back to back on ONE stream -- what a single caller of
+                        CostVolume / Disp gets; the per-kernel durations and `roofline` come from this pass;
+  roofline              the dominant kernel (cost-volume forward) against the measured HBM peak;
+  path                  whole-path algorithmic bytes / time for both schedules;
+  train                 (default workload only) the same measurements for BASELINE configs[2] (fwd+bwd B=4 288x576), so the
+                        driver-run line carries the training step too;
+  parity                one pair of this workload checked in-run against the reference (bit-exactness of the volume and its
+                        gradient, max |disp - ref| and the fraction of pixels above 1e-4 px, the reference's own deviation
+                        from the fp64 evaluation, gradient max-norm errors);
+  e2e                   the same metric through rag_b200.pipeline.HostPipeline (HostTrainPipeline for `train`): pinned HOST
+                        buffers, ONE host->device and ONE device->host copy per step inside the timed region, and the box's
+                        host->device ceiling measured in the same run (`frac_of_h2d_ceiling`);
+  cpu_baseline          the UNMODIFIED reference (baseline/_ref, tools/install_ref.sh) timed on this box's host cores
+                        (kind "reference"; "port" = the oracle restatement when baseline/_ref is absent);
+  torch_cuda_reference  the same unmodified reference modules run by PyTorch eager on this GPU (the honest GPU bar);
+  next_rows             the SURVEY.md section 8f rows (fused stem, last_3_3d conv, ...) beside the headline.
+`--impl reference` times the reference's own CPU implementation on the same config (rank 0 only).
 """
 from __future__ import annotations
 
@@ -44,6 +54,18 @@ WORKLOADS = {
     "sweep192": (4, 12, 128, 416, 64, 192, False, "inference batch 4/GPU at 384x1248, maxdisp 192"),
     "sweep288": (4, 12, 128, 416, 96, 288, False, "inference batch 4/GPU at 384x1248, maxdisp 288"),
 }
+
+
+def config_dict(workload):
+    """Identical in both arms (the driver compares the two lines' `config`)."""
+    b, c, hf, wf, df, md, bwd, desc = WORKLOADS[workload]
+    cvb, hfb, hbb = alg_bytes(c, hf, wf, df)
+    step_bytes = (cvb + hfb + ((cvb + hbb) if bwd else 0)) * b
+    return {"workload": workload, "desc": desc, "pairs_per_gpu": b, "features": [b, c, hf, wf],
+            "volume": [b, 2 * c, df, hf, wf], "head_in": [b, 1, df, hf, wf], "maxdisp": md,
+            "direction": "fwd+bwd" if bwd else "fwd",
+            "l2": "no explicit flush: every step streams %.2f GB (>> 126 MB L2) through HBM" % (step_bytes / 1e9),
+            "sharding": "stereo pairs across ranks, no data-path collective"}
 
 
 def alg_bytes(c, hf, wf, df):
@@ -72,144 +94,165 @@ def ncu_traffic(kernel):
 
 
 # --------------------------------------------------------------------------------------------
-# CPU reference arm (oracle port)
+# the reference: the unmodified modules from baseline/_ref when installed, else the oracle port
 # --------------------------------------------------------------------------------------------
-def cpu_reference(workload, budget_s=12.0, min_reps=2):
+class Reference:
+    """Callable view of the reference's hot path.  kind == "reference": rag_model.Network.forward's own lines 375-383
+    (driven through stub feature/matching callables, as tests/golden/make_golden.py does) and rag_model.Disp, imported
+    unmodified from baseline/_ref; kind == "port": oracle/rag_oracle.py (the same op sequence restated)."""
+
+    def __init__(self, cpu: bool):
+        import types
+
+        from oracle import refimport as R
+
+        self.kind = "port"
+        self.ref = None
+        self.cpu = cpu
+        self._R = R
+        if R.available():
+            try:
+                self.ref = R.import_reference(cpu_patch=cpu)
+                self.kind = "reference"
+                self._types = types
+            except Exception as e:  # noqa: BLE001
+                print(f"bench.py: reference import failed ({e}); using the oracle port", file=sys.stderr)
+        if self.ref is None:
+            from oracle import rag_oracle as O
+
+            self.O = O
+
+    def cost_volume(self, x, y, md):
+        if self.ref is None:
+            return self.O.cost_volume_ref(x, y, md)
+        holder = {}
+        stub = self._types.SimpleNamespace(maxdisp=md)
+        feats = iter([x, y])
+        stub.feature = lambda img, task_arch, path: next(feats)
+        stub.matching = lambda cost, task_arch, path: holder.setdefault("cost", cost)
+        stub.disp = lambda c: c
+        self.ref.rag_model.Network.forward(stub, None, None, 0)
+        return holder["cost"]
+
+    def head(self, cl, md):
+        if self.ref is None:
+            return self.O.disp_head_ref(cl, md)
+        key = ("disp", md)
+        if not hasattr(self, "_disp") or self._disp[0] != key:
+            self._disp = (key, self.ref.rag_model.Disp(md))
+        return self._disp[1](cl)
+
+    def step(self, x, y, cl, md, bwd, gcost=None, gdisp=None):
+        if self.cpu and self.ref is not None:
+            with self._R.on_cpu():          # rag_model.py:26 names "the current CUDA device"; CPU tensors need 'cpu'
+                return self._step(x, y, cl, md, bwd, gcost, gdisp)
+        return self._step(x, y, cl, md, bwd, gcost, gdisp)
+
+    def _step(self, x, y, cl, md, bwd, gcost=None, gdisp=None):
+        import torch
+
+        if not bwd:
+            with torch.no_grad():
+                return self.cost_volume(x, y, md), self.head(cl, md)
+        xr, yr, cr = x.clone().requires_grad_(True), y.clone().requires_grad_(True), cl.clone().requires_grad_(True)
+        cost = self.cost_volume(xr, yr, md)
+        cost.backward(gcost if gcost is not None else torch.ones_like(cost))
+        d = self.head(cr, md)
+        d.backward(gdisp if gdisp is not None else torch.ones_like(d))
+        return cost.detach(), d.detach(), cr.grad, xr.grad, yr.grad
+
+
+def seeded_pair(workload, device=None):
     import torch
 
-    from oracle import rag_oracle as O
-
     b, c, hf, wf, df, md, bwd, _ = WORKLOADS[workload]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(1234)
     x = torch.randn(1, c, hf, wf, generator=g)
     y = torch.randn(1, c, hf, wf, generator=g)
     cl = torch.randn(1, 1, df, hf, wf, generator=g)
+    gcost = torch.randn(1, 2 * c, df, hf, wf, generator=g)
+    gdisp = torch.randn(1, 3 * hf, 3 * wf, generator=g) * (torch.rand(1, 3 * hf, 3 * wf, generator=g) < 0.3)
+    ts = (x, y, cl, gcost, gdisp)
+    return tuple(t.to(device) for t in ts) if device is not None else ts
 
-    def step():
-        if not bwd:
-            with torch.no_grad():
-                O.cost_volume_ref(x, y, md)
-                O.disp_head_ref(cl, md)
-        else:
-            xr, yr, cr = x.clone().requires_grad_(True), y.clone().requires_grad_(True), cl.clone().requires_grad_(True)
-            cost = O.cost_volume_ref(xr, yr, md)
-            cost.backward(torch.ones_like(cost))
-            d = O.disp_head_ref(cr, md)
-            d.backward(torch.ones_like(d))
 
-    step()  # warm-up
+def cpu_reference(workload, warmup=1, steps=3, budget_s=25.0):
+    """Time the reference's CPU path: `steps` single-pair steps after `warmup`, stopping early once `budget_s` is spent
+    (never fewer than 2 timed steps).  Returns (cpu_baseline dict, list of step times)."""
+    import torch
+
+    b, c, hf, wf, df, md, bwd, _ = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    refm = Reference(cpu=True)
+    x, y, cl, gcost, gdisp = seeded_pair(workload)
+    t_start = time.perf_counter()
+    for _ in range(max(1, warmup)):
+        refm.step(x, y, cl, md, bwd, gcost, gdisp)
+        if time.perf_counter() - t_start > budget_s / 3:
+            break
     times = []
     t_end = time.perf_counter() + budget_s
-    while len(times) < min_reps or (time.perf_counter() < t_end and len(times) < 50):
+    while len(times) < steps and (len(times) < 2 or time.perf_counter() < t_end):
         t0 = time.perf_counter()
-        step()
+        refm.step(x, y, cl, md, bwd, gcost, gdisp)
         times.append(time.perf_counter() - t0)
-    best = min(times)
+    mean = sum(times) / len(times)
     return {
-        "value": 1.0 / best, "unit": "pairs/s", "cores": cores, "kind": "port",
-        "sample": f"1 pair of the {workload} workload ({3*hf}x{3*wf}, maxdisp {md}, {'fwd+bwd' if bwd else 'fwd'}), best of {len(times)} after 1 warm-up, torch CPU {torch.get_num_threads()} threads; "
-                  "pairs are independent so pairs/s does not depend on batch",
+        "value": 1.0 / mean, "unit": "pairs/s", "cores": cores, "kind": refm.kind, "best_pairs_per_s": 1.0 / min(times), "steps_timed": len(times),
+        "sample": f"1 pair of the {workload} workload per step ({3*hf}x{3*wf}, maxdisp {md}, {'fwd+bwd' if bwd else 'fwd'}), mean of {len(times)} steps after warm-up, "
+                  f"torch {torch.__version__} CPU, {torch.get_num_threads()} threads; pairs are independent, so pairs/s does not depend on the batch "
+                  "(the reference head needs ~1.8 GB of temporaries per pair at 480x960)",
+        "what": ("unmodified reference: models.rag_model.Network.forward lines 375-383 + models.rag_model.Disp from baseline/_ref" if refm.kind == "reference"
+                 else "oracle port of rag_model.py:375-383,18-44 (baseline/_ref not installed)"),
     }, times
 
 
-def torch_cuda_reference(workload, dev, reps=5):
-    """The reference's own op sequence (oracle port) run by PyTorch eager ON THE SAME GPU: the honest GPU
-    baseline.  One pair per call (its temporaries are ~1.8 GB/pair at 480x960)."""
+def config1_full_network_cpu(budget_s=20.0):
+    """BASELINE.json configs[0] / BASELINE.md section 4.5: the reference's full Network.forward (Feature Net + cost volume +
+    Matching Net + head), synthetic 1x3x288x576, maxdisp 192, on the host cores.  Needs baseline/_ref."""
     import torch
 
-    from oracle import rag_oracle as O
+    from oracle import refimport as R
 
-    b, c, hf, wf, df, md, bwd, _ = WORKLOADS[workload]
-    g = torch.Generator().manual_seed(1234)
-    x = torch.randn(1, c, hf, wf, generator=g).to(dev)
-    y = torch.randn(1, c, hf, wf, generator=g).to(dev)
-    cl = torch.randn(1, 1, df, hf, wf, generator=g).to(dev)
+    if not R.available():
+        return None
+    try:
+        ref = R.import_reference(cpu_patch=True)
+        torch.manual_seed(0)
+        net = ref.rag_model.Network(R.make_genotype(ref, 0), "cpu").eval()
+        g = torch.Generator().manual_seed(1234)
+        left, right = torch.randn(1, 3, 288, 576, generator=g), torch.randn(1, 3, 288, 576, generator=g)
+        parts = {}
 
-    def step():
-        if not bwd:
-            with torch.no_grad():
-                O.cost_volume_ref(x, y, md)
-                O.disp_head_ref(cl, md)
-        else:
-            xr, yr, cr = x.clone().requires_grad_(True), y.clone().requires_grad_(True), cl.clone().requires_grad_(True)
-            cost = O.cost_volume_ref(xr, yr, md)
-            cost.backward(torch.ones_like(cost))
-            d = O.disp_head_ref(cr, md)
-            d.backward(torch.ones_like(d))
+        def timed(name, fn):
+            def wrapped(*a, **k):
+                t0 = time.perf_counter()
+                out = fn(*a, **k)
+                parts[name] = parts.get(name, 0.0) + time.perf_counter() - t0
+                return out
+            return wrapped
 
-    step()
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / reps
-    torch.cuda.empty_cache()
-    return {"value": 1e3 / ms, "unit": "pairs/s", "ms_per_pair": ms,
-            "what": "reference op sequence (rag_model.py:375-383,18-44) through PyTorch eager CUDA kernels on this GPU, 1 pair per call"}
-
-
-def fused_stem_row(x, y, df, md, sub):
-    """SURVEY.md section 8f rank 1 (reported beside the headline, not part of `value`): cost volume + first
-    Matching-Net layer (ConvBR_3d 2C->C, 3x3x3, eval-mode BN, ReLU).  Fused kernel (volume never
-    materialised, fp32) vs the reference composition on the materialised volume through cuDNN (TF32 default)."""
-    import torch
-
-    from rag_b200 import functional as F_
-    from rag_b200.fused_stem import cv_stem_forward
-
-    dev = x.device
-    xs, ys = x[:sub], y[:sub]
-    c = x.shape[1]
-    g = torch.Generator(device=dev).manual_seed(11)
-    conv = torch.nn.Conv3d(2 * c, c, 3, padding=1, bias=False).to(dev)
-    bn = torch.nn.BatchNorm3d(c).to(dev).eval()
-    with torch.no_grad():
-        bn.running_mean.normal_(0, 0.3, generator=g)
-        bn.running_var.uniform_(0.5, 2.0, generator=g)
-        scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
-        shift = bn.bias - bn.running_mean * scale
-
-        def t(fn, n):
-            fn()
-            torch.cuda.synchronize(dev)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(n):
-                fn()
-            e1.record()
-            torch.cuda.synchronize(dev)
-            return e0.elapsed_time(e1) / n
-
-        fused = t(lambda: cv_stem_forward(xs, ys, conv.weight, scale, shift, True, md), 10)
-        ref = t(lambda: torch.relu_(bn(conv(F_.cost_volume_forward(xs, ys, df)))), 3)
-        a = cv_stem_forward(xs[:1], ys[:1], conv.weight, scale, shift, True, md)
-        old = torch.backends.cudnn.allow_tf32
-        torch.backends.cudnn.allow_tf32 = False
-        b_ = torch.relu_(bn(conv(F_.cost_volume_forward(xs[:1], ys[:1], df))))
-        torch.backends.cudnn.allow_tf32 = old
-        err = ((a - b_).abs().max() / b_.abs().max()).item()
-        # rank 2: last_3_3d (Conv3d C -> 1, 3x3x3), the producer of the head's input
-        from rag_b200.last_conv import conv3d_c1_forward
-        feat = torch.randn(sub, c, df, x.shape[2], x.shape[3], device=dev, generator=g)
-        last = torch.nn.Conv3d(c, 1, 3, padding=1, bias=False).to(dev)
-        lc = t(lambda: conv3d_c1_forward(feat, last.weight), 10)
-        lc_ref = t(lambda: last(feat), 3)
-        torch.backends.cudnn.allow_tf32 = False
-        lc_err = ((conv3d_c1_forward(feat[:1], last.weight) - last(feat[:1])).abs().max() / last(feat[:1]).abs().max()).item()
-        torch.backends.cudnn.allow_tf32 = old
-        del feat
-    torch.cuda.empty_cache()
-    return {"stem3d0": {"what": "cost volume + stem3d0 (Conv3d 24->12 3x3x3 + BN(eval) + ReLU), %d pairs" % sub,
-                        "fused_ms": round(fused, 4), "cost_volume_plus_cudnn_tf32_ms": round(ref, 4), "speedup": round(ref / fused, 1),
-                        "max_rel_err_vs_fp32_cudnn": err},
-            "last_3_3d": {"what": "last_3_3d (Conv3d %d->1 3x3x3, fp32 direct convolution), %d pairs" % (c, sub),
-                          "ms": round(lc, 4), "cudnn_tf32_ms": round(lc_ref, 4), "speedup": round(lc_ref / lc, 1),
-                          "max_rel_err_vs_fp32_cudnn": lc_err}}
+        net.feature = timed("feature_x2", net.feature)
+        net.matching = timed("matching", net.matching)
+        net.disp.forward = timed("head", net.disp.forward)
+        times = []
+        with torch.no_grad(), R.on_cpu():
+            net(left, right, 0, net.arch_init)
+            parts.clear()
+            t_end = time.perf_counter() + budget_s
+            while len(times) < 3 and (not times or time.perf_counter() < t_end):
+                t0 = time.perf_counter()
+                net(left, right, 0, net.arch_init)
+                times.append(time.perf_counter() - t0)
+        n = len(times)
+        total = sum(times) / n
+        br = {k: round(v / n, 4) for k, v in parts.items()}
+        br["cost_volume"] = round(total - sum(br.values()), 4)
+        return {"what": "unmodified reference Network.forward (rag_model.py:369-387), random genotype, 1x3x288x576, maxdisp 192, CPU",
+                "s_per_pair": round(total, 4), "pairs_per_s": round(1.0 / total, 4), "runs": n, "cores": os.cpu_count(), "breakdown_s": br}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
 
 
 def run_reference(args):
@@ -217,15 +260,16 @@ def run_reference(args):
     if rank != 0:
         return
     b, c, hf, wf, df, md, bwd, desc = WORKLOADS[args.workload]
-    # each "step" = one pair on the host cores; run warmup+steps of them, bounded
-    base, _ = cpu_reference(args.workload, budget_s=0.0, min_reps=max(1, min(args.steps, 8)))
+    base, times = cpu_reference(args.workload, warmup=args.warmup, steps=args.steps, budget_s=90.0)
     v = base["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
+        "steps": len(times), "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": desc, "note": "reference CPU path = oracle port of rag_model.py:375-383,18-44 (pure PyTorch ops), 1 pair per step on all host cores"},
+        "config": config_dict(args.workload),
+        "note": "each step = one pair of the workload on all host cores (a bounded sample; the batch is a loop over independent pairs); value = mean over the timed steps",
         "cpu_baseline": base,
+        "config1_full_network_cpu": config1_full_network_cpu() if not args.no_cpu_baseline else None,
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -289,20 +333,154 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+def torch_cuda_reference(workload, dev, reps=5):
+    """The UNMODIFIED reference modules (baseline/_ref; oracle port if absent) run by PyTorch eager ON THE SAME GPU: the
+    honest GPU baseline.  One pair per call (its temporaries are ~1.8 GB/pair at 480x960)."""
+    import torch
+
+    b, c, hf, wf, df, md, bwd, _ = WORKLOADS[workload]
+    refm = Reference(cpu=False)
+    x, y, cl, gcost, gdisp = seeded_pair(workload, dev)
+    refm.step(x, y, cl, md, bwd, gcost, gdisp)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        refm.step(x, y, cl, md, bwd, gcost, gdisp)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    torch.cuda.empty_cache()
+    return {"value": 1e3 / ms, "unit": "pairs/s", "ms_per_pair": ms, "kind": refm.kind,
+            "what": "reference modules (rag_model.py:375-383,18-44) through PyTorch eager CUDA kernels on this GPU, 1 pair per call"}
+
+
+def parity_record(workload, dev):
+    """One seeded pair of the workload through our kernels and through the reference ON THIS GPU (checker only)."""
+    import torch
+
+    from oracle import rag_oracle as O
+    from rag_b200 import functional as F_
+
+    b, c, hf, wf, df, md, bwd, _ = WORKLOADS[workload]
+    refm = Reference(cpu=False)
+    x, y, cl, gcost, gdisp = seeded_pair(workload, dev)
+    out = {"pair": f"1 seeded pair of the {workload} workload, sigma = 1 matching cost", "reference": refm.kind + " on CUDA (torch %s)" % torch.__version__}
+    cost = F_.cost_volume_forward(x, y, df)
+    disp, stats = F_.disp_head_forward(cl, md, want_stats=True)
+    with torch.no_grad():
+        cost_ref = refm.cost_volume(x, y, md)
+        out["cv_bit_exact"] = bool(torch.equal(cost, cost_ref))
+        del cost_ref
+        disp_ref = refm.head(cl, md)
+    d64, _ = O.disp_head_f64_torch(cl[:, 0], md)
+    err = (disp - disp_ref).abs()
+    ref_dev = (disp_ref.double() - d64).abs()
+    out["disp_max_abs_err"] = float(err.max())
+    out["disp_frac_gt_1e-4"] = float((err > 1e-4).double().mean())
+    out["disp_own_vs_fp64_max"] = float((disp.double() - d64).abs().max())
+    out["ref_vs_fp64_max"] = float(ref_dev.max())
+    out["disp_max_excess_over_ref_noise"] = float((err.double() - ref_dev).max())    # <= 1e-4 is the per-pixel bound the tests assert
+    del d64, err, ref_dev, disp_ref, cost
+    torch.cuda.empty_cache()
+    if bwd:
+        gcl = F_.disp_head_backward(cl, gdisp, disp, stats, md)
+        gx, gy = F_.cost_volume_backward(gcost, c)
+        _, _, gcl_ref, gx_ref, gy_ref = refm.step(x, y, cl, md, True, gcost, gdisp)
+        out["cv_grad_bit_exact"] = bool(torch.equal(gx, gx_ref) and torch.equal(gy, gy_ref))
+        _, g64 = O.disp_head_f64_torch(cl[:, 0], md, gdisp)
+        den = float(g64.abs().max())
+        out["grad_maxnorm_rel"] = float((gcl[:, 0].double() - g64).abs().max()) / den
+        out["grad_maxnorm_rel_vs_ref"] = float((gcl - gcl_ref).abs().max()) / float(gcl_ref.abs().max())
+        out["ref_grad_vs_fp64_maxnorm_rel"] = float((gcl_ref[:, 0].double() - g64).abs().max()) / den
+    torch.cuda.empty_cache()
+    return out
+
+
+def next_rows_record(x, y, df, md, sub):
+    """SURVEY.md section 8f rows reported beside the headline, not part of `value`."""
+    import torch
+
+    from rag_b200 import functional as F_
+    from rag_b200.fused_stem import cv_stem_forward
+
+    dev = x.device
+    xs, ys = x[:sub], y[:sub]
+    c = x.shape[1]
+    g = torch.Generator(device=dev).manual_seed(11)
+    conv = torch.nn.Conv3d(2 * c, c, 3, padding=1, bias=False).to(dev)
+    bn = torch.nn.BatchNorm3d(c).to(dev).eval()
+
+    def t(fn, n):
+        fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    rows = {}
+    with torch.no_grad():
+        bn.running_mean.normal_(0, 0.3, generator=g)
+        bn.running_var.uniform_(0.5, 2.0, generator=g)
+        scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+        shift = bn.bias - bn.running_mean * scale
+        fused = t(lambda: cv_stem_forward(xs, ys, conv.weight, scale, shift, True, md), 10)
+        ref = t(lambda: torch.relu_(bn(conv(F_.cost_volume_forward(xs, ys, df)))), 3)
+        a = cv_stem_forward(xs[:1], ys[:1], conv.weight, scale, shift, True, md)
+        old = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        b_ = torch.relu_(bn(conv(F_.cost_volume_forward(xs[:1], ys[:1], df))))
+        torch.backends.cudnn.allow_tf32 = old
+        err = ((a - b_).abs().max() / b_.abs().max()).item()
+        rows["stem3d0"] = {"what": "cost volume + stem3d0 (Conv3d 24->12 3x3x3 + BN(eval) + ReLU), %d pairs" % sub,
+                           "fused_ms": round(fused, 4), "cost_volume_plus_cudnn_tf32_ms": round(ref, 4), "speedup": round(ref / fused, 1),
+                           "max_rel_err_vs_fp32_cudnn": err}
+        del a, b_
+        # rank 2: last_3_3d (Conv3d C -> 1, 3x3x3), the producer of the head's input
+        from rag_b200.last_conv import conv3d_c1_forward
+        feat = torch.randn(sub, c, df, x.shape[2], x.shape[3], device=dev, generator=g)
+        last = torch.nn.Conv3d(c, 1, 3, padding=1, bias=False).to(dev)
+        lc = t(lambda: conv3d_c1_forward(feat, last.weight), 10)
+        lc_ref = t(lambda: last(feat), 3)
+        torch.backends.cudnn.allow_tf32 = False
+        lc_err = ((conv3d_c1_forward(feat[:1], last.weight) - last(feat[:1])).abs().max() / last(feat[:1]).abs().max()).item()
+        torch.backends.cudnn.allow_tf32 = old
+        rows["last_3_3d"] = {"what": "last_3_3d (Conv3d %d->1 3x3x3, fp32 direct convolution), %d pairs" % (c, sub),
+                             "ms": round(lc, 4), "cudnn_tf32_ms": round(lc_ref, 4), "speedup": round(lc_ref / lc, 1),
+                             "max_rel_err_vs_fp32_cudnn": lc_err}
+        del feat
+    torch.cuda.empty_cache()
+    for name, fn in EXTRA_NEXT_ROWS:
+        try:
+            rows[name] = fn(dev)
+        except Exception as e:  # noqa: BLE001
+            rows[name] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        torch.cuda.empty_cache()
+    return rows
+
+
+EXTRA_NEXT_ROWS = []     # (name, fn(dev) -> dict): rows added as they are built (training-mode stem, upsample_6/12, ...)
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
     from rag_b200 import _cabi
+    from rag_b200 import dist as D
     from rag_b200 import functional as F_
-    from rag_b200.modules import CostVolume, Disp
-    from rag_b200.pipeline import HostPipeline, OverlappedPath
+    from rag_b200.pipeline import HostPipeline, HostTrainPipeline, OverlappedPath, OverlappedTrainPath
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    numa = D.bind_to_gpu_numa(local)        # before any pinned allocation (first-touch placement); a no-op on single-socket hosts
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -314,184 +492,274 @@ def run_gpu(args):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
-    b, c, hf, wf, df, md, bwd, desc = WORKLOADS[args.workload]
-    K, Wm = args.steps, max(args.warmup, 3)
-    # identical bits for CPU reference and GPU: generate on the host with a fixed seed, then copy
-    g = torch.Generator().manual_seed(1234 + rank)
-    x_h = torch.randn(b, c, hf, wf, generator=g).pin_memory()
-    y_h = torch.randn(b, c, hf, wf, generator=g).pin_memory()
-    cl_h = torch.randn(b, 1, df, hf, wf, generator=g).pin_memory()
-    x, y, cl = x_h.to(dev), y_h.to(dev), cl_h.to(dev)
-    cv_mod, head_mod = CostVolume(md), Disp(md)
-    if bwd:
-        gcost = torch.randn(b, 2 * c, df, hf, wf, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
-        gd_h = torch.randn(b, 3 * hf, 3 * wf, generator=g) * (torch.rand(b, 3 * hf, 3 * wf, generator=g) < 0.3)
-        gdisp = gd_h.to(dev)
+    def max_over_ranks(vals):
+        if world == 1:
+            return [float(v) for v in vals]
+        t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
 
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    marks = [[ev() for _ in range(5)] for _ in range(K)]
-
-    sub = 8 if args.workload == "router" else b   # router: one call per scene path
-
-    def step(mk=None):
-        if mk: mk[0].record()
-        if not bwd:
-            cost = [F_.cost_volume_forward(x[i:i + sub], y[i:i + sub], df) for i in range(0, b, sub)]
-            if mk: mk[1].record()
-            disp = [F_.disp_head_forward(cl[i:i + sub], md, want_stats=False)[0] for i in range(0, b, sub)]
-            if mk: mk[2].record()
-            return cost, disp
-        cost = F_.cost_volume_forward(x, y, df)
-        if mk: mk[1].record()
-        disp, stats = F_.disp_head_forward(cl, md, want_stats=True)
-        if mk: mk[2].record()
-        gcl = F_.disp_head_backward(cl, gdisp, disp, stats, md)
-        if mk: mk[3].record()
-        gx, gy = F_.cost_volume_backward(gcost, c)
-        if mk: mk[4].record()
-        return cost, disp, gcl, gx, gy
-
-    for _ in range(Wm):
-        out = step()
-    del out
-
-    # ---- serial pass: the kernels back to back on one stream, each bracketed by events.  This is where the
-    # per-kernel durations (roofline) come from; for the training workload it is also the timed region. ----
-    def serial_pass():
-        barrier()
-        t0, t1 = ev(), ev()
-        t0.record()
-        for k in range(K):
-            out = step(marks[k])
-        t1.record()
-        torch.cuda.synchronize()
-        del out
-        return t0.elapsed_time(t1)
-
-    # ---- overlapped pass (inference workloads): cost volume and disparity head on two streams, the
-    # schedule of rag_b200.pipeline.OverlappedPath for a stream of batches ----
-    opath = OverlappedPath(md, dev) if not bwd else None
-
-    def overlapped_step():
-        outs = [opath.step(x[i:i + sub], y[i:i + sub], cl[i:i + sub]) for i in range(0, b, sub)]
-        return outs
-
-    def overlapped_pass():
-        for _ in range(Wm):
-            outs = overlapped_step()
-        opath.join()
-        barrier()
-        t0, t1 = ev(), ev()
-        t0.record()
-        for k in range(K):
-            outs = overlapped_step()
-        opath.join()
-        t1.record()
-        torch.cuda.synchronize()
-        del outs
-        return t0.elapsed_time(t1)
-
-    sampler = ClockSampler(local) if rank == 0 else None
-    serial_ms = None
-    if not bwd:
-        serial_ms = serial_pass()            # untimed for `value`: kernel durations only
-    barrier()
-    n0 = _cabi.launch_count()
-    if sampler: sampler.start()
-    total_ms = overlapped_pass() if not bwd else serial_pass()
-    if sampler: clocks = sampler.stop()
-    launches = _cabi.launch_count() - n0 - (0 if bwd else Wm * 2 * (b // sub))   # minus the warm-up launches of the pass
-    barrier()
-    if world > 1:
-        t = torch.tensor([total_ms, serial_ms if serial_ms is not None else total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t[0].item())
-        serial_ms = float(t[1].item()) if serial_ms is not None else None
-    value = world * b * K / (total_ms * 1e-3)
-
-    # per-kernel average durations (serial pass: each kernel alone on the GPU, back to back)
-    n_seg = 4 if bwd else 2
-    seg_ms = [sum(marks[k][i].elapsed_time(marks[k][i + 1]) for k in range(K)) / K for i in range(n_seg)]
-    cvb, hfb, hbb = alg_bytes(c, hf, wf, df)
+    K, Wm = args.steps, max(args.warmup, 3)
     peak, peak_src = measured_peak()
-    n_sub = b // sub
-    cv_ms = seg_ms[0] / n_sub                       # average duration of ONE cost-volume launch
-    achieved = cvb * sub / (cv_ms * 1e-3) / 1e9
-    lean = wf % 4 == 0
-    roofline = {
-        "bound": "hbm", "kernel": ("cv_fwd_lean_kernel<256,2,true>" if lean else "cv_fwd_kernel") + " (cost-volume forward)",
-        "achieved": round(achieved, 1), "peak": peak,
-        "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": ncu_traffic("cv_fwd_lean_kernel" if lean else "cv_fwd_kernel"),
-        "peak_source": peak_src, "alg_bytes_per_launch": cvb * sub, "avg_launch_ms": round(cv_ms, 5),
-        "timed_in": "serial pass of %d steps in this run (kernels back to back on one stream, CUDA events around each)" % K,
-        "note": "a write-only stream: the measured peak is a COPY (read+write) figure, a pure fill of the same bytes runs at ~7.45 TB/s",
-    }
-    path_bytes = (cvb + hfb + ((cvb + hbb) if bwd else 0)) * b
-    kernels = {"cv_fwd_ms": seg_ms[0], "head_fwd_ms": seg_ms[1]}
-    if bwd:
-        kernels.update({"head_bwd_ms": seg_ms[2], "cv_bwd_ms": seg_ms[3]})
-    step_ms = total_ms / K
-    path = {
-        "alg_bytes_per_step": path_bytes, "achieved_GBps": round(path_bytes / (step_ms * 1e-3) / 1e9, 1),
-        "frac_of_hbm_peak": round(path_bytes / (step_ms * 1e-3) / 1e9 / peak, 4),
-        "schedule": ("serial: the four kernels back to back on one stream" if bwd else
-                     "overlapped: cost volume and disparity head on two streams (rag_b200.pipeline.OverlappedPath); the two kernels of a step have no "
-                     "data dependence (in the network the Matching Net sits between them: head of batch i runs beside the volume of batch i+1)"),
-        "kernel_ms": {k: round(v, 5) for k, v in kernels.items()},
-        "note": "the head kernels are FP32-pipe bound (one exp2 + 7-12 FP32 ops per pixel per low-res bin), not HBM bound; see DESIGN.md",
-    }
-    if serial_ms is not None:
-        path["serial"] = {"ms_per_step": round(serial_ms / K, 5), "pairs_per_s": round(world * b * K / (serial_ms * 1e-3), 1),
-                          "frac_of_hbm_peak": round(path_bytes / (serial_ms / K * 1e-3) / 1e9 / peak, 4)}
+    sampler = ClockSampler(local) if rank == 0 else None
 
-    # ---- e2e: HOST buffers through the public pipeline (H2D + kernels + D2H per step) ----
-    pipe = HostPipeline(md, dev)
+    def measure(workload, with_clocks):
+        """Serial pass (kernels back to back on one stream, events around each) + overlapped pass (two streams)."""
+        b, c, hf, wf, df, md, bwd, desc = WORKLOADS[workload]
+        # identical bits for CPU reference and GPU: generate on the host with a fixed seed, then copy
+        g = torch.Generator().manual_seed(1234 + rank)
+        x = torch.randn(b, c, hf, wf, generator=g).to(dev)
+        y = torch.randn(b, c, hf, wf, generator=g).to(dev)
+        cl = torch.randn(b, 1, df, hf, wf, generator=g).to(dev)
+        gcost = gdisp = None
+        if bwd:
+            gcost = torch.randn(b, 2 * c, df, hf, wf, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+            gdisp = (torch.randn(b, 3 * hf, 3 * wf, generator=g) * (torch.rand(b, 3 * hf, 3 * wf, generator=g) < 0.3)).to(dev)
+        marks = [[ev() for _ in range(5)] for _ in range(K)]
+        sub = 8 if workload == "router" else b   # router: one call per scene path
+        n_sub = b // sub
+
+        def step(mk=None):
+            if mk: mk[0].record()
+            if not bwd:
+                cost = [F_.cost_volume_forward(x[i:i + sub], y[i:i + sub], df) for i in range(0, b, sub)]
+                if mk: mk[1].record()
+                disp = [F_.disp_head_forward(cl[i:i + sub], md, want_stats=False)[0] for i in range(0, b, sub)]
+                if mk: mk[2].record()
+                return cost, disp
+            cost = F_.cost_volume_forward(x, y, df)
+            if mk: mk[1].record()
+            disp, stats = F_.disp_head_forward(cl, md, want_stats=True)
+            if mk: mk[2].record()
+            gcl = F_.disp_head_backward(cl, gdisp, disp, stats, md)
+            if mk: mk[3].record()
+            gx, gy = F_.cost_volume_backward(gcost, c)
+            if mk: mk[4].record()
+            return cost, disp, gcl, gx, gy
+
+        def serial_pass():
+            for _ in range(Wm):
+                out = step()
+            barrier()
+            t0, t1 = ev(), ev()
+            t0.record()
+            for k in range(K):
+                out = step(marks[k])
+            t1.record()
+            torch.cuda.synchronize()
+            del out
+            return t0.elapsed_time(t1)
+
+        opath = OverlappedTrainPath(md, dev) if bwd else OverlappedPath(md, dev)
+
+        def overlapped_step():
+            if bwd:
+                return opath.step(x, y, cl, gcost, gdisp)
+            return [opath.step(x[i:i + sub], y[i:i + sub], cl[i:i + sub]) for i in range(0, b, sub)]
+
+        def overlapped_pass():
+            for _ in range(Wm):
+                outs = overlapped_step()
+            opath.join()
+            barrier()
+            t0, t1 = ev(), ev()
+            t0.record()
+            for k in range(K):
+                outs = overlapped_step()
+            opath.join()
+            t1.record()
+            torch.cuda.synchronize()
+            del outs
+            return t0.elapsed_time(t1)
+
+        def graph_pass():
+            """The same two-stream step captured ONCE into a CUDA graph (fork/join included) and replayed K times."""
+            if bwd:
+                graphs = [opath.capture(x, y, cl, gcost, gdisp)]
+            else:
+                graphs = [opath.capture(x[i:i + sub], y[i:i + sub], cl[i:i + sub]) for i in range(0, b, sub)]
+            for _ in range(Wm):
+                for gr, _o in graphs:
+                    gr.replay()
+            barrier()
+            t0, t1 = ev(), ev()
+            t0.record()
+            for k in range(K):
+                for gr, _o in graphs:
+                    gr.replay()
+            t1.record()
+            torch.cuda.synchronize()
+            del graphs
+            return t0.elapsed_time(t1)
+
+        serial_ms = serial_pass()
+        barrier()
+        n0 = _cabi.launch_count()
+        eager_ms = overlapped_pass()
+        barrier()
+        n0 = _cabi.launch_count()
+        if with_clocks and sampler: sampler.start()
+        total_ms = graph_pass() if not args.no_graph else overlapped_pass()
+        clocks = sampler.stop() if (with_clocks and sampler) else None
+        graph_ms = None if args.no_graph else total_ms
+        used_graph = not args.no_graph
+        if used_graph and eager_ms < total_ms:
+            # the small training kernels overlap better ACROSS steps (two free-running streams) than inside one captured
+            # fork/join per step: keep the faster schedule as the headline and report both
+            total_ms, used_graph = eager_ms, False
+        per_step = (4 if bwd else 2 * n_sub)
+        launches = K * per_step            # kernels of ours per timed step (a graph replay launches the captured ones)
+        barrier()
+        total_ms, serial_ms, eager_ms, graph_ms = max_over_ranks([total_ms, serial_ms, eager_ms, graph_ms if graph_ms is not None else 0.0])
+        n_seg = 4 if bwd else 2
+        seg_ms = [sum(marks[k][i].elapsed_time(marks[k][i + 1]) for k in range(K)) / K for i in range(n_seg)]
+        cvb, hfb, hbb = alg_bytes(c, hf, wf, df)
+        cv_ms = seg_ms[0] / n_sub                       # average duration of ONE cost-volume launch
+        achieved = cvb * sub / (cv_ms * 1e-3) / 1e9
+        lean = wf % 4 == 0
+        kname = "cv_fwd_lean_kernel<256,2,true>" if lean else "cv_fwd_kernel"
+        roofline = {
+            "bound": "hbm", "kernel": kname + " (cost-volume forward)",
+            "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "traffic": ncu_traffic("cv_fwd_lean_kernel" if lean else "cv_fwd_kernel") if workload in ("infer", "router") else None,
+            "peak_source": peak_src, "alg_bytes_per_launch": cvb * sub, "avg_launch_ms": round(cv_ms, 5),
+            "timed_in": "serial pass of %d steps in this run (kernels back to back on one stream, CUDA events around each)" % K,
+            "note": "a write-only stream: the measured peak is a COPY (read+write) figure, a pure fill of the same bytes runs at ~7.45 TB/s",
+        }
+        path_bytes = (cvb + hfb + ((cvb + hbb) if bwd else 0)) * b
+        kernels = {"cv_fwd_ms": seg_ms[0], "head_fwd_ms": seg_ms[1]}
+        if bwd:
+            kernels.update({"head_bwd_ms": seg_ms[2], "cv_bwd_ms": seg_ms[3]})
+        kfrac = {"cv_fwd": cvb * b / (seg_ms[0] * 1e-3) / 1e9 / peak, "head_fwd": hfb * b / (seg_ms[1] * 1e-3) / 1e9 / peak}
+        if bwd:
+            kfrac.update({"head_bwd": hbb * b / (seg_ms[2] * 1e-3) / 1e9 / peak, "cv_bwd": cvb * b / (seg_ms[3] * 1e-3) / 1e9 / peak})
+        step_ms, sstep_ms = total_ms / K, serial_ms / K
+
+        def frac(ms):
+            return round(path_bytes / (ms * 1e-3) / 1e9 / peak, 4)
+
+        path = {
+            "alg_bytes_per_step": path_bytes,
+            "overlapped": {"ms_per_step": round(step_ms, 5), "pairs_per_s": round(world * b / (step_ms * 1e-3), 1), "frac_of_hbm_peak": frac(step_ms),
+                           "launched_as": "one CUDA graph replay per step (the two-stream step captured once)" if used_graph else "eager launches on two free-running streams"},
+            "overlapped_graph": ({"ms_per_step": round(graph_ms / K, 5), "pairs_per_s": round(world * b * K / (graph_ms * 1e-3), 1), "frac_of_hbm_peak": frac(graph_ms / K)} if graph_ms else None),
+            "overlapped_eager": {"ms_per_step": round(eager_ms / K, 5), "pairs_per_s": round(world * b * K / (eager_ms * 1e-3), 1), "frac_of_hbm_peak": frac(eager_ms / K)},
+            "serial": {"ms_per_step": round(sstep_ms, 5), "pairs_per_s": round(world * b / (sstep_ms * 1e-3), 1), "frac_of_hbm_peak": frac(sstep_ms)},
+            "kernel_ms": {k: round(v, 5) for k, v in kernels.items()},
+            "kernel_frac_of_hbm_peak": {k: round(v, 4) for k, v in kfrac.items()},
+            "schedule_note": ("overlapped = the volume kernels on one stream (persistent grids, launched first) and the head kernels on another "
+                              "(rag_b200.pipeline.%s); the kernels of a step have no data dependence on each other (in the network the Matching Net "
+                              "sits between them), so a stream of batches overlaps them; serial = back to back on one stream" % type(opath).__name__),
+            "note": "the head kernels are FP32-pipe bound (one exp2 + 7-12 FP32 ops per pixel per low-res bin), not HBM bound; see DESIGN.md",
+        }
+        rec = {"value": world * b * K / (total_ms * 1e-3), "value_serial": world * b * K / (serial_ms * 1e-3), "ms_per_step": step_ms,
+               "ms_per_step_serial": sstep_ms, "schedule": "overlapped, CUDA-graph replay" if used_graph else "overlapped, eager two-stream", "roofline": roofline, "path": path, "gpu_launches": int(launches), "clocks": clocks}
+        return rec, (x, y, cl, gcost, gdisp)
+
+    main, tensors = measure(args.workload, with_clocks=True)
+    b, c, hf, wf, df, md, bwd, desc = WORKLOADS[args.workload]
+    x, y, cl, gcost, gdisp = tensors
+
+    # ---- e2e: HOST buffers through the public pipeline (ONE H2D + kernels + ONE D2H per step) ----
+    pipe = HostTrainPipeline(md, dev) if bwd else HostPipeline(md, dev)
     Ke = max(3, min(K, 50))
+    gh = torch.Generator().manual_seed(99 + rank)
+
+    def host_step():
+        slot = pipe.acquire((b, c, hf, wf), (b, 1, df, hf, wf))
+        return pipe.submit(slot, gcost) if bwd else pipe.submit(slot)
+
+    for _ in range(pipe.depth):              # fill every slot's pinned staging buffer once (the data loader's job), untimed
+        slot = pipe.acquire((b, c, hf, wf), (b, 1, df, hf, wf))
+        for k, v in slot.host.items():
+            v.normal_(generator=gh)
+            if k == "gdisp":
+                v.mul_((torch.rand(v.shape, generator=gh) < 0.3).float())
+        pipe.submit(slot, gcost) if bwd else pipe.submit(slot)
     for _ in range(3):
-        pipe.submit(x_h, y_h, cl_h)
+        host_step()
     pipe.drain()
     barrier()
     e0, e1 = ev(), ev()
     e0.record()
-    last = None
     for _ in range(Ke):
-        last = pipe.submit(x_h, y_h, cl_h)
+        last = host_step()
     pipe.drain()
     e1.record()
     torch.cuda.synchronize()
     e2e_ms = e0.elapsed_time(e1)
     barrier()
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    checksum = float(last["disp_h"].double().mean())
-    h2d = (x_h.numel() + y_h.numel() + cl_h.numel()) * 4
-    d2h = last["disp_h"].numel() * 4
+    h2d, d2h = last.h2d_bytes, last.d2h_bytes
+    # the box's copy ceiling with the same ranks active: the same bytes, one plain pinned copy per direction, no kernels
+    def ceiling(n_bytes, to_device):
+        hbuf = torch.empty(n_bytes // 4, dtype=torch.float32).pin_memory()
+        hbuf.zero_()
+        dbuf = torch.empty(n_bytes // 4, dtype=torch.float32, device=dev)
+        fn = (lambda: dbuf.copy_(hbuf, non_blocking=True)) if to_device else (lambda: hbuf.copy_(dbuf, non_blocking=True))
+        for _ in range(2):
+            fn()
+        barrier()
+        c0, c1 = ev(), ev()
+        c0.record()
+        for _ in range(10):
+            fn()
+        c1.record()
+        torch.cuda.synchronize()
+        ms = c0.elapsed_time(c1) / 10
+        barrier()
+        return ms
+    h2d_ms = ceiling(h2d, True)
+    e2e_ms, h2d_ms = max_over_ranks([e2e_ms, h2d_ms])
+    checksum = float(last.result["disp"].double().mean())
+    e2e_step = e2e_ms / Ke
     e2e = {"value": world * b * Ke / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "steps": Ke, "ms_per_step": e2e_ms / Ke, "mode": "forward (inference) through rag_b200.pipeline.HostPipeline, pinned host buffers, double-buffered copies",
-           "mean_disp": checksum}
+           "steps": Ke, "ms_per_step": e2e_step, "copies_per_step": {"h2d": 1, "d2h": 1},
+           "mode": ("forward + backward (training step) through rag_b200.pipeline.HostTrainPipeline" if bwd else "forward (inference) through rag_b200.pipeline.HostPipeline")
+                   + ": one coalesced pinned staging buffer per direction, one cudaMemcpyAsync each way per step, double-buffered against the kernels",
+           "h2d_GBps_per_rank": round(h2d / (e2e_step * 1e-3) / 1e9, 2),
+           "h2d_ceiling_GBps_per_rank": round(h2d / (h2d_ms * 1e-3) / 1e9, 2),
+           "frac_of_h2d_ceiling": round(h2d_ms / e2e_step, 4),
+           "ceiling_note": "ceiling = the same bytes as one plain pinned cudaMemcpyAsync per step on every rank at once, measured in this run (slowest rank); "
+                           "the box's PCIe fabric, not the kernels, bounds e2e (profiles/r2_h2d_ceiling.md)",
+           "numa_binding": numa, "mean_disp": checksum}
+    del pipe
+    torch.cuda.empty_cache()
 
-    cpu = None
-    torch_gpu = None
-    next_rows = None
+    train = None
+    if args.workload == "infer" and not args.no_train_record:
+        del tensors
+        keep = (x, y)
+        trec, ttens = measure("train", with_clocks=False)
+        del ttens
+        train = {"config": config_dict("train"), "value": trec["value"], "value_serial": trec["value_serial"], "unit": "pairs/s",
+                 "ms_per_step": trec["ms_per_step"], "ms_per_step_serial": trec["ms_per_step_serial"], "schedule": trec["schedule"],
+                 "roofline": trec["roofline"], "path": trec["path"], "gpu_launches": trec["gpu_launches"], "steps": K, "warmup": Wm}
+        torch.cuda.empty_cache()
+
+    cpu = torch_gpu = next_rows = parity = config1 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_reference(args.workload, budget_s=12.0)
+        parity = parity_record(args.workload, dev)
+        if train is not None:
+            train["parity"] = parity_record("train", dev)
+            train["torch_cuda_reference"] = torch_cuda_reference("train", dev, reps=3)
+            train["cpu_baseline"], _ = cpu_reference("train", warmup=1, steps=3, budget_s=10.0)
         torch_gpu = torch_cuda_reference(args.workload, dev)
         if not bwd:
-            next_rows = fused_stem_row(x, y, df, md, sub)
+            next_rows = next_rows_record(x, y, df, md, 8 if args.workload == "router" else b)
+        cpu, _ = cpu_reference(args.workload, warmup=1, steps=20, budget_s=15.0)
+        if args.workload == "infer":
+            config1 = config1_full_network_cpu(budget_s=12.0)
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": desc, "pairs_per_gpu": b, "features": [b, c, hf, wf],
-                       "volume": [b, 2 * c, df, hf, wf], "head_in": [b, 1, df, hf, wf], "maxdisp": md,
-                       "l2": "no explicit flush: every step streams %.2f GB (>> 126 MB L2) through HBM" % (path_bytes / 1e9),
-                       "sharding": "stereo pairs across ranks, no data-path collective"},
-            "roofline": roofline, "path": path, "cpu_baseline": cpu, "torch_cuda_reference": torch_gpu, "next_rows": next_rows, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "metric": METRIC, "value": main["value"], "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args.workload),
+            "schedule": main["schedule"], "value_serial": main["value_serial"], "ms_per_step_serial": main["ms_per_step_serial"],
+            "roofline": main["roofline"], "path": main["path"], "train": train, "parity": parity,
+            "cpu_baseline": cpu, "config1_full_network_cpu": config1, "torch_cuda_reference": torch_gpu, "next_rows": next_rows,
+            "e2e": e2e, "gpu_launches": main["gpu_launches"], "clocks": main["clocks"],
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -505,7 +773,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="infer")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-side legs (cpu_baseline, parity, torch_cuda_reference, next_rows)")
+    ap.add_argument("--no-graph", action="store_true", help="time the two-stream schedule with eager launches instead of CUDA-graph replays")
+    ap.add_argument("--no-train-record", action="store_true", help="default workload only: skip the configs[2] training sub-record")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

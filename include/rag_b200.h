@@ -118,7 +118,8 @@ RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int 
  *                          per item (default without a workspace when Wf % 4 == 0); 2 = lean persistent, 256 threads, one
  *                          CTA per SM (default with a workspace); 3 = lean persistent, 512 threads (SM sharing);
  *                          4 = TMA bulk-store kernel (cp.async.bulk shared->global).  2-4 need the workspace.
- *   rag_cost_volume_bwd_v  0 = 128-bit vector kernel (default when Wf % 4 == 0), 1 = scalar (any width)
+ *   rag_cost_volume_bwd_v  0 = 128-bit vector kernel (default when Wf % 4 == 0), 1 = scalar (any width),
+ *                          2 = the vector kernel as a persistent grid of 4 CTAs per SM (SM sharing with the head backward)
  *   rag_disp_head_fwd_v    0 = any (Dl, maxdisp); 1 = first x3 kernel (any width); 2 = cube-root tiled kernel (default when
  *                          maxdisp == 3*Dl and Wl % 4 == 0); 3 = as 2 with the lambda correction at every step + TwoSum totals
  *   rag_disp_head_bwd_v    0 = any-ratio gather; 1 = block-row tasks, parts added in place (default when maxdisp == 3*Dl);
@@ -129,6 +130,7 @@ RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int 
  * of one 512-thread CTA per SM whose store stream leaves most of the SM to the FP32-bound head. */
 #define RAG_CV_FWD_LEAN 2     /* default with a workspace: persistent, one 256-thread CTA per SM                  */
 #define RAG_CV_FWD_SHARED 3   /* same kernel, one 512-thread CTA per SM: best when sharing SMs with the head        */
+#define RAG_CV_BWD_SHARED 2   /* backward as a persistent grid: launched first, it leaves room for the head backward */
 RAG_API int rag_cost_volume_fwd_v(const float* x, const float* y, float* cost,
                           int B, int C, int Df, int Hf, int Wf, void* workspace, int variant, void* stream);
 RAG_API int rag_cost_volume_bwd_v(const float* gcost, float* gx, float* gy,

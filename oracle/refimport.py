@@ -58,7 +58,7 @@ def import_reference(cpu_patch: bool = False) -> types.SimpleNamespace:
         import torch
 
         if not torch.cuda.is_available():
-            torch.cuda.current_device = lambda: "cpu"  # rag_model.py:26
+            torch.cuda.current_device = lambda: "cpu"  # rag_model.py:26 (permanent: there is no CUDA device to name)
     import automl.genotypes_2d as genotypes_2d
     import automl.mdenas_basicmodel as mdenas_basicmodel
     import automl.operations_3d as operations_3d
@@ -70,6 +70,25 @@ def import_reference(cpu_patch: bool = False) -> types.SimpleNamespace:
         raise RuntimeError(f"'utils' resolved to {ref_utils.__file__}, not the reference's src/utils.py")
     return types.SimpleNamespace(src=src, rag_model=rag_model, mdenas_basicmodel=mdenas_basicmodel,
                                  operations_3d=operations_3d, genotypes_2d=genotypes_2d, utils=ref_utils, metrics=metrics)
+
+
+class on_cpu:
+    """Context manager for running the unmodified reference head on CPU tensors on a machine that HAS a CUDA device:
+    rag_model.py:26 builds its ``arange`` on ``torch.cuda.current_device()``, so for the duration of the block that
+    function answers 'cpu' (the one monkeypatch of SURVEY.md section 8c); restored on exit."""
+
+    def __enter__(self):
+        import torch
+
+        self._orig = torch.cuda.current_device
+        torch.cuda.current_device = lambda: "cpu"
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+
+        torch.cuda.current_device = self._orig
+        return False
 
 
 def make_genotype(ref, seed: int = 0):

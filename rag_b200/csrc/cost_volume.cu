@@ -134,16 +134,10 @@ cv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, float* _
 // ---------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------
-// Vector path (Wf % 4 == 0).  grid: x over Hf*Wv vectors, y = c, z = b.
-template <int NT, int U, int MINB>
-__global__ void __launch_bounds__(NT, MINB)
-cv_bwd_v4_kernel(const float* __restrict__ g, float* __restrict__ gx, float* __restrict__ gy,
-                 int C, int Df, int Hf, int Wf) {
-    const int Wv = Wf >> 2;
-    const int PV = Hf * Wv;
-    const int p = blockIdx.x * NT + threadIdx.x;
-    if (p >= PV) return;
-    const int c = blockIdx.y, b = blockIdx.z;
+// Vector path (Wf % 4 == 0): one thread owns vector p of the (b, c) plane.
+template <int U>
+__device__ __forceinline__ void cv_bwd_v4_unit(const float* __restrict__ g, float* __restrict__ gx, float* __restrict__ gy,
+                                               int C, int Df, int Wv, int PV, int p, int c, int b) {
     const int wv = p % Wv;
     const int w0 = wv << 2;
     const size_t planeV = (size_t)PV;
@@ -195,6 +189,36 @@ cv_bwd_v4_kernel(const float* __restrict__ g, float* __restrict__ gx, float* __r
     const size_t o = (size_t)(b * C + c) * planeV + p;
     reinterpret_cast<float4*>(gx)[o] = ax;
     reinterpret_cast<float4*>(gy)[o] = ay;
+}
+
+// grid: x over Hf*Wv vectors, y = c, z = b.
+template <int NT, int U, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
+cv_bwd_v4_kernel(const float* __restrict__ g, float* __restrict__ gx, float* __restrict__ gy,
+                 int C, int Df, int Hf, int Wf) {
+    const int Wv = Wf >> 2;
+    const int PV = Hf * Wv;
+    const int p = blockIdx.x * NT + threadIdx.x;
+    if (p >= PV) return;
+    cv_bwd_v4_unit<U>(g, gx, gy, C, Df, Wv, PV, p, blockIdx.y, blockIdx.z);
+}
+
+// Persistent form: a grid of `per_sm` CTAs per SM that is resident at once walks the items (b*C + c, block of NT vectors)
+// in order.  Used when the kernel has to SHARE the SMs with the FP32-bound head backward on a second stream
+// (rag_b200.pipeline.OverlappedTrainPath): launched first, its small footprint (NT threads x ~48 registers per CTA)
+// leaves the register file to the head's CTAs, which the block scheduler can then dispatch beside it.
+template <int NT, int U>
+__global__ void __launch_bounds__(NT)
+cv_bwd_v4_persistent_kernel(const float* __restrict__ g, float* __restrict__ gx, float* __restrict__ gy,
+                            int BC, int C, int Df, int Hf, int Wf, int n_blk) {
+    const int Wv = Wf >> 2;
+    const int PV = Hf * Wv;
+    const long long n_items = (long long)BC * n_blk;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int bc = (int)(item / n_blk), blk = (int)(item - (long long)bc * n_blk);
+        const int p = blk * NT + threadIdx.x;
+        if (p < PV) cv_bwd_v4_unit<U>(g, gx, gy, C, Df, Wv, PV, p, bc % C, bc / C);
+    }
 }
 
 // Scalar path (any Wf).  grid: x over Hf*Wf elements, y = c, z = b.
@@ -359,13 +383,21 @@ int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, i
     return launch_cv_fwd<1, 256>(x, y, cost, B, C, Df, Hf, Wf, st);
 }
 
-// variant: 0 = default (128-bit vector kernel when Wf % 4 == 0 and aligned, else scalar); 1 = scalar
+// variant: 0 = default (128-bit vector kernel when Wf % 4 == 0 and aligned, else scalar); 1 = scalar;
+// 2 = RAG_CV_BWD_SHARED: the vector kernel as a persistent grid of 4 x 128-thread CTAs per SM (SM sharing)
 int cost_volume_bwd(const float* g, float* gx, float* gy, int B, int C, int Df, int Hf, int Wf,
                     int variant, cudaStream_t st) {
     if (int e = check_cv_args(g, gx, gy, B, C, Df, Hf, Wf)) return e;
-    if (variant < 0 || variant > 1) return fail(RAG_E_VARIANT, "cost_volume_bwd: unknown variant %d", variant);
+    if (variant < 0 || variant > 2) return fail(RAG_E_VARIANT, "cost_volume_bwd: unknown variant %d", variant);
     const bool a16 = aligned(g, 16) && aligned(gx, 16) && aligned(gy, 16);
-    if (variant != 1 && Wf % 4 == 0 && a16) {
+    if (variant == 2) {
+        if (!(Wf % 4 == 0 && a16)) return fail(RAG_E_VARIANT, "cost_volume_bwd: variant 2 needs Wf %% 4 == 0 and 16-byte aligned pointers");
+        constexpr int NT = 128;
+        const int PV = Hf * (Wf / 4), n_blk = (PV + NT - 1) / NT;
+        const long long n_items = (long long)B * C * n_blk;
+        const int grid = (int)std::min<long long>(n_items, (long long)num_sms() * 4);
+        cv_bwd_v4_persistent_kernel<NT, 4><<<grid, NT, 0, st>>>(g, gx, gy, B * C, C, Df, Hf, Wf, n_blk);
+    } else if (variant != 1 && Wf % 4 == 0 && a16) {
         constexpr int NT = 128;
         const int PV = Hf * (Wf / 4);
         dim3 grid((PV + NT - 1) / NT, C, B);

@@ -48,3 +48,31 @@ def wrap_ddp(model: torch.nn.Module, local_rank: int):
         dev = [local_rank] if torch.cuda.is_available() else None
         return DDP(model, device_ids=dev, find_unused_parameters=True)
     return model
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin the calling process to the CPU cores that are local to GPU ``local_rank`` (NVML's ideal CPU affinity =
+    the cores of the NUMA node / socket the GPU's PCIe root hangs off).  Call it BEFORE allocating pinned host
+    buffers: pinned pages are placed on the NUMA node of the thread that first touches them, and a host->device
+    copy from the remote socket crosses the inter-socket link (with 8 ranks that link, not PCIe, becomes the
+    end-to-end limit).  Returns what was done; never raises (no NVML / no permission = unbound)."""
+    info = {"bound": False}
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(local_rank)
+        n_cpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(bound=True, cpus=len(allowed), first=allowed[0], last=allowed[-1])
+        try:
+            info["numa_node"] = int(nv.nvmlDeviceGetNumaNodeId(h))
+        except Exception:
+            pass
+    except Exception as e:  # noqa: BLE001
+        info["error"] = f"{type(e).__name__}: {e}"[:120]
+    return info

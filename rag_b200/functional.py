@@ -113,11 +113,17 @@ def _head_shape(cost_lr: torch.Tensor):
     return b, dl, hl, wl
 
 
-def disp_head_forward(cost_lr: torch.Tensor, maxdisp: int, want_stats: bool = True, variant: int | None = None):
+def disp_head_forward(cost_lr: torch.Tensor, maxdisp: int, want_stats: bool = True, variant: int | None = None,
+                      out: torch.Tensor | None = None):
+    """``out``: optional caller-owned contiguous [B,3Hl,3Wl] CUDA fp32 tensor the disparity is written into."""
     _require(cost_lr, "cost_lr")
     cost_lr = cost_lr.contiguous()
     b, dl, hl, wl = _head_shape(cost_lr)
-    disp = torch.empty((b, 3 * hl, 3 * wl), dtype=torch.float32, device=cost_lr.device)
+    if out is not None:
+        _require(out, "out")
+        if tuple(out.shape) != (b, 3 * hl, 3 * wl) or not out.is_contiguous() or out.device != cost_lr.device:
+            raise RuntimeError(f"rag_b200: out must be a contiguous [{b},{3 * hl},{3 * wl}] tensor on {cost_lr.device}")
+    disp = out if out is not None else torch.empty((b, 3 * hl, 3 * wl), dtype=torch.float32, device=cost_lr.device)
     stats = torch.empty((b, 2, 3 * hl, 3 * wl), dtype=torch.float32, device=cost_lr.device) if want_stats else None
     if disp.numel() == 0:
         return disp, stats

@@ -1,19 +1,20 @@
-"""Host-buffer entry point of the hot path: pinned host tensors in, pinned host disparity out.
+"""Schedules of the hot path around the four kernels: two-stream overlap on the device, and the HOST-buffer entry
+points (pinned host tensors in, pinned host results out) that bench.py times as ``e2e``.
 
-This is the call a host-side user of the path makes when the data does not already live on the
-GPU (and what bench.py times as ``e2e``): per step it copies the step's inputs host->device,
-runs the cost-volume and disparity-head kernels through the public modules, and copies the
-disparity map device->host.  Copies run on a side stream and are double-buffered against the
-compute stream, so steady-state throughput is max(PCIe time, kernel time) per step.
+Host side: ONE coalesced pinned staging buffer per direction and per slot, so a step issues ONE ``cudaMemcpyAsync``
+host->device and ONE device->host (the box's PCIe fabric is the end-to-end limit, profiles/r2_h2d_ceiling.md; fewer,
+larger copies are what it wants).  The caller fills the staging views in place (``slot.x`` / ``.y`` / ``.cost_lr`` are
+views of the pinned buffer: collate straight into them), then ``submit(slot)``.  Copies run on side streams and are
+double-buffered against the compute stream: steady-state throughput is max(PCIe time, kernel time) per step.
 """
 from __future__ import annotations
 
 import torch
 
 from . import functional as F_
-from .modules import CostVolume, Disp
 
 CV_FWD_SHARED = 3    # include/rag_b200.h RAG_CV_FWD_SHARED
+CV_BWD_SHARED = 2    # include/rag_b200.h RAG_CV_BWD_SHARED
 
 
 class OverlappedPath:
@@ -33,12 +34,16 @@ class OverlappedPath:
         self.s_cv = torch.cuda.Stream(self.device)
         self.s_head = torch.cuda.Stream(self.device)
 
-    def step(self, x: torch.Tensor, y: torch.Tensor, cost_lr: torch.Tensor, want_stats: bool = False):
-        """x, y [B,C,Hf,Wf] and cost_lr [B,1,Dl,Hl,Wl] on the device, ready on the current stream.
-        Returns (cost, disp, stats_or_None); cost is valid on ``self.s_cv``, disp/stats on ``self.s_head``."""
+    def _fork(self):
         cur = torch.cuda.current_stream(self.device)
         self.s_cv.wait_stream(cur)
         self.s_head.wait_stream(cur)
+        return cur
+
+    def step(self, x: torch.Tensor, y: torch.Tensor, cost_lr: torch.Tensor, want_stats: bool = False):
+        """x, y [B,C,Hf,Wf] and cost_lr [B,1,Dl,Hl,Wl] on the device, ready on the current stream.
+        Returns (cost, disp, stats_or_None); cost is valid on ``self.s_cv``, disp/stats on ``self.s_head``."""
+        cur = self._fork()
         with torch.no_grad():
             with torch.cuda.stream(self.s_cv):
                 cost = F_.cost_volume_forward(x, y, int(self.maxdisp / 3), variant=CV_FWD_SHARED if x.shape[-1] % 4 == 0 else None)
@@ -60,70 +65,188 @@ class OverlappedPath:
         cur.wait_stream(self.s_cv)
         cur.wait_stream(self.s_head)
 
+    def capture(self, *args, **kw):
+        """Capture one ``step(*args)`` + ``join()`` (the two-stream fork/join included) into a CUDA graph over the given
+        STATIC input tensors.  Returns ``(graph, outputs)``: refill the inputs in place, ``graph.replay()``, read the
+        outputs.  A replay costs one launch on the host instead of ~10 calls per step, which matters for the small training
+        kernels (80 us each: the eager two-stream step is host-bound).  Every launch of the library is capturable: work
+        counters live in per-launch workspaces that the captured memset nodes re-zero on every replay."""
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.step(*args, **kw)             # warm-up outside the capture (cudaFuncSetAttribute, allocator pools)
+            self.join()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            outs = self.step(*args, **kw)
+            self.join()
+        return graph, outs
+
+
+class OverlappedTrainPath(OverlappedPath):
+    """The training step (forward + backward of both operators) on the same two streams: the HBM-bound volume kernels
+    (cost-volume forward, then its backward) on one stream as persistent grids, the FP32-bound head kernels (forward,
+    then backward) on the other.  Inside a network the partners differ (the Matching Net sits between the operators, and
+    its backward between their backwards); what the schedule shows is that the two kinds of kernel do not compete for
+    the same resource, so a training step costs ~max(volume stream, head stream) instead of their sum."""
+
+    def step(self, x, y, cost_lr, gcost, gdisp):
+        cur = self._fork()
+        c = x.shape[1]
+        shared = x.shape[-1] % 4 == 0
+        with torch.no_grad():
+            with torch.cuda.stream(self.s_cv):
+                cost = F_.cost_volume_forward(x, y, int(self.maxdisp / 3), variant=CV_FWD_SHARED if shared else None)
+                gx, gy = F_.cost_volume_backward(gcost, c, variant=CV_BWD_SHARED if shared else None)
+            with torch.cuda.stream(self.s_head):
+                disp, stats = F_.disp_head_forward(cost_lr, self.maxdisp, want_stats=True)
+                gcl = F_.disp_head_backward(cost_lr, gdisp, disp, stats, self.maxdisp)
+        for t in (x, y, gcost):
+            t.record_stream(self.s_cv)
+        for t in (cost_lr, gdisp):
+            t.record_stream(self.s_head)
+        for t in (cost, gx, gy, disp, stats, gcl):
+            t.record_stream(cur)
+        return cost, disp, gcl, gx, gy
+
+
+class _Slot:
+    """One in-flight step: pinned staging (views into one buffer per direction), device mirrors, events."""
+
+    def __init__(self, shapes_in: dict, shapes_out: dict, device):
+        def carve(shapes, pinned):
+            n = sum(int(torch.Size(s).numel()) for s in shapes.values())
+            buf = torch.empty(n, dtype=torch.float32).pin_memory() if pinned else torch.empty(n, dtype=torch.float32, device=device)
+            views, o = {}, 0
+            for k, s in shapes.items():
+                m = int(torch.Size(s).numel())
+                views[k] = buf[o:o + m].view(s)
+                o += m
+            return buf, views
+
+        self.h_in, self.host = carve(shapes_in, True)        # the caller fills self.host[...] in place
+        self.d_in, self.dev = carve(shapes_in, False)
+        self.d_out, self.dev_out = carve(shapes_out, False)
+        self.h_out, self.result = carve(shapes_out, True)    # valid after done.synchronize()
+        self.ready, self.free, self.done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.keep = None
+
+    def __getattr__(self, name):           # slot.x, slot.y, slot.cost_lr ... -> pinned input views
+        host = self.__dict__.get("host", {})
+        if name in host:
+            return host[name]
+        raise AttributeError(name)
+
+    @property
+    def h2d_bytes(self):
+        return self.h_in.numel() * 4
+
+    @property
+    def d2h_bytes(self):
+        return self.h_out.numel() * 4
+
 
 class HostPipeline:
+    """Inference from host buffers: features + matching cost in, disparity out.
+
+        pipe = HostPipeline(192, dev)
+        slot = pipe.acquire((B, C, Hf, Wf), (B, 1, Dl, Hl, Wl))    # waits until the slot's previous use has finished
+        slot.x[...] = ...; slot.y[...] = ...; slot.cost_lr[...] = ...   # fill the pinned staging views in place
+        pipe.submit(slot)                                           # 1 H2D copy, 2 kernels, 1 D2H copy -- all async
+        slot.done.synchronize(); slot.result["disp"]                # pinned host [B,3Hl,3Wl]
+    """
+
     def __init__(self, maxdisp: int = 192, device: torch.device | str = "cuda", depth: int = 2):
         self.device = torch.device(device)
         self.maxdisp = maxdisp
-        self.cv = CostVolume(maxdisp)
-        self.head = Disp(maxdisp)
         self.depth = depth
         self._copy = torch.cuda.Stream(self.device)
         self._d2h = torch.cuda.Stream(self.device)
-        self._slots = None
+        self._slots, self._key, self._n = None, None, 0
 
-    def _ensure(self, x_h, cl_h):
-        key = (tuple(x_h.shape), tuple(cl_h.shape))
-        if self._slots is not None and self._key == key:
-            return
-        self._key = key
-        b, _, dl, hl, wl = cl_h.shape
-        self._slots = []
-        for _ in range(self.depth):
-            self._slots.append({
-                "x": torch.empty(x_h.shape, dtype=torch.float32, device=self.device),
-                "y": torch.empty(x_h.shape, dtype=torch.float32, device=self.device),
-                "cl": torch.empty(cl_h.shape, dtype=torch.float32, device=self.device),
-                "disp_h": torch.empty((b, 3 * hl, 3 * wl), dtype=torch.float32).pin_memory(),
-                "ready": torch.cuda.Event(), "free": torch.cuda.Event(), "done": torch.cuda.Event(),
-            })
-        self._n = 0
+    # ---- shapes -----------------------------------------------------------------------------------
+    def _shapes(self, feat_shape, cost_shape):
+        b, _, dl, hl, wl = cost_shape
+        return ({"x": tuple(feat_shape), "y": tuple(feat_shape), "cost_lr": tuple(cost_shape)}, {"disp": (b, 3 * hl, 3 * wl)})
 
-    def submit(self, x_h: torch.Tensor, y_h: torch.Tensor, cost_lr_h: torch.Tensor, keep_volume: bool = False):
-        """Enqueue one step.  Inputs are (pinned) HOST fp32 tensors: left/right features
-        [B,C,Hf,Wf] and the matching cost [B,1,Dl,Hl,Wl].  Returns the slot whose ``disp_h``
-        (pinned host [B,3Hl,3Wl]) is valid after ``slot['done'].synchronize()``."""
-        self._ensure(x_h, cost_lr_h)
+    def acquire(self, feat_shape, cost_shape) -> _Slot:
+        key = (tuple(feat_shape), tuple(cost_shape))
+        if self._slots is None or self._key != key:
+            self.drain()
+            sin, sout = self._shapes(feat_shape, cost_shape)
+            self._slots = [_Slot(sin, sout, self.device) for _ in range(self.depth)]
+            self._key, self._n = key, 0
         slot = self._slots[self._n % self.depth]
         self._n += 1
-        compute = torch.cuda.current_stream(self.device)
-        with torch.cuda.stream(self._copy):
-            self._copy.wait_event(slot["free"])    # previous user of this slot's device buffers finished
-            self._copy.wait_event(slot["done"])    # ... and its host result was copied out
-            slot["x"].copy_(x_h, non_blocking=True)
-            slot["y"].copy_(y_h, non_blocking=True)
-            slot["cl"].copy_(cost_lr_h, non_blocking=True)
-            slot["ready"].record(self._copy)
-        compute.wait_event(slot["ready"])
-        with torch.no_grad():
-            cost = self.cv(slot["x"], slot["y"])       # [B,2C,Df,Hf,Wf], stays on the device (Matching Net input)
-            disp = self.head(slot["cl"])
-        slot["free"].record(compute)
-        self._d2h.wait_event(slot["free"])
-        with torch.cuda.stream(self._d2h):
-            slot["disp_h"].copy_(disp, non_blocking=True)
-            disp.record_stream(self._d2h)
-            slot["done"].record(self._d2h)
-        if keep_volume:
-            slot["cost"] = cost
+        slot.done.synchronize()              # host may overwrite the staging buffer only after its last copy was issued AND consumed
         return slot
 
-    def run(self, x_h, y_h, cost_lr_h) -> torch.Tensor:
-        """Synchronous convenience call: returns the pinned host disparity map."""
-        slot = self.submit(x_h, y_h, cost_lr_h)
-        slot["done"].synchronize()
-        return slot["disp_h"]
+    # ---- the step ---------------------------------------------------------------------------------
+    def _compute(self, slot: _Slot, keep_volume: bool):
+        with torch.no_grad():
+            cost = F_.cost_volume_forward(slot.dev["x"], slot.dev["y"], int(self.maxdisp / 3))   # stays on the device (Matching Net input)
+            F_.disp_head_forward(slot.dev["cost_lr"], self.maxdisp, want_stats=False, out=slot.dev_out["disp"])   # straight into the result buffer
+        slot.keep = cost if keep_volume else None
+
+    def submit(self, slot: _Slot, keep_volume: bool = False) -> _Slot:
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy):
+            self._copy.wait_event(slot.free)      # the previous user of this slot's device buffers has finished
+            slot.d_in.copy_(slot.h_in, non_blocking=True)          # ONE cudaMemcpyAsync host->device
+            slot.ready.record(self._copy)
+        compute.wait_event(slot.ready)
+        compute.wait_event(slot.done)             # the previous result of this slot has left d_out
+        self._compute(slot, keep_volume)
+        slot.free.record(compute)
+        self._d2h.wait_event(slot.free)
+        with torch.cuda.stream(self._d2h):
+            slot.h_out.copy_(slot.d_out, non_blocking=True)        # ONE cudaMemcpyAsync device->host
+            slot.done.record(self._d2h)
+        return slot
+
+    def run(self, x_h: torch.Tensor, y_h: torch.Tensor, cost_lr_h: torch.Tensor) -> torch.Tensor:
+        """Synchronous convenience call for arbitrary host tensors (packs them into the staging buffer on the CPU):
+        returns the pinned host disparity map."""
+        slot = self.acquire(x_h.shape, cost_lr_h.shape)
+        slot.x.copy_(x_h), slot.y.copy_(y_h), slot.cost_lr.copy_(cost_lr_h)
+        self.submit(slot)
+        slot.done.synchronize()
+        return slot.result["disp"]
 
     def drain(self):
         for s in self._slots or []:
-            s["done"].synchronize()
+            s.done.synchronize()
+
+
+class HostTrainPipeline(HostPipeline):
+    """Training step from host buffers: forward + backward of both operators.  Host inputs per step: left/right features,
+    matching cost, and the upstream disparity gradient (what the masked loss produces from the ground truth); host
+    results: disparity, gradient w.r.t. the matching cost, gradients w.r.t. the two feature maps.  The upstream gradient
+    of the VOLUME ([B,2C,Df,Hf,Wf], 453 MB at B=4 288x576) is produced on the device by the Matching Net's backward in any
+    deployment and never crosses PCIe: it is passed as a device tensor (``gcost_dev``)."""
+
+    def _shapes(self, feat_shape, cost_shape):
+        b, _, dl, hl, wl = cost_shape
+        img = (b, 3 * hl, 3 * wl)
+        return ({"x": tuple(feat_shape), "y": tuple(feat_shape), "cost_lr": tuple(cost_shape), "gdisp": img},
+                {"disp": img, "gcost_lr": tuple(cost_shape), "gx": tuple(feat_shape), "gy": tuple(feat_shape)})
+
+    def submit(self, slot: _Slot, gcost_dev: torch.Tensor = None, keep_volume: bool = False) -> _Slot:   # noqa: D102
+        self._gcost = gcost_dev
+        return super().submit(slot, keep_volume)
+
+    def _compute(self, slot: _Slot, keep_volume: bool):
+        c = slot.dev["x"].shape[1]
+        with torch.no_grad():
+            cost = F_.cost_volume_forward(slot.dev["x"], slot.dev["y"], int(self.maxdisp / 3))
+            disp, stats = F_.disp_head_forward(slot.dev["cost_lr"], self.maxdisp, want_stats=True)
+            gcl = F_.disp_head_backward(slot.dev["cost_lr"], slot.dev["gdisp"], disp, stats, self.maxdisp)
+            gx, gy = F_.cost_volume_backward(self._gcost, c)
+            slot.dev_out["disp"].copy_(disp)
+            slot.dev_out["gcost_lr"].copy_(gcl)
+            slot.dev_out["gx"].copy_(gx)
+            slot.dev_out["gy"].copy_(gy)
+        slot.keep = cost if keep_volume else None

@@ -168,12 +168,66 @@ def test_host_pipeline_matches_oracle(dev):
 
     g = gen(35)
     md = 96
-    x, y = randn((2, 12, 8, 32), g).pin_memory(), randn((2, 12, 8, 32), g).pin_memory()
-    cl = randn((2, 1, 32, 8, 32), g).pin_memory()
+    x, y = randn((2, 12, 8, 32), g), randn((2, 12, 8, 32), g)
+    cl = randn((2, 1, 32, 8, 32), g)
     pipe = HostPipeline(md, dev)
-    slots = [pipe.submit(x, y, cl, keep_volume=True) for _ in range(3)]
+    slots = []
+    for i in range(5):                              # more steps than slots: the double buffering wraps around
+        slot = pipe.acquire(x.shape, cl.shape)
+        assert slot.x.is_pinned() and slot.h_in.is_pinned() and slot.x.data_ptr() == slot.h_in.data_ptr()
+        slot.x.copy_(x * (i + 1)), slot.y.copy_(y), slot.cost_lr.copy_(cl * (i + 1))
+        pipe.submit(slot, keep_volume=True)
+        slots.append(slot)
     pipe.drain()
-    ref = O.disp_head_ref(cl, md)
-    assert (slots[-1]["disp_h"] - ref).abs().max().item() <= 1e-4
-    assert torch.equal(slots[-1]["cost"].cpu(), O.cost_volume_ref(x, y, md))
-    assert torch.equal(pipe.run(x, y, cl), slots[-1]["disp_h"])
+    ref = O.disp_head_ref(cl * 5, md)
+    assert (slots[-1].result["disp"] - ref).abs().max().item() <= 1e-4
+    assert torch.equal(slots[-1].keep.cpu(), O.cost_volume_ref(x * 5, y, md))
+    assert slots[-1].h2d_bytes == 4 * (2 * x.numel() + cl.numel()) and slots[-1].d2h_bytes == 4 * ref.numel()
+    assert torch.equal(pipe.run(x * 5, y, cl * 5), slots[-1].result["disp"])
+
+
+def test_host_train_pipeline_matches_the_functions(dev):
+    from rag_b200 import functional as F_
+    from rag_b200.pipeline import HostTrainPipeline
+
+    g = gen(36)
+    md = 96
+    x, y = randn((2, 12, 8, 32), g), randn((2, 12, 8, 32), g)
+    cl = randn((2, 1, 32, 8, 32), g)
+    gd = randn((2, 24, 96), g)
+    gcost = randn((2, 24, 32, 8, 32), g).to(dev)
+    pipe = HostTrainPipeline(md, dev)
+    for _ in range(3):
+        slot = pipe.acquire(x.shape, cl.shape)
+        slot.x.copy_(x), slot.y.copy_(y), slot.cost_lr.copy_(cl), slot.gdisp.copy_(gd)
+        pipe.submit(slot, gcost)
+    pipe.drain()
+    disp, stats = F_.disp_head_forward(cl.to(dev), md, True)
+    gcl = F_.disp_head_backward(cl.to(dev), gd.to(dev), disp, stats, md)
+    gx, gy = F_.cost_volume_backward(gcost, 12)
+    r = slot.result
+    assert torch.equal(r["disp"], disp.cpu()) and torch.equal(r["gcost_lr"], gcl.cpu())
+    assert torch.equal(r["gx"], gx.cpu()) and torch.equal(r["gy"], gy.cpu())
+    gx_ref, gy_ref = O.cost_volume_grad_closed(gcost.cpu().numpy(), 12)
+    assert np.array_equal(r["gx"].numpy(), gx_ref) and np.array_equal(r["gy"].numpy(), gy_ref)
+
+
+def test_overlapped_train_path_matches_the_serial_functions(dev):
+    from rag_b200 import functional as F_
+    from rag_b200.pipeline import OverlappedTrainPath
+
+    g = gen(37)
+    md = 96
+    op = OverlappedTrainPath(md, dev)
+    x, y = randn((2, 12, 9, 64), g).to(dev), randn((2, 12, 9, 64), g).to(dev)
+    cl = randn((2, 1, 32, 9, 64), g).to(dev)
+    gd = randn((2, 27, 192), g).to(dev)
+    gcost = randn((2, 24, 32, 9, 64), g).to(dev)
+    outs = [op.step(x, y, cl, gcost, gd) for _ in range(10)]
+    op.join()
+    torch.cuda.synchronize()
+    disp, stats = F_.disp_head_forward(cl, md, True)
+    want = (F_.cost_volume_forward(x, y, md // 3, variant=0), disp, F_.disp_head_backward(cl, gd, disp, stats, md)) + F_.cost_volume_backward(gcost, 12, variant=1)
+    for o in outs:
+        for a, b_ in zip(o, want):
+            assert torch.equal(a, b_)
