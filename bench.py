@@ -463,7 +463,58 @@ def next_rows_record(x, y, df, md, sub):
     return rows
 
 
-EXTRA_NEXT_ROWS = []     # (name, fn(dev) -> dict): rows added as they are built (training-mode stem, upsample_6/12, ...)
+def stem_train_row(dev):
+    """SURVEY.md section 8f rank 1, training: cost volume + stem3d0 = Conv3d(24->12) + BatchNorm3d(train) + ReLU, forward + backward
+    at BASELINE configs[2] (B=4, 288x576).  Fused (rag_b200.fused_stem.FusedStemFn: no volume, no volume gradient, no conv output)
+    vs the reference composition on the materialised volume through cuDNN (TF32, its default)."""
+    import torch
+
+    from rag_b200.functional import cost_volume
+    from rag_b200.fused_stem import VirtualCostVolume, stem_forward
+
+    class Layer(torch.nn.Module):                       # the fields of the reference's ConvBR_3d (operations_3d.py:31-47)
+        def __init__(self):
+            super().__init__()
+            self.relu, self.use_bn = True, True
+            self.conv = torch.nn.Conv3d(24, 12, 3, 1, 1, bias=False)
+            self.bn = torch.nn.BatchNorm3d(12)
+
+    b, hf, wf, md = 4, 96, 192, 192
+    g = torch.Generator(device=dev).manual_seed(3)
+    layer = Layer().to(dev).train()
+    x = torch.randn(b, 12, hf, wf, device=dev, generator=g, requires_grad=True)
+    y = torch.randn(b, 12, hf, wf, device=dev, generator=g, requires_grad=True)
+    gout = torch.randn(b, 12, md // 3, hf, wf, device=dev, generator=g)
+
+    def fused():
+        stem_forward(layer, VirtualCostVolume(x, y, md)).backward(gout)
+
+    def ref():
+        torch.relu(layer.bn(layer.conv(cost_volume(x, y, md)))).backward(gout)
+
+    def t(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        torch.cuda.reset_peak_memory_stats(dev)
+        base = torch.cuda.memory_allocated(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n, (torch.cuda.max_memory_allocated(dev) - base) / 2**20
+
+    f_ms, f_mem = t(fused, 10)
+    r_ms, r_mem = t(ref, 3)
+    return {"what": "cost volume + stem3d0 (Conv3d 24->12 3x3x3 + BatchNorm3d(train) + ReLU), forward + backward, B=4 288x576",
+            "fused_ms": round(f_ms, 4), "cost_volume_plus_cudnn_tf32_ms": round(r_ms, 4), "speedup": round(r_ms / f_ms, 1),
+            "fused_peak_extra_MiB": round(f_mem), "cudnn_peak_extra_MiB": round(r_mem),
+            "parity": "tests/test_fused_stem_gpu.py: every gradient within 1e-5 max-norm of the fp64 evaluation (ReLU mask fixed)"}
+
+
+EXTRA_NEXT_ROWS = [("stem3d0_train", stem_train_row)]     # (name, fn(dev) -> dict): rows added as they are built
 
 
 def run_gpu(args):

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RAG_B200_ABI_VERSION 8
+#define RAG_B200_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
@@ -178,6 +178,27 @@ RAG_API int rag_cv_stem_fwd_v(const float* x, const float* y, const float* w, co
  * workspace: as for rag_cv_stem_fwd (nullable). */
 RAG_API int rag_cv_stem_moments(const float* x, const float* y, const float* w, double* moments,
                         int B, int C, int O, int Df, int Hf, int Wf, void* workspace, void* stream);
+
+/* Backward of that fused layer (training) -- again without the volume, its gradient, or any other
+ * [B,2C,Df,Hf,Wf] tensor.  Replaces the autograd of src/models/rag_model.py:375-383 + ConvBR_3d (operations_3d.py:31-47:
+ * Conv3d -> BatchNorm3d -> ReLU) for BatchNorm in train() (batch statistics) or eval() (running statistics).
+ * g   [B,O,Df,Hf,Wf]  upstream gradient of the layer output
+ * pre [B,O,Df,Hf,Wf]  the layer's pre-activation gamma*zh + beta (rag_cv_stem_fwd with relu = 0 and the forward's
+ *                     scale/shift; the host side recomputes it for the backward instead of keeping it alive)
+ * Step 1, rag_cv_stem_bn_bwd_sums: sums [O,2] DOUBLE = (sum g', sum g'*zh) over (B,Df,Hf,Wf), g' = g [pre > 0],
+ *   zh = (pre - beta[o]) * ginv[o] (ginv = 1/gamma) -- the BatchNorm weight/bias gradients and the two means of the
+ *   train-mode BatchNorm backward.  rows_ws: DOUBLE workspace [B*Hf*O*2].  Deterministic (fixed-order fp64).
+ * Step 2, rag_cv_stem_bwd: consts [O,5] = (a, m1, m2, beta, 1/gamma) with a = gamma*rstd and, in train mode,
+ *   m1 = sums[o,0]/n, m2 = sums[o,1]/n (n = B*Df*Hf*Wf), in eval mode m1 = m2 = 0; the gradient at the convolution output
+ *   gz = a (g' - m1 - zh m2) is formed on the fly and reduced along d into the 2-D maps the transpose needs, then
+ *   gx, gy [B,C,Hf,Wf] (both or neither; need w) and gw [O,2C,3,3,3] (nullable; needs x, y) are 2-D contractions.
+ *   workspace: rag_cv_stem_bwd_workspace_bytes(B,C,O,Hf,Wf) bytes, 16-byte aligned, caller-owned.
+ * Needs C == 12, O <= 32, Df >= 3, 8 <= Wf <= 1016, Wf % 4 == 0. */
+RAG_API int rag_cv_stem_bn_bwd_sums(const float* g, const float* pre, const float* beta, const float* ginv, double* sums,
+                            double* rows_ws, int B, int O, int Df, int Hf, int Wf, void* stream);
+RAG_API size_t rag_cv_stem_bwd_workspace_bytes(int B, int C, int O, int Hf, int Wf);
+RAG_API int rag_cv_stem_bwd(const float* g, const float* pre, const float* consts, const float* x, const float* y, const float* w,
+                    float* gx, float* gy, float* gw, void* workspace, int B, int C, int O, int Df, int Hf, int Wf, void* stream);
 
 /* The Matching Net's last layer, the producer of the head's input (inference):
  * `self.last_3_3d[i](...)` = ConvBR_3d(C, 1, 3, 1, 1, bn=False, relu=False), src/models/rag_model.py:269,361-365,

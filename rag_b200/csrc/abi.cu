@@ -20,6 +20,9 @@ int cv_stem_fwd(const float*, const float*, const float*, const float*, const fl
 size_t cv_stem_workspace_bytes(int, int);
 int cv_stem_moments(const float*, const float*, const float*, double*, int, int, int, int, int, int, float*, cudaStream_t);
 int conv3d_c1_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+int cv_stem_bn_bwd_sums(const float*, const float*, const float*, const float*, double*, double*, int, int, int, int, int, cudaStream_t);
+size_t cv_stem_bwd_workspace_bytes(int, int, int, int, int);
+int cv_stem_bwd(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
 }  // namespace rag
 
 using namespace rag;
@@ -97,6 +100,15 @@ RAG_API int rag_cv_stem_moments(const float* x, const float* y, const float* w, 
 RAG_API int rag_cv_stem_fwd_v(const float* x, const float* y, const float* w, const float* scale, const float* shift,
                       int relu, float* out, int B, int C, int O, int Df, int Hf, int Wf, void* workspace, int variant, void* stream) {
     return cv_stem_fwd(x, y, w, scale, shift, relu, out, B, C, O, Df, Hf, Wf, static_cast<float*>(workspace), variant, ST(stream));
+}
+RAG_API int rag_cv_stem_bn_bwd_sums(const float* g, const float* pre, const float* beta, const float* ginv, double* sums,
+                            double* rows_ws, int B, int O, int Df, int Hf, int Wf, void* stream) {
+    return cv_stem_bn_bwd_sums(g, pre, beta, ginv, sums, rows_ws, B, O, Df, Hf, Wf, ST(stream));
+}
+RAG_API size_t rag_cv_stem_bwd_workspace_bytes(int B, int C, int O, int Hf, int Wf) { return cv_stem_bwd_workspace_bytes(B, C, O, Hf, Wf); }
+RAG_API int rag_cv_stem_bwd(const float* g, const float* pre, const float* consts, const float* x, const float* y, const float* w,
+                    float* gx, float* gy, float* gw, void* workspace, int B, int C, int O, int Df, int Hf, int Wf, void* stream) {
+    return cv_stem_bwd(g, pre, consts, x, y, w, gx, gy, gw, static_cast<float*>(workspace), B, C, O, Df, Hf, Wf, ST(stream));
 }
 RAG_API int rag_conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int D, int H, int W, void* stream) {
     return conv3d_c1_fwd(in, w, out, B, C, D, H, W, ST(stream));

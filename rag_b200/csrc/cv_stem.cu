@@ -548,7 +548,7 @@ int cv_stem_moments(const float* x, const float* y, const float* w, double* mome
                          (size_t)kStemStages * 3 * nt * sizeof(float2);
     if (smem2 > 200 * 1024) return fail(RAG_E_SHAPE, "cv_stem_moments: Wf=%d too wide for shared memory", Wf);
     auto kern = cv_stem_fwd2_kernel<12, false, true>;
-    if (smem2 > 48 * 1024) {
+    if (smem2 + 8192 > 48 * 1024) {                  // + the kernel's 8 KB of static shared memory (fp64 reduction buffers)
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         if (e != cudaSuccess) return fail((int)e, "cv_stem_moments: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }

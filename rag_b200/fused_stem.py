@@ -1,4 +1,4 @@
-"""Fused cost volume + first Matching-Net layer, inference only.
+"""Fused cost volume + first Matching-Net layer, inference AND training.
 
 The reference builds the [B,2C,Df,Hf,Wf] volume (rag_model.py:375-383) and immediately feeds it to
 ``self.stem3d0[i]`` = ConvBR_3d(2C->C, 3x3x3) (rag_model.py:341, operations_3d.py:31-47).  Because the
@@ -8,9 +8,12 @@ the layer's 51 GFLOP/pair become ~10 FMA per output.
 
 Drop-in mechanism: ``cost_volume_lazy`` returns a ``VirtualCostVolume`` (just the two feature tensors);
 ``stem_forward`` -- bound onto ``ConvBR_3d.forward`` by ``rag_b200.network.install`` -- recognises it and
-runs the fused kernel (conv + folded eval-mode BN + ReLU).  Whenever the fusion does not apply
-(autograd needed, BatchNorm in training mode, a different conv geometry) the volume is materialised with
-the cost-volume kernel and the layer runs as in the reference.
+runs the fused kernel (conv + folded BatchNorm + ReLU).  With autograd the layer runs as ``FusedStemFn``: batch
+statistics from the collapsed row maps, the forward kernel, and a backward that rebuilds the gradient at the
+convolution output on the fly and reduces it along the disparity axis (csrc/cv_stem_train.cu) -- neither the
+volume, nor its gradient, nor the convolution output are ever held.  Whenever the fusion does not apply (a
+different conv geometry, no BatchNorm / ReLU, affine-free BatchNorm) the volume is materialised with the
+cost-volume kernel and the layer runs as in the reference.
 """
 from __future__ import annotations
 
@@ -104,6 +107,97 @@ def cv_stem_batch_stats(x, y, weight, maxdisp=192):
     return mean, s[:, 1] / n - mean * mean, n
 
 
+class FusedStemFn(torch.autograd.Function):
+    """out = relu(batchnorm(conv3d(cost_volume(x, y), weight))) with gradients w.r.t. x, y, weight, gamma, beta.
+
+    ``mean`` / ``rstd`` [O] fp32 are the statistics the BatchNorm normalises with (batch statistics in train(), running
+    ones in eval()); ``batch_stats`` says which (it decides whether the mean terms of the BatchNorm backward apply).
+    Saved for the backward: the two feature maps, the weight, four [O] vectors -- no [B,*,Df,Hf,Wf] tensor: the layer's
+    pre-activation is RECOMPUTED by the forward kernel inside ``backward`` into a temporary."""
+
+    @staticmethod
+    def forward(ctx, x, y, weight, gamma, beta, mean, rstd, batch_stats, maxdisp):
+        scale = gamma * rstd
+        shift = beta - mean * scale
+        out = cv_stem_forward(x, y, weight, scale, shift, True, maxdisp)
+        ctx.save_for_backward(x, y, weight, gamma, beta, scale, shift, rstd)
+        ctx.batch_stats, ctx.maxdisp = bool(batch_stats), maxdisp
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, y, weight, gamma, beta, scale, shift, rstd = ctx.saved_tensors
+        g = g.contiguous()
+        b, c, hf, wf = x.shape
+        o = weight.shape[0]
+        df = g.shape[2]
+        n = b * df * hf * wf
+        dev = x.device
+        L = _cabi.lib()
+        need_in = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        need_w = ctx.needs_input_grad[2]
+        with torch.cuda.device(dev):
+            pre = cv_stem_forward(x, y, weight, scale, shift, False, ctx.maxdisp)       # temporary: gamma*zh + beta
+            ginv = torch.where(gamma != 0, 1.0 / gamma, torch.zeros_like(gamma)).contiguous()
+            betac = beta.contiguous()
+            sums = torch.empty((o, 2), dtype=torch.float64, device=dev)
+            rows = torch.empty((b * hf * o * 2,), dtype=torch.float64, device=dev)
+            rc = L.rag_cv_stem_bn_bwd_sums(g.data_ptr(), pre.data_ptr(), betac.data_ptr(), ginv.data_ptr(), sums.data_ptr(), rows.data_ptr(),
+                                           b, o, df, hf, wf, _stream(x))
+            _cabi.check(rc, "rag_cv_stem_bn_bwd_sums")
+            gbeta = sums[:, 0].to(torch.float32)
+            ggamma = sums[:, 1].to(torch.float32)
+            gx = gy = gw = None
+            if need_in or need_w:
+                m = (sums / n).to(torch.float32) if ctx.batch_stats else torch.zeros((o, 2), dtype=torch.float32, device=dev)
+                consts = torch.stack([scale, m[:, 0], m[:, 1], betac, ginv], dim=1).contiguous()
+                ws = torch.empty(int(L.rag_cv_stem_bwd_workspace_bytes(b, c, o, hf, wf)) // 4, dtype=torch.float32, device=dev)
+                if need_in:
+                    gx, gy = torch.empty_like(x), torch.empty_like(y)
+                if need_w:
+                    gw = torch.empty_like(weight)
+                rc = L.rag_cv_stem_bwd(g.data_ptr(), pre.data_ptr(), consts.data_ptr(), x.data_ptr(), y.data_ptr(), weight.data_ptr(),
+                                       gx.data_ptr() if gx is not None else None, gy.data_ptr() if gy is not None else None,
+                                       gw.data_ptr() if gw is not None else None, ws.data_ptr(), b, c, o, df, hf, wf, _stream(x))
+                _cabi.check(rc, "rag_cv_stem_bwd")
+        return (gx if ctx.needs_input_grad[0] else None, gy if ctx.needs_input_grad[1] else None, gw,
+                ggamma if ctx.needs_input_grad[3] else None, gbeta if ctx.needs_input_grad[4] else None, None, None, None, None)
+
+
+def _train_fusable(self, vol: VirtualCostVolume) -> bool:
+    """The layer csrc/cv_stem_train.cu differentiates: Conv3d(2*12 -> O <= 32, 3x3x3) + affine BatchNorm3d + ReLU on a volume
+    with Wf % 4 == 0, 8 <= Wf <= 1016 and Df >= 3."""
+    bn = self.bn
+    b, c, hf, wf = vol.x.shape
+    return (self.use_bn and bool(self.relu) and isinstance(bn, nn.BatchNorm3d) and bn.affine and bn.weight.dtype == torch.float32
+            and (bn.training or bn.track_running_stats) and c == 12 and self.conv.out_channels <= 32
+            and wf % 4 == 0 and 8 <= wf <= 1016 and int(vol.maxdisp / 3) >= 3 and hf <= 65535 and b <= 32767)
+
+
+def stem_train_forward(self, vol: VirtualCostVolume) -> torch.Tensor:
+    """ConvBR_3d.forward on a VirtualCostVolume with autograd (train() or eval() BatchNorm), fused.  Updates the running
+    statistics exactly like nn.BatchNorm3d does in train() (momentum / cumulative average, unbiased variance)."""
+    bn = self.bn
+    x, y, w = vol.x.contiguous(), vol.y.contiguous(), self.conv.weight
+    use_batch = bn.training or not bn.track_running_stats
+    if use_batch:
+        mean64, var64, n = cv_stem_batch_stats(x.detach(), y.detach(), w.detach(), vol.maxdisp)
+        if bn.training and bn.track_running_stats:
+            with torch.no_grad():
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked.add_(1)
+                f = (1.0 / float(bn.num_batches_tracked)) if bn.momentum is None else bn.momentum
+                bn.running_mean.mul_(1 - f).add_(mean64.to(bn.running_mean.dtype), alpha=f)
+                bn.running_var.mul_(1 - f).add_((var64 * (n / max(n - 1, 1))).to(bn.running_var.dtype), alpha=f)
+        mean = mean64.to(torch.float32)
+        rstd = torch.rsqrt(var64 + bn.eps).to(torch.float32)
+    else:
+        mean = bn.running_mean
+        rstd = torch.rsqrt(bn.running_var + bn.eps)
+    return FusedStemFn.apply(x, y, w, bn.weight, bn.bias, mean, rstd, use_batch, vol.maxdisp)
+
+
 def _fusable(conv: nn.Conv3d, vol: VirtualCostVolume) -> bool:
     return (isinstance(conv, nn.Conv3d) and conv.bias is None and conv.kernel_size == (3, 3, 3) and conv.stride == (1, 1, 1)
             and conv.padding == (1, 1, 1) and conv.dilation == (1, 1, 1) and conv.groups == 1
@@ -122,8 +216,12 @@ def stem_forward(self, x):
     needs_grad = torch.is_grad_enabled() and (x.x.requires_grad or x.y.requires_grad
                                               or any(p.requires_grad for p in self.parameters()))
     bn_batch_stats = self.use_bn and (self.bn.training or not self.bn.track_running_stats)
-    if needs_grad or not _fusable(self.conv, x):
+    if not _fusable(self.conv, x):
         return stem_forward(self, x.materialize())          # the reference's path on the materialised volume
+    if needs_grad:
+        if _train_fusable(self, x):
+            return stem_train_forward(self, x)               # fused forward + volume-free backward (csrc/cv_stem_train.cu)
+        return stem_forward(self, x.materialize())
     if bn_batch_stats:                                       # conv fused, BatchNorm with batch statistics by torch
         out = cv_stem_forward(x.x, x.y, self.conv.weight, maxdisp=x.maxdisp)
         out = self.bn(out)

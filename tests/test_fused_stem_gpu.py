@@ -247,3 +247,201 @@ def test_batch_stats_match_the_reference_running_stat_update():
     var1 = (1 - mom) * torch.from_numpy(z["bn_var0"]).double() + mom * var.cpu() * n / (n - 1)
     np.testing.assert_allclose(mean1.numpy(), z["bn_mean1"], rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(var1.numpy(), z["bn_var1"], rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# training: fused forward + volume-free backward (csrc/cv_stem_train.cu, rag_b200.fused_stem.FusedStemFn)
+# ---------------------------------------------------------------------------------------------------------------------
+def _mx(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def ref_stem_masked(x, y, layer, maxdisp, mask):
+    """The reference composition with the ReLU decision GIVEN (mask = out > 0 of the run under test) and the pre-activation
+    returned next to the output.  A gradient through a ReLU is discontinuous in its input: two evaluations that differ by
+    one ulp disagree on the handful of elements whose pre-activation is ~0 (7e7 elements at B=4 288x576 -> a few flips, each
+    worth O(1) in max-norm), which says nothing about either evaluation's arithmetic.  So: arithmetic is compared with the
+    mask fixed, and the mask itself is checked separately (it may differ from the fp64 one only where |pre| is rounding noise)."""
+    pre = layer.bn(layer.conv(O.cost_volume_ref(x, y, maxdisp)))
+    return pre * mask.to(pre.dtype), pre
+
+
+def test_training_stem_matches_the_reference_golden():
+    """tests/golden/trainstem_*.npz: the reference's own ConvBR_3d(2C, C, 3, 1, 1) in train() on the volume its
+    Network.forward builds -- output, gradients w.r.t. both feature maps, the conv weight and the BatchNorm affine
+    parameters, running statistics after the step (CPU fp32).  1e-5 max-norm (SURVEY.md section 8a H-3 reading)."""
+    import os
+
+    import numpy as np
+
+    from rag_b200.fused_stem import VirtualCostVolume, stem_forward
+    from tests.conftest import GOLDEN
+
+    z = np.load(os.path.join(GOLDEN, "trainstem_b2_c12_h5_w12_md24.npz"))
+    t = lambda k: torch.from_numpy(z[k]).cuda()  # noqa: E731
+    md = int(z["maxdisp"])
+    layer = ConvBR_3d(24, 12).cuda().train()
+    layer.bn.eps, layer.bn.momentum = float(z["bn_eps"]), float(z["bn_momentum"])
+    with torch.no_grad():
+        layer.conv.weight.copy_(t("weight")); layer.bn.weight.copy_(t("bn_weight")); layer.bn.bias.copy_(t("bn_bias"))
+        layer.bn.running_mean.copy_(t("bn_mean0")); layer.bn.running_var.copy_(t("bn_var0"))
+    x, y = t("x").requires_grad_(True), t("y").requires_grad_(True)
+    out = stem_forward(layer, VirtualCostVolume(x, y, md))
+    assert out.grad_fn is not None and "FusedStemFn" in type(out.grad_fn).__name__
+    out.backward(t("gout"))
+    tol = 1e-5
+    assert _mx(out.detach(), t("out")) <= tol
+    for got, key in ((x.grad, "gx"), (y.grad, "gy"), (layer.conv.weight.grad, "gweight"), (layer.bn.weight.grad, "gbn_weight"),
+                     (layer.bn.bias.grad, "gbn_bias")):
+        assert _mx(got, t(key)) <= tol, f"{key}: {_mx(got, t(key)):.3e}"
+    np.testing.assert_allclose(layer.bn.running_mean.cpu().numpy(), z["bn_mean1"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(layer.bn.running_var.cpu().numpy(), z["bn_var1"], rtol=1e-5, atol=1e-6)
+    assert int(layer.bn.num_batches_tracked) == 1
+
+
+TRAIN_SHAPES = [
+    # (B, Hf, Wf, maxdisp, O)
+    (2, 6, 40, 48, 12),       # Df = 16
+    (1, 5, 96, 192, 12),      # Df = 64
+    (1, 3, 12, 48, 12),       # Wf < Df: mostly masked
+    (2, 4, 416, 288, 5),      # config-5 width (4 column chunks), O != C, Df = 96
+    (1, 4, 16, 9, 12),        # Df = 3: no interior d
+    (1, 9, 132, 96, 32),      # Wf just over one 128-column chunk, O = 32
+]
+
+
+@pytest.mark.parametrize("shape", TRAIN_SHAPES, ids=str)
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_training_stem_forward_backward_vs_fp64(shape, mode):
+    """Fused layer vs the materialised composition evaluated in fp64 on the GPU (volume -> Conv3d -> BatchNorm3d -> ReLU, autograd)
+    and vs the same composition in fp32 (what the reference runs): ours must be within 1e-5 max-norm of fp64 on every gradient,
+    i.e. no further from the truth than the fp32 reference is."""
+    from rag_b200.fused_stem import VirtualCostVolume, stem_forward
+
+    b, hf, wf, md, o = shape
+    g = gen(hash((shape, mode)) % 997)
+    layer = ConvBR_3d(24, o).cuda()
+    with torch.no_grad():
+        layer.bn.weight.copy_(0.5 + torch.rand(o, generator=g)); layer.bn.bias.copy_(0.3 * torch.randn(o, generator=g))
+        layer.bn.running_mean.copy_(0.2 * torch.randn(o, generator=g)); layer.bn.running_var.copy_(0.5 + torch.rand(o, generator=g))
+    layer.train(mode == "train")
+    x0, y0 = randn((b, 12, hf, wf), g).cuda(), randn((b, 12, hf, wf), g).cuda()
+    gout = randn((b, o, int(md / 3), hf, wf), g).cuda()
+    gout = gout * (torch.rand(gout.shape, generator=g).cuda() < 0.7)           # some exact zeros upstream
+    state = copy.deepcopy(layer.state_dict())
+
+    def run(fn, dtype):
+        lay = copy.deepcopy(layer).to(dtype)
+        lay.load_state_dict({k: v.to(dtype) if v.is_floating_point() else v for k, v in state.items()})
+        x, y = x0.to(dtype).clone().requires_grad_(True), y0.to(dtype).clone().requires_grad_(True)
+        out = fn(lay, x, y)
+        pre = None
+        if isinstance(out, tuple):
+            out, pre = out
+        out.backward(gout.to(dtype))
+        return [out.detach(), x.grad, y.grad, lay.conv.weight.grad, lay.bn.weight.grad, lay.bn.bias.grad, lay.bn.running_mean, lay.bn.running_var], pre
+
+    ours, _ = run(lambda lay, x, y: stem_forward(lay, VirtualCostVolume(x, y, md)), torch.float32)
+    mask = ours[0] > 0
+    ref64, pre64 = run(lambda lay, x, y: ref_stem_masked(x, y, lay, md, mask), torch.float64)
+    ref32, _ = run(lambda lay, x, y: ref_stem_masked(x, y, lay, md, mask), torch.float32)
+    flips = (pre64.detach() > 0) != mask
+    assert not flips.any() or pre64.detach()[flips].abs().max().item() <= 1e-5, "the ReLU decision differs from fp64 beyond rounding noise"
+    names = ["out", "gx", "gy", "gweight", "ggamma", "gbeta", "running_mean", "running_var"]
+    for n, a, r32, r64 in zip(names, ours, ref32, ref64):
+        e_ours, e_ref = _mx(a, r64), _mx(r32, r64)
+        assert e_ours <= 1e-5, f"{n}: ours vs fp64 {e_ours:.3e} (fp32 reference vs fp64: {e_ref:.3e})"
+
+
+def test_training_stem_partial_gradients_and_determinism():
+    """Frozen weight (only the feature maps want a gradient), frozen features (only the layer's parameters), and bitwise
+    repeatability of the whole backward (fixed-order reductions, no atomics)."""
+    from rag_b200.fused_stem import VirtualCostVolume, stem_forward
+
+    g = gen(5)
+    md = 96
+    layer = ConvBR_3d(24, 12).cuda().train()
+    x0, y0 = randn((2, 12, 7, 64), g).cuda(), randn((2, 12, 7, 64), g).cuda()
+    gout = randn((2, 12, 32, 7, 64), g).cuda()
+    state = copy.deepcopy(layer.state_dict())
+
+    def run(req_in, req_par):
+        layer.load_state_dict(state)
+        layer.zero_grad(set_to_none=True)
+        for p in layer.parameters():
+            p.requires_grad_(req_par)
+        x, y = x0.clone().requires_grad_(req_in), y0.clone().requires_grad_(req_in)
+        out = stem_forward(layer, VirtualCostVolume(x, y, md))
+        out.backward(gout)
+        return x.grad, y.grad, layer.conv.weight.grad, layer.bn.weight.grad, layer.bn.bias.grad
+
+    full = run(True, True)
+    again = run(True, True)
+    for a, b_ in zip(full, again):
+        assert torch.equal(a, b_)
+    only_in = run(True, False)
+    assert torch.equal(only_in[0], full[0]) and torch.equal(only_in[1], full[1]) and only_in[2] is None and only_in[3] is None
+    only_par = run(False, True)
+    assert only_par[0] is None and all(torch.equal(a, b_) for a, b_ in zip(only_par[2:], full[2:]))
+    for p in layer.parameters():
+        p.requires_grad_(True)
+
+
+def test_training_stem_at_the_training_config_without_the_volume():
+    """BASELINE config 3 (B=4, 288x576): parity with the PyTorch CUDA layers on the materialised volume (fp32, TF32 off) and
+    the memory the step needs: the fused path must never hold a [B,24,Df,Hf,Wf]-sized tensor (453 MB here)."""
+    from rag_b200 import functional as F_
+    from rag_b200.fused_stem import VirtualCostVolume, stem_forward
+
+    b, hf, wf, md, o = 4, 96, 192, 192, 12
+    g = gen(6)
+    layer = ConvBR_3d(24, o).cuda().train()
+    x0, y0 = randn((b, 12, hf, wf), g).cuda(), randn((b, 12, hf, wf), g).cuda()
+    gout = randn((b, o, 64, hf, wf), g).cuda()
+    state = copy.deepcopy(layer.state_dict())
+    vol_bytes = b * 24 * 64 * hf * wf * 4
+
+    def run(fn):
+        layer.load_state_dict(state)
+        layer.zero_grad(set_to_none=True)
+        x, y = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        out = fn(x, y)
+        out.backward(gout)
+        torch.cuda.synchronize()
+        peak = torch.cuda.max_memory_allocated() - base
+        res = [out.detach().clone(), x.grad, y.grad, layer.conv.weight.grad.clone(), layer.bn.weight.grad.clone(), layer.bn.bias.grad.clone(),
+               layer.bn.running_mean.clone(), layer.bn.running_var.clone()]
+        del out
+        return res, peak
+
+    ref, ref_peak = run(lambda x, y: ConvBR_3d.forward(layer, F_.cost_volume(x, y, md)))
+    ours, our_peak = run(lambda x, y: stem_forward(layer, VirtualCostVolume(x, y, md)))
+    names = ["out", "gx", "gy", "gweight", "ggamma", "gbeta", "running_mean", "running_var"]
+    for n in (0, 6, 7):                                     # forward quantities: directly comparable
+        assert _mx(ours[n], ref[n]) <= 1e-5, f"{names[n]}: {_mx(ours[n], ref[n]):.3e}"
+    # backward: the ReLU decisions of the two fp32 forwards disagree on a few of the 7e7 elements (pre-activation ~ 0), each worth
+    # O(1e-2) of max-norm in gx/gy -- so the arithmetic is compared with the mask FIXED to ours, against fp64 (see ref_stem_masked)
+    mask = ours[0] > 0
+    n_flip = int(((ref[0] > 0) != mask).sum())
+    assert n_flip <= 200, n_flip
+    lay64 = copy.deepcopy(layer).double()
+    lay64.load_state_dict({k: v.double() if v.is_floating_point() else v for k, v in state.items()})
+    x64, y64 = x0.double().requires_grad_(True), y0.double().requires_grad_(True)
+    out64, pre64 = ref_stem_masked(x64, y64, lay64, md, mask)
+    out64.backward(gout.double())
+    flips = (pre64.detach() > 0) != mask
+    assert not flips.any() or pre64.detach()[flips].abs().max().item() <= 1e-5
+    want = [out64.detach(), x64.grad, y64.grad, lay64.conv.weight.grad, lay64.bn.weight.grad, lay64.bn.bias.grad]
+    errs = {n: _mx(a, r) for n, a, r in zip(names, ours, want)}
+    for n, e in errs.items():
+        assert e <= 1e-5, f"{n}: {e:.3e} vs fp64 with the same ReLU mask"
+    print(f"\ntraining stem at B=4 288x576 vs fp64 (mask fixed): {errs}; ReLU decisions differing from the fp32 cuDNN forward: {n_flip} of {mask.numel()}")
+    del lay64, x64, y64, out64, pre64, want
+    # out (226 MB) + the recomputed pre-activation (226 MB) + maps/partials: well under the volume + conv output + their gradients
+    assert our_peak < 0.45 * ref_peak, (our_peak, ref_peak)
+    assert our_peak < 3 * vol_bytes // 2 + (64 << 20), (our_peak, vol_bytes)
+    print(f"\ntraining stem at B=4 288x576: peak extra memory fused {our_peak / 2**20:.0f} MiB vs materialised {ref_peak / 2**20:.0f} MiB")
