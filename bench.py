@@ -514,7 +514,47 @@ def stem_train_row(dev):
             "parity": "tests/test_fused_stem_gpu.py: every gradient within 1e-5 max-norm of the fp64 evaluation (ReLU mask fixed)"}
 
 
-EXTRA_NEXT_ROWS = [("stem3d0_train", stem_train_row)]     # (name, fn(dev) -> dict): rows added as they are built
+def tail_rows(dev):
+    """SURVEY.md section 8f rank 2, training: upsample_6 (trilinear, align_corners=True) forward + backward and the backward of
+    last_3_3d at BASELINE configs[2] (B=4, 288x576), beside ATen / cuDNN (TF32 default)."""
+    import torch
+    import torch.nn.functional as F
+
+    from rag_b200.last_conv import Conv3dC1Fn
+    from rag_b200.upsample import trilinear_resize
+
+    b, c, d, h, w = 4, 12, 64, 96, 192
+    g = torch.Generator(device=dev).manual_seed(4)
+
+    def t(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    x = torch.randn(b, c, d // 2, h // 2, w // 2, device=dev, generator=g, requires_grad=True)
+    go = torch.randn(b, c, d, h, w, device=dev, generator=g)
+    ours = t(lambda: trilinear_resize(x, (d, h, w), True).backward(go), 10)
+    aten = t(lambda: F.interpolate(x, (d, h, w), mode="trilinear", align_corners=True).backward(go), 5)
+    feat = torch.randn(b, c, d, h, w, device=dev, generator=g, requires_grad=True)
+    wt = (torch.randn(1, c, 3, 3, 3, device=dev, generator=g) * 0.1).requires_grad_(True)
+    g1 = torch.randn(b, 1, d, h, w, device=dev, generator=g)
+    conv_ours = t(lambda: Conv3dC1Fn.apply(feat, wt).backward(g1), 10)
+    conv_ref = t(lambda: F.conv3d(feat, wt, padding=1).backward(g1), 3)
+    return {"upsample_6": {"what": "nn.Upsample trilinear align_corners=True [4,12,32,48,96] -> [4,12,64,96,192], forward + backward",
+                           "ms": round(ours, 4), "aten_ms": round(aten, 4), "speedup": round(aten / ours, 1),
+                           "note": "backward is a deterministic gather (ATen: atomicAdd scatter)"},
+            "last_3_3d_train": {"what": "last_3_3d (Conv3d 12->1 3x3x3) forward + backward (data + weight gradient), B=4 288x576",
+                                "ms": round(conv_ours, 4), "cudnn_tf32_ms": round(conv_ref, 4), "speedup": round(conv_ref / conv_ours, 1)}}
+
+
+EXTRA_NEXT_ROWS = [("stem3d0_train", stem_train_row), ("tail_train", tail_rows)]     # (name, fn(dev) -> dict)
 
 
 def run_gpu(args):

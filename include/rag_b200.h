@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RAG_B200_ABI_VERSION 9
+#define RAG_B200_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
@@ -205,9 +205,27 @@ RAG_API int rag_cv_stem_bwd(const float* g, const float* pre, const float* const
  * i.e. a bias-free Conv3d C -> 1, 3x3x3, stride 1, zero padding 1 (src/automl/operations_3d.py:31-47):
  *   out[b,0,d,h,w] = sum_{c,kd,kh,kw} w[0,c,kd,kh,kw] * in[b,c,d+kd-1,h+kh-1,w+kw-1]
  * in [B,C,D,H,W]; w [1,C,3,3,3] (Conv3d.weight); out [B,1,D,H,W].  fp32 accumulation (cuDNN's default for
- * this layer is TF32).  Needs W % 4 == 0, C <= 64, B*ceil(D/16) <= 65535 and 16-byte aligned in/out.  Forward only.
+ * this layer is TF32).  Needs W % 4 == 0, C <= 64, B*ceil(D/16) <= 65535 and 16-byte aligned in/out.
  * Not capturable (RAG_E_CAPTURE on a capturing stream): see the conventions at the top of this file. */
 RAG_API int rag_conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int D, int H, int W, void* stream);
+
+/* Backward of that layer (training).  g [B,1,D,H,W] = upstream gradient of the layer output.
+ *   gin [B,C,D,H,W] (nullable; needs w):  gin[b,c,p] = sum_k w[0,c,k] * g[b,0,p-k+1]
+ *   gw  [1,C,3,3,3] (nullable; needs in and workspace):  gw[0,c,k] = sum_{b,p} in[b,c,p+k-1] * g[b,0,p]
+ * workspace: rag_conv3d_c1_bwd_workspace_bytes(C) bytes, caller-owned.  Deterministic (fixed-order reductions, no atomics).
+ * Needs W % 4 == 0 and 16-byte aligned g / in / gin.  Capturable (weights are read from global memory here). */
+RAG_API size_t rag_conv3d_c1_bwd_workspace_bytes(int C);
+RAG_API int rag_conv3d_c1_bwd(const float* g, const float* in, const float* w, float* gin, float* gw, void* workspace,
+                      int B, int C, int D, int H, int W, void* stream);
+
+/* Trilinear resize of [B*C, Di,Hi,Wi] -> [B*C, Do,Ho,Wo] with PyTorch's fp32 index arithmetic: the `upsample_6` /
+ * `upsample_12` steps of the Matching Net's tail, nn.Upsample(size=..., mode='trilinear', align_corners=True) at
+ * src/models/rag_model.py:356-366 and :675-685 (align_corners = 0 gives F.interpolate's default convention).
+ * The backward is a GATHER per input voxel in a fixed order: bitwise repeatable, unlike ATen's atomicAdd scatter. */
+RAG_API int rag_trilinear_resize_fwd(const float* in, float* out, int BC, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
+                             int align_corners, void* stream);
+RAG_API int rag_trilinear_resize_bwd(const float* gout, float* gin, int BC, int Di, int Hi, int Wi, int Do, int Ho, int Wo,
+                             int align_corners, void* stream);
 
 /* Eval-time input staging: uint8 HWC image -> ImageNet-normalised fp32 CHW, zero-padded on the
  * top and right.  Replaces src/dataloaders/data_io.py:6-13 + stereo_dataset.py:88-102.

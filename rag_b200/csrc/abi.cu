@@ -20,6 +20,10 @@ int cv_stem_fwd(const float*, const float*, const float*, const float*, const fl
 size_t cv_stem_workspace_bytes(int, int);
 int cv_stem_moments(const float*, const float*, const float*, double*, int, int, int, int, int, int, float*, cudaStream_t);
 int conv3d_c1_fwd(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+int conv3d_c1_bwd(const float*, const float*, const float*, float*, float*, float*, int, int, int, int, int, cudaStream_t);
+size_t conv3d_c1_bwd_workspace_bytes(int);
+int trilinear_resize_fwd(const float*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
+int trilinear_resize_bwd(const float*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 int cv_stem_bn_bwd_sums(const float*, const float*, const float*, const float*, double*, double*, int, int, int, int, int, cudaStream_t);
 size_t cv_stem_bwd_workspace_bytes(int, int, int, int, int);
 int cv_stem_bwd(const float*, const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*, int, int, int, int, int, int, cudaStream_t);
@@ -112,6 +116,17 @@ RAG_API int rag_cv_stem_bwd(const float* g, const float* pre, const float* const
 }
 RAG_API int rag_conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int D, int H, int W, void* stream) {
     return conv3d_c1_fwd(in, w, out, B, C, D, H, W, ST(stream));
+}
+RAG_API size_t rag_conv3d_c1_bwd_workspace_bytes(int C) { return conv3d_c1_bwd_workspace_bytes(C); }
+RAG_API int rag_conv3d_c1_bwd(const float* g, const float* in, const float* w, float* gin, float* gw, void* workspace,
+                      int B, int C, int D, int H, int W, void* stream) {
+    return conv3d_c1_bwd(g, in, w, gin, gw, static_cast<float*>(workspace), B, C, D, H, W, ST(stream));
+}
+RAG_API int rag_trilinear_resize_fwd(const float* in, float* out, int BC, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int align_corners, void* stream) {
+    return trilinear_resize_fwd(in, out, BC, Di, Hi, Wi, Do, Ho, Wo, align_corners, ST(stream));
+}
+RAG_API int rag_trilinear_resize_bwd(const float* gout, float* gin, int BC, int Di, int Hi, int Wi, int Do, int Ho, int Wo, int align_corners, void* stream) {
+    return trilinear_resize_bwd(gout, gin, BC, Di, Hi, Wi, Do, Ho, Wo, align_corners, ST(stream));
 }
 RAG_API int rag_normalize_pad(const uint8_t* img, float* out, int B, int H, int W, int top_pad, int right_pad, void* stream) {
     return normalize_pad(img, out, B, H, W, top_pad, right_pad, ST(stream));

@@ -1,0 +1,188 @@
+// Backward of `last_3_3d`: the bias-free Conv3d C -> 1, 3x3x3, pad 1 that produces the head's
+// input (src/models/rag_model.py:269, applied at :361-365; src/automl/operations_3d.py:31-47 with bn=False, relu=False).
+//     gin[b,c,d,h,w]      = sum_{kd,kh,kw} W[0,c,kd,kh,kw] * g[b,0,d-kd+1,h-kh+1,w-kw+1]          (data gradient)
+//     gW[0,c,kd,kh,kw]    = sum_{b,d,h,w}  in[b,c,d+kd-1,h+kh-1,w+kw-1] * g[b,0,d,h,w]            (weight gradient)
+// Both read the ONE-channel upstream gradient g through the same 3x3x6 register window per thread (4 adjacent w): the data
+// gradient re-uses the window for all C channels (1296 FMAs per window, output streamed with 128-bit stores: the C-times
+// larger tensor is written once), the weight gradient keeps 27 running sums per thread for one channel over many tiles and
+// reduces once per CTA (fixed order, fp64 final pass: deterministic).  cuDNN has no good kernel for a 1-channel side.
+#include "common.cuh"
+
+namespace rag {
+
+constexpr int kLbD = 4, kLbH = 8, kLbW = 32;                // tile of positions per CTA: 4 x 8 x 32, thread = 4 adjacent w
+constexpr int kLbSW = kLbW + 8;                             // staged row: w0-4 .. w0+35 (16-byte aligned segments)
+constexpr int kLbRows = (kLbD + 2) * (kLbH + 2);
+
+// stage g[b, d0-1 .. d0+4, h0-1 .. h0+8, w0-4 .. w0+35] (zero outside the volume) into smem [rows][kLbSW]
+__device__ __forceinline__ void lb_stage(float* sm, const float* __restrict__ g, int b, int d0, int h0, int w0, int D, int H, int W) {
+    const size_t vol = (size_t)D * H * W;
+    for (int i = threadIdx.x; i < kLbRows * (kLbSW / 4); i += 256) {
+        const int row = i / (kLbSW / 4), v = i - row * (kLbSW / 4);
+        const int dz = row / (kLbH + 2), hy = row - dz * (kLbH + 2);
+        const int gd = d0 - 1 + dz, gh = h0 - 1 + hy, gw = w0 - 4 + 4 * v;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W)   // W % 4 == 0: a quad is inside or outside as a whole
+            val = __ldg(reinterpret_cast<const float4*>(g + (size_t)b * vol + ((size_t)gd * H + gh) * W + gw));
+        *reinterpret_cast<float4*>(sm + row * kLbSW + 4 * v) = val;
+    }
+}
+
+// the thread's window: win[kd][kh][0..5] = g at (d+kd-1, h+kh-1, w0+4tw-1 .. w0+4tw+4)
+__device__ __forceinline__ void lb_window(const float* sm, int td, int th, int tw, float (&win)[3][3][6]) {
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const float* p = sm + ((td + kd) * (kLbH + 2) + th + kh) * kLbSW + 4 * tw;   // column (w0-4) + 4tw
+            const float4 m = *reinterpret_cast<const float4*>(p + 4);
+            win[kd][kh][0] = p[3];
+            win[kd][kh][1] = m.x; win[kd][kh][2] = m.y; win[kd][kh][3] = m.z; win[kd][kh][4] = m.w;
+            win[kd][kh][5] = p[8];
+        }
+}
+
+// grid (ceil(W/32), ceil(H/8), B*ceil(D/4)); 256 threads.  smem: tile | weights [C][27]
+__global__ void __launch_bounds__(256)
+conv3d_c1_bwd_data_kernel(const float* __restrict__ g, const float* __restrict__ wgt, float* __restrict__ gin,
+                          int C, int D, int H, int W, int n_dt) {
+    extern __shared__ __align__(16) float lbd_smem[];
+    float* tile = lbd_smem;
+    float* ws = tile + kLbRows * kLbSW;
+    const int b = blockIdx.z / n_dt, d0 = (blockIdx.z - b * n_dt) * kLbD, h0 = blockIdx.y * kLbH, w0 = blockIdx.x * kLbW;
+    for (int i = threadIdx.x; i < C * 27; i += 256) ws[i] = __ldg(wgt + i);
+    lb_stage(tile, g, b, d0, h0, w0, D, H, W);
+    __syncthreads();
+    const int tw = threadIdx.x & 7, th = (threadIdx.x >> 3) & 7, td = threadIdx.x >> 6;
+    const int d = d0 + td, h = h0 + th, w = w0 + 4 * tw;
+    if (d >= D || h >= H || w >= W) return;
+    float win[3][3][6];
+    lb_window(tile, td, th, tw, win);
+    const size_t vol = (size_t)D * H * W;
+    float* o = gin + (size_t)b * C * vol + ((size_t)d * H + h) * W + w;
+    for (int c = 0; c < C; ++c) {
+        const float* wc = ws + c * 27;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // gin[p] = sum_k W[k] g[p - k + 1]: tap (kd,kh,kw) reads the window at (2-kd, 2-kh, i + 2 - kw) for output i
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float wv = wc[(kd * 3 + kh) * 3 + kw];
+                    const float* r = win[2 - kd][2 - kh];
+                    acc.x = __fmaf_rn(wv, r[0 + 2 - kw], acc.x);
+                    acc.y = __fmaf_rn(wv, r[1 + 2 - kw], acc.y);
+                    acc.z = __fmaf_rn(wv, r[2 + 2 - kw], acc.z);
+                    acc.w = __fmaf_rn(wv, r[3 + 2 - kw], acc.w);
+                }
+        st_stream(reinterpret_cast<float4*>(o + (size_t)c * vol), acc);
+    }
+}
+
+// grid (n_groups, C); 256 threads; CTA (grp, c) walks tiles grp, grp + n_groups, ... and accumulates its channel's 27 sums.
+// part [C][n_groups][27]
+__global__ void __launch_bounds__(256)
+conv3d_c1_bwd_weight_kernel(const float* __restrict__ g, const float* __restrict__ in, float* __restrict__ part,
+                            int B, int C, int D, int H, int W, int n_wt, int n_ht, int n_dt) {
+    extern __shared__ __align__(16) float lbw_smem[];
+    __shared__ float red[8][27];
+    const int c = blockIdx.y, n_groups = gridDim.x;
+    const int tw = threadIdx.x & 7, th = (threadIdx.x >> 3) & 7, td = threadIdx.x >> 6;
+    const size_t vol = (size_t)D * H * W;
+    const int n_tiles = B * n_dt * n_ht * n_wt;
+    float acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+    for (int t = blockIdx.x; t < n_tiles; t += n_groups) {
+        const int wt = t % n_wt, ht = (t / n_wt) % n_ht, dt = (t / (n_wt * n_ht)) % n_dt, b = t / (n_wt * n_ht * n_dt);
+        const int d0 = dt * kLbD, h0 = ht * kLbH, w0 = wt * kLbW;
+        __syncthreads();
+        lb_stage(lbw_smem, g, b, d0, h0, w0, D, H, W);
+        __syncthreads();
+        const int d = d0 + td, h = h0 + th, w = w0 + 4 * tw;
+        if (d < D && h < H && w < W) {
+            float win[3][3][6];
+            lb_window(lbw_smem, td, th, tw, win);
+            const float4 x = __ldg(reinterpret_cast<const float4*>(in + ((size_t)b * C + c) * vol + ((size_t)d * H + h) * W + w));
+            // gW[k] += in[p] g[p - k + 1]: for input position i (0..3) tap (kd,kh,kw) pairs with window (2-kd, 2-kh, i + 2 - kw)
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float* r = win[2 - kd][2 - kh];
+                        float a = acc[(kd * 3 + kh) * 3 + kw];
+                        a = __fmaf_rn(x.x, r[0 + 2 - kw], a);
+                        a = __fmaf_rn(x.y, r[1 + 2 - kw], a);
+                        a = __fmaf_rn(x.z, r[2 + 2 - kw], a);
+                        a = __fmaf_rn(x.w, r[3 + 2 - kw], a);
+                        acc[(kd * 3 + kh) * 3 + kw] = a;
+                    }
+        }
+    }
+    // CTA reduction, fixed order: lanes by shuffle tree, then the 8 warps in order
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        float v = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) v += red[wv][threadIdx.x];
+        part[((size_t)c * n_groups + blockIdx.x) * 27 + threadIdx.x] = v;
+    }
+}
+
+// gw[c][k] = sum over groups of part[c][grp][k], fixed order, fp64.  grid C, 32 threads (lanes = taps)
+__global__ void conv3d_c1_bwd_weight_final_kernel(const float* __restrict__ part, float* __restrict__ gw, int n_groups) {
+    const int c = blockIdx.x, k = threadIdx.x;
+    if (k >= 27) return;
+    double a = 0.0;
+    for (int i = 0; i < n_groups; ++i) a += (double)part[((size_t)c * n_groups + i) * 27 + k];
+    gw[c * 27 + k] = (float)a;
+}
+
+constexpr int kLbGroups = 148;
+
+size_t conv3d_c1_bwd_workspace_bytes(int C) { return C > 0 ? (size_t)C * kLbGroups * 27 * sizeof(float) : 0; }
+
+// gin [B,C,D,H,W] (nullable; needs w) and gw [1,C,3,3,3] (nullable; needs in + workspace) from g [B,1,D,H,W]
+int conv3d_c1_bwd(const float* g, const float* in, const float* w, float* gin, float* gw, float* workspace,
+                  int B, int C, int D, int H, int W, cudaStream_t st) {
+    if (!g) return fail(RAG_E_NULL, "conv3d_c1_bwd: null pointer");
+    if (gin && !w) return fail(RAG_E_NULL, "conv3d_c1_bwd: the data gradient needs the weight");
+    if (gw && (!in || !workspace)) return fail(RAG_E_NULL, "conv3d_c1_bwd: the weight gradient needs the layer input and a workspace");
+    if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: non-positive dimension");
+    if (W % 4 != 0) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: W=%d must be a multiple of 4", W);
+    if ((size_t)D * H * W >= ((size_t)1 << 31) || C > 1024) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: D*H*W must be < 2^31 and C <= 1024");
+    if (!aligned(g, 16) || (gin && !aligned(gin, 16)) || (in && !aligned(in, 16))) return fail(RAG_E_ALIGN, "conv3d_c1_bwd: g, in, gin must be 16-byte aligned");
+    const int n_wt = (W + kLbW - 1) / kLbW, n_ht = (H + kLbH - 1) / kLbH, n_dt = (D + kLbD - 1) / kLbD;
+    if ((long long)B * n_dt > 65535 || n_ht > 65535 || (long long)B * n_dt * n_ht * n_wt >= (1LL << 31))
+        return fail(RAG_E_SHAPE, "conv3d_c1_bwd: B*ceil(D/4) and ceil(H/8) must be <= 65535");
+    const size_t tile_bytes = (size_t)kLbRows * kLbSW * sizeof(float);
+    if (gin) {
+        const size_t smem = tile_bytes + (size_t)C * 27 * sizeof(float);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(conv3d_c1_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail((int)e, "conv3d_c1_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        }
+        conv3d_c1_bwd_data_kernel<<<dim3(n_wt, n_ht, B * n_dt), 256, smem, st>>>(g, w, gin, C, D, H, W, n_dt);
+        if (int rc = check_launch("conv3d_c1_bwd(data)")) return rc;
+    }
+    if (gw) {
+        conv3d_c1_bwd_weight_kernel<<<dim3(kLbGroups, C), 256, tile_bytes, st>>>(g, in, workspace, B, C, D, H, W, n_wt, n_ht, n_dt);
+        if (int rc = check_launch("conv3d_c1_bwd(weight)")) return rc;
+        conv3d_c1_bwd_weight_final_kernel<<<C, 32, 0, st>>>(workspace, gw, kLbGroups);
+        if (int rc = check_launch("conv3d_c1_bwd(weight final)")) return rc;
+    }
+    return RAG_OK;
+}
+
+}  // namespace rag

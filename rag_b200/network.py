@@ -78,7 +78,7 @@ def basic_network_forward(self, left, right, fea_ops, mat_ops):
     return _head(self, cost)
 
 
-def install(rag_model=None, mdenas_basicmodel=None, operations_3d=None, fuse_stem: bool = False) -> dict:
+def install(rag_model=None, mdenas_basicmodel=None, operations_3d=None, fuse_stem: bool = False, upsample: bool = False) -> dict:
     """Bind the B200 hot path onto the reference's modules (pass the imported module objects
     ``models.rag_model`` and/or ``automl.mdenas_basicmodel``).  Returns what was patched.
     New networks constructed afterwards get ``rag_b200.Disp``; existing instances keep working
@@ -91,7 +91,11 @@ def install(rag_model=None, mdenas_basicmodel=None, operations_3d=None, fuse_ste
     sends ``last_3_3d`` (a bias-free Conv3d C -> 1, 3x3x3 without BN/ReLU, rag_model.py:269) through
     csrc/last_conv.cu when no gradient is wanted (rag_b200/last_conv.py).  NOTE: only the
     growable ``Network`` starts its Matching Net with a ConvBR_3d on the raw volume in all configurations;
-    the search supernet (``BasicNetwork``/``AutoMatching``) keeps the materialised volume."""
+    the search supernet (``BasicNetwork``/``AutoMatching``) keeps the materialised volume.
+
+    ``upsample=True`` (needs ``rag_model``) sends the ``upsample_6`` / ``upsample_12`` steps of ``matching()`` /
+    ``search_matching()`` (``nn.Upsample(..., mode='trilinear', align_corners=True)``, rag_model.py:356-357,675-676) through
+    csrc/trilinear.cu, forward and deterministic backward (rag_b200/upsample.py)."""
     global _FUSE_STEM, _STEM_AWARE
     done = {}
 
@@ -112,6 +116,13 @@ def install(rag_model=None, mdenas_basicmodel=None, operations_3d=None, fuse_ste
         bind(rag_model, "Disp", Disp)
         bind(rag_model, "DisparityRegression", DisparityRegression)
         done["rag_model"] = ["Network.forward", "Network.search_forward", "Disp", "DisparityRegression"]
+    if upsample:
+        if rag_model is None:
+            raise ValueError("upsample=True needs rag_model (the reference's models.rag_model module)")
+        from .upsample import NNProxy
+
+        bind(rag_model, "nn", NNProxy())        # `nn.Upsample(...)` inside matching() now resolves to rag_b200.upsample.Upsample
+        done["rag_model"].append("nn.Upsample")
     if mdenas_basicmodel is not None:
         bind(mdenas_basicmodel.BasicNetwork, "forward", basic_network_forward)
         bind(mdenas_basicmodel, "Disp", Disp)
