@@ -14,8 +14,8 @@
 //     gy[c,h',u ] = sum_{o,kd,kh,kw} W[o,C+c,kd,kh,kw] S[kd,kw==2][o,h,u+kd-kw]
 //     gW[o,  c,kd,kh,kw] = sum_{b,h,w'} x[c,h',w'] Tw[kd,kw][o,h,w'-kw+1]
 //     gW[o,C+c,kd,kh,kw] = sum_{b,h,u } y[c,h',u ] S[kd,kw==2][o,h,u+kd-kw]
-// (fp64 prototype checked against the reference's autograd through the materialised volume:
-// oracle/rag_oracle.py stem_backward_volume_free_f64).  gz itself is never stored either: it is rebuilt on the fly from
+// (the fp64 prototype of this algebra is checked against the reference's autograd through the materialised volume in the
+// CPU test-suite: stem_backward_volume_free_f64, tests/test_oracle_golden.py).  gz itself is never stored either: it is rebuilt on the fly from
 // the upstream gradient g of the layer OUTPUT and the layer's PRE-ACTIVATION `pre` = gamma*zh + beta (out = relu(pre)):
 //     gp = g [pre > 0],  zh = (pre - beta) / gamma
 //     gz = a (gp - m1 - zh m2),  a = gamma*rstd,  m1 = mean(gp), m2 = mean(gp zh)   (train)   |   gz = a gp   (eval)
