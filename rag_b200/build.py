@@ -34,14 +34,32 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile to a temporary file and rename it into place under a file lock: under torchrun every rank may find the library
+    missing or stale at the same moment, and a rank must never dlopen a half-written .so."""
+    import fcntl
+    import tempfile
+
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc()] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():          # another rank built it while we waited for the lock
+                return LIB
+            fd, tmp = tempfile.mkstemp(prefix="librag_b200.", suffix=".so.tmp", dir=HERE)
+            os.close(fd)
+            cmd = [nvcc()] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+            os.chmod(tmp, 0o755)
+            os.replace(tmp, LIB)                           # atomic on POSIX
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

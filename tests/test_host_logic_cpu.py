@@ -124,3 +124,81 @@ def test_install_patches_the_reference_classes():
             rm.Network.forward(stub, None, None, 0)
     finally:
         rm.Network.forward = orig
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (only in the build container)")
+def test_install_uninstall_flags_and_upsample_proxy_on_the_reference():
+    """install() / uninstall() bookkeeping on the UNMODIFIED reference (CPU: only the bindings, no kernels): every binding is
+    restored, install(fuse_stem=False) after a fused install switches the default off, and install(upsample=True) exposes
+    rag_b200.upsample.Upsample as rag_model.nn.Upsample while every other name still resolves to torch.nn."""
+    sys.path.insert(0, REF)
+    try:
+        import automl.mdenas_basicmodel as mb
+        import automl.operations_3d as ops3d
+        import models.rag_model as rm
+    finally:
+        sys.path.remove(REF)
+    from rag_b200 import network as N
+    from rag_b200.upsample import Upsample
+
+    N.uninstall()
+    orig = (rm.Network.forward, rm.Network.search_forward, mb.BasicNetwork.forward, ops3d.ConvBR_3d.forward, rm.Disp, rm.nn)
+    try:
+        done = N.install(rm, mb, ops3d, fuse_stem=True, upsample=True)
+        assert "nn.Upsample" in done["rag_model"] and done["operations_3d"] == ["ConvBR_3d.forward"]
+        assert N._FUSE_STEM and N._STEM_AWARE
+        assert rm.nn.Upsample is Upsample and rm.nn.Conv3d is torch.nn.Conv3d and rm.nn.ModuleList is torch.nn.ModuleList
+        up = rm.nn.Upsample(size=[4, 6, 8], mode="trilinear", align_corners=True)       # what matching() builds per call
+        x = torch.randn(1, 2, 2, 3, 4)
+        assert torch.equal(up(x), torch.nn.Upsample(size=[4, 6, 8], mode="trilinear", align_corners=True)(x))   # CPU: nn.Upsample itself
+        N.install(rm, mb)                                   # plain install afterwards: fusion default off again
+        assert not N._FUSE_STEM
+        stub = type("S", (), {"maxdisp": 48})()
+        with pytest.raises(RuntimeError, match="no CPU fallback"):   # _volume() takes the materialising path -> CUDA-only kernel
+            N._volume(stub, torch.zeros(1, 12, 2, 4), torch.zeros(1, 12, 2, 4), 48)
+        stub.rag_b200_fuse_stem = True                       # per-instance opt-in while ConvBR_3d is fusion-aware
+        from rag_b200.fused_stem import VirtualCostVolume
+
+        assert isinstance(N._volume(stub, torch.zeros(1, 12, 2, 4), torch.zeros(1, 12, 2, 4), 48), VirtualCostVolume)
+    finally:
+        n = N.uninstall()
+    assert n >= 8
+    assert (rm.Network.forward, rm.Network.search_forward, mb.BasicNetwork.forward, ops3d.ConvBR_3d.forward, rm.Disp, rm.nn) == orig
+    assert rm.nn is torch.nn and not N._FUSE_STEM and not N._STEM_AWARE
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (only in the build container)")
+def test_refimport_installs_and_verifies_the_reference(tmp_path):
+    """tools/install_ref.sh + oracle/refimport.py: the copy under baseline/_ref is byte-identical (sha256 manifest), imports, and the
+    scoped CPU monkeypatch restores torch.cuda.current_device."""
+    import subprocess
+
+    from oracle import refimport as R
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["bash", os.path.join(root, "tools", "install_ref.sh")], check=True, capture_output=True)
+    assert R.available() and R.verify_manifest() >= 20
+    ref = R.import_reference(cpu_patch=True)
+    g = R.make_genotype(ref, 0)
+    assert g.normal.shape == (6, 2) and g.reduce.shape == (6, 2) and set(g.normal[:, 1]) <= {0, 1}
+    before = torch.cuda.current_device
+    with R.on_cpu():
+        assert torch.cuda.current_device() == "cpu"
+        d = ref.rag_model.Disp(24)(torch.randn(1, 1, 8, 2, 3))       # the unmodified reference head on CPU tensors
+    assert torch.cuda.current_device is before and d.shape == (1, 6, 9)
+
+
+def test_fp64_torch_evaluator_matches_the_numpy_evaluator():
+    """oracle.disp_head_f64_torch (used on the GPU at BASELINE sizes) against oracle.disp_head_grad_f64 (numpy)."""
+    from oracle import rag_oracle as O
+
+    g = torch.Generator().manual_seed(3)
+    for (b, dl, hl, wl, md) in [(2, 16, 5, 12, 48), (1, 20, 3, 4, 60), (1, 7, 2, 3, 24)]:
+        cl = torch.randn(b, dl, hl, wl, generator=g)
+        gd = torch.randn(b, 3 * hl, 3 * wl, generator=g)
+        d, gg = O.disp_head_grad_f64(cl.numpy(), gd.numpy(), md)
+        d2, g2 = O.disp_head_f64_torch(cl, md, gd)
+        assert np.abs(d - d2.numpy()).max() <= 1e-12
+        assert np.abs(gg - g2.numpy()).max() <= 1e-12 * max(1.0, np.abs(gg).max())
+        d3, none = O.disp_head_f64_torch(cl, md)
+        assert none is None and torch.equal(d3, d2)
