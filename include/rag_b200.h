@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RAG_B200_ABI_VERSION 10
+#define RAG_B200_ABI_VERSION 12
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
@@ -179,25 +179,44 @@ RAG_API int rag_cv_stem_fwd_v(const float* x, const float* y, const float* w, co
 RAG_API int rag_cv_stem_moments(const float* x, const float* y, const float* w, double* moments,
                         int B, int C, int O, int Df, int Hf, int Wf, void* workspace, void* stream);
 
-/* Backward of that fused layer (training) -- again without the volume, its gradient, or any other
- * [B,2C,Df,Hf,Wf] tensor.  Replaces the autograd of src/models/rag_model.py:375-383 + ConvBR_3d (operations_3d.py:31-47:
- * Conv3d -> BatchNorm3d -> ReLU) for BatchNorm in train() (batch statistics) or eval() (running statistics).
- * g   [B,O,Df,Hf,Wf]  upstream gradient of the layer output
- * pre [B,O,Df,Hf,Wf]  the layer's pre-activation gamma*zh + beta (rag_cv_stem_fwd with relu = 0 and the forward's
- *                     scale/shift; the host side recomputes it for the backward instead of keeping it alive)
- * Step 1, rag_cv_stem_bn_bwd_sums: sums [O,2] DOUBLE = (sum g', sum g'*zh) over (B,Df,Hf,Wf), g' = g [pre > 0],
- *   zh = (pre - beta[o]) * ginv[o] (ginv = 1/gamma) -- the BatchNorm weight/bias gradients and the two means of the
- *   train-mode BatchNorm backward.  rows_ws: DOUBLE workspace [B*Hf*O*2].  Deterministic (fixed-order fp64).
- * Step 2, rag_cv_stem_bwd: consts [O,5] = (a, m1, m2, beta, 1/gamma) with a = gamma*rstd and, in train mode,
- *   m1 = sums[o,0]/n, m2 = sums[o,1]/n (n = B*Df*Hf*Wf), in eval mode m1 = m2 = 0; the gradient at the convolution output
- *   gz = a (g' - m1 - zh m2) is formed on the fly and reduced along d into the 2-D maps the transpose needs, then
- *   gx, gy [B,C,Hf,Wf] (both or neither; need w) and gw [O,2C,3,3,3] (nullable; needs x, y) are 2-D contractions.
- *   workspace: rag_cv_stem_bwd_workspace_bytes(B,C,O,Hf,Wf) bytes, 16-byte aligned, caller-owned.
+/* The fused layer with autograd (training) -- again without the volume, its gradient, or any other
+ * [B,2C,Df,Hf,Wf] tensor.  Replaces src/models/rag_model.py:375-383 + ConvBR_3d (operations_3d.py:31-47: Conv3d ->
+ * BatchNorm3d -> ReLU) and their autograd, for BatchNorm in train() (batch statistics) or eval() (running statistics).
+ * Forward:  z = rag_cv_stem_fwd(x, y, w, scale = NULL, shift = NULL, relu = 0)            the convolution output
+ *           rag_cv_stem_z_moments(z) -> sums [O,2] DOUBLE = (sum z, sum z^2) over (B,Df,Hf,Wf)   (train(): mean, biased variance)
+ *           rag_cv_stem_bn_relu(z, scale, shift): z <- max(fma(z, scale[o], shift[o]), 0) IN PLACE = the layer output,
+ *           scale = gamma*rstd, shift = beta - mean*scale.
+ * Backward: z is RECOMPUTED with rag_cv_stem_fwd (the host side does not keep it alive), then, with g [B,O,Df,Hf,Wf] the
+ *   upstream gradient of the layer output and bn [O,4] = (scale, shift, mean, rstd):
+ *   rag_cv_stem_bn_bwd_sums -> sums [O,2] DOUBLE = (sum g', sum g'*zh), g' = g [fma(z,scale,shift) > 0] (the forward's own ReLU
+ *     decision, bit for bit), zh = (z - mean)*rstd: the BatchNorm bias / weight gradients and the two means of the train-mode
+ *     BatchNorm backward;
+ *   rag_cv_stem_bwd, consts [O,7] = (a, m1, m2, scale, shift, mean, rstd) with a = gamma*rstd and, in train mode,
+ *     m1 = sums[o,0]/n, m2 = sums[o,1]/n (n = B*Df*Hf*Wf), in eval mode m1 = m2 = 0: the gradient at the convolution output
+ *     gz = a (g' - m1 - zh m2) is formed on the fly and reduced along d into the 2-D maps the transpose needs, then
+ *     gx, gy [B,C,Hf,Wf] (both or neither; need w) and gw [O,2C,3,3,3] (nullable; needs x, y) are 2-D contractions.
+ * rows_ws: DOUBLE workspace [B*Hf*O*2]; workspace: rag_cv_stem_bwd_workspace_bytes(B,C,O,Hf,Wf) bytes, 16-byte aligned;
+ * both caller-owned.  Deterministic (fixed-order reductions, no atomics).
  * Needs C == 12, O <= 32, Df >= 3, 8 <= Wf <= 1016, Wf % 4 == 0. */
-RAG_API int rag_cv_stem_bn_bwd_sums(const float* g, const float* pre, const float* beta, const float* ginv, double* sums,
+RAG_API int rag_cv_stem_z_moments(const float* z, double* sums, double* rows_ws, int B, int O, int Df, int Hf, int Wf, void* stream);
+/* Per-channel finalisers (one tiny launch each instead of a dozen elementwise framework kernels):
+ * rag_cv_stem_bn_finalize: sums [O,2] DOUBLE (from rag_cv_stem_z_moments; used when batch != 0) or the running statistics
+ *   (batch == 0) -> bn [O,4] = (scale, shift, mean, rstd) fp32 and stats [O,2] DOUBLE = (mean, biased variance); with batch and
+ *   update != 0 the running estimates are updated in place as nn.BatchNorm does in train() (r = (1-momentum) r + momentum * batch
+ *   value, unbiased variance n/(n-1)); n = B*Df*Hf*Wf.  scale / shift for rag_cv_stem_bn_relu are columns 0 / 1 of bn (stride 4:
+ *   pass bn and bn + 1 is NOT valid -- use rag_cv_stem_bn_relu_bn below).
+ * rag_cv_stem_bwd_consts: sums [O,2] DOUBLE (from rag_cv_stem_bn_bwd_sums) + bn -> consts [O,7] for rag_cv_stem_bwd and
+ *   gparam [2,O] = (d/d gamma, d/d beta). */
+RAG_API int rag_cv_stem_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                            double* stats, float* bn, int O, double n, double eps, double momentum, int batch, int update, void* stream);
+RAG_API int rag_cv_stem_bwd_consts(const double* sums, const float* bn, float* consts, float* gparam, int O, double n, int batch, void* stream);
+RAG_API int rag_cv_stem_bn_relu(float* z, const float* scale, const float* shift, int B, int O, int Df, int Hf, int Wf, void* stream);
+/* the same with scale / shift taken from columns 0 / 1 of bn [O,4] */
+RAG_API int rag_cv_stem_bn_relu_bn(float* z, const float* bn, int B, int O, int Df, int Hf, int Wf, void* stream);
+RAG_API int rag_cv_stem_bn_bwd_sums(const float* g, const float* z, const float* bn, double* sums,
                             double* rows_ws, int B, int O, int Df, int Hf, int Wf, void* stream);
 RAG_API size_t rag_cv_stem_bwd_workspace_bytes(int B, int C, int O, int Hf, int Wf);
-RAG_API int rag_cv_stem_bwd(const float* g, const float* pre, const float* consts, const float* x, const float* y, const float* w,
+RAG_API int rag_cv_stem_bwd(const float* g, const float* z, const float* consts, const float* x, const float* y, const float* w,
                     float* gx, float* gy, float* gw, void* workspace, int B, int C, int O, int Df, int Hf, int Wf, void* stream);
 
 /* The Matching Net's last layer, the producer of the head's input (inference):

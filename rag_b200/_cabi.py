@@ -12,7 +12,7 @@ import os
 
 from . import build as _build
 
-ABI_VERSION = 10
+ABI_VERSION = 12
 
 _f = C.POINTER(C.c_float)
 _d = C.POINTER(C.c_double)
@@ -44,7 +44,12 @@ SIGNATURES = {
     "rag_cv_stem_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "rag_cv_stem_fwd_v": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "rag_cv_stem_moments": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
-    "rag_cv_stem_bn_bwd_sums": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rag_cv_stem_z_moments": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rag_cv_stem_bn_relu": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rag_cv_stem_bn_relu_bn": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rag_cv_stem_bn_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.c_double, C.c_double, C.c_double, _i, _i, _vp]),
+    "rag_cv_stem_bwd_consts": (_i, [_vp, _vp, _vp, _vp, _i, C.c_double, _i, _vp]),
+    "rag_cv_stem_bn_bwd_sums": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rag_cv_stem_bwd_workspace_bytes": (C.c_size_t, [_i, _i, _i, _i, _i]),
     "rag_cv_stem_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rag_conv3d_c1_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -110,24 +110,48 @@ def cv_stem_batch_stats(x, y, weight, maxdisp=192):
 class FusedStemFn(torch.autograd.Function):
     """out = relu(batchnorm(conv3d(cost_volume(x, y), weight))) with gradients w.r.t. x, y, weight, gamma, beta.
 
-    ``mean`` / ``rstd`` [O] fp32 are the statistics the BatchNorm normalises with (batch statistics in train(), running
-    ones in eval()); ``batch_stats`` says which (it decides whether the mean terms of the BatchNorm backward apply).
-    Saved for the backward: the two feature maps, the weight, four [O] vectors -- no [B,*,Df,Hf,Wf] tensor: the layer's
-    pre-activation is RECOMPUTED by the forward kernel inside ``backward`` into a temporary."""
+    Forward: the convolution output z from the fused kernel (the volume is never built), its batch moments in one read
+    (``batch_stats``; else the given running statistics), BatchNorm + ReLU IN PLACE.  Returns ``(out, mean, var)`` -- the
+    statistics the layer normalised with, fp64, non-differentiable (the caller updates the running estimates from them).
+    Saved for the backward: the two feature maps, the weight and a few [O] vectors -- no [B,*,Df,Hf,Wf] tensor: z is
+    RECOMPUTED by the forward kernel inside ``backward`` into a temporary, and the backward kernels re-evaluate the forward's
+    own expression ``fma(z, scale, shift) > 0`` for the ReLU decision (bit-identical)."""
 
     @staticmethod
-    def forward(ctx, x, y, weight, gamma, beta, mean, rstd, batch_stats, maxdisp):
-        scale = gamma * rstd
-        shift = beta - mean * scale
-        out = cv_stem_forward(x, y, weight, scale, shift, True, maxdisp)
-        ctx.save_for_backward(x, y, weight, gamma, beta, scale, shift, rstd)
+    def forward(ctx, x, y, weight, gamma, beta, running_mean, running_var, batch_stats, update_running, momentum, eps, maxdisp):
+        b, c, hf, wf = x.shape
+        o = weight.shape[0]
+        dev = x.device
+        L = _cabi.lib()
+        z = cv_stem_forward(x, y, weight, None, None, False, maxdisp)
+        df = z.shape[2]
+        n = b * df * hf * wf
+        gamma, beta = gamma.contiguous(), beta.contiguous()
+        with torch.cuda.device(dev):
+            st = _stream(x)
+            sums = None
+            if batch_stats:
+                sums = torch.empty((o, 2), dtype=torch.float64, device=dev)
+                rows = torch.empty((b * hf * o * 2,), dtype=torch.float64, device=dev)
+                _cabi.check(L.rag_cv_stem_z_moments(z.data_ptr(), sums.data_ptr(), rows.data_ptr(), b, o, df, hf, wf, st), "rag_cv_stem_z_moments")
+            stats = torch.empty((o, 2), dtype=torch.float64, device=dev)         # (mean, biased variance) the layer normalises with
+            bn = torch.empty((o, 4), dtype=torch.float32, device=dev)            # (scale, shift, mean, rstd)
+            rc = L.rag_cv_stem_bn_finalize(sums.data_ptr() if sums is not None else None, gamma.data_ptr(), beta.data_ptr(),
+                                           running_mean.data_ptr() if running_mean is not None else None,
+                                           running_var.data_ptr() if running_var is not None else None,
+                                           stats.data_ptr(), bn.data_ptr(), o, float(n), float(eps), float(momentum), int(bool(batch_stats)),
+                                           int(bool(update_running)), st)
+            _cabi.check(rc, "rag_cv_stem_bn_finalize")
+            _cabi.check(L.rag_cv_stem_bn_relu_bn(z.data_ptr(), bn.data_ptr(), b, o, df, hf, wf, st), "rag_cv_stem_bn_relu")
+        ctx.save_for_backward(x, y, weight, bn)
         ctx.batch_stats, ctx.maxdisp = bool(batch_stats), maxdisp
-        return out
+        ctx.mark_non_differentiable(stats)
+        return z, stats                               # z now holds the layer output
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, g):
-        x, y, weight, gamma, beta, scale, shift, rstd = ctx.saved_tensors
+    def backward(ctx, g, _gstats):
+        x, y, weight, bn = ctx.saved_tensors
         g = g.contiguous()
         b, c, hf, wf = x.shape
         o = weight.shape[0]
@@ -138,31 +162,30 @@ class FusedStemFn(torch.autograd.Function):
         need_in = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         need_w = ctx.needs_input_grad[2]
         with torch.cuda.device(dev):
-            pre = cv_stem_forward(x, y, weight, scale, shift, False, ctx.maxdisp)       # temporary: gamma*zh + beta
-            ginv = torch.where(gamma != 0, 1.0 / gamma, torch.zeros_like(gamma)).contiguous()
-            betac = beta.contiguous()
+            st = _stream(x)
+            z = cv_stem_forward(x, y, weight, None, None, False, ctx.maxdisp)           # temporary: the convolution output again
             sums = torch.empty((o, 2), dtype=torch.float64, device=dev)
             rows = torch.empty((b * hf * o * 2,), dtype=torch.float64, device=dev)
-            rc = L.rag_cv_stem_bn_bwd_sums(g.data_ptr(), pre.data_ptr(), betac.data_ptr(), ginv.data_ptr(), sums.data_ptr(), rows.data_ptr(),
-                                           b, o, df, hf, wf, _stream(x))
+            rc = L.rag_cv_stem_bn_bwd_sums(g.data_ptr(), z.data_ptr(), bn.data_ptr(), sums.data_ptr(), rows.data_ptr(), b, o, df, hf, wf, st)
             _cabi.check(rc, "rag_cv_stem_bn_bwd_sums")
-            gbeta = sums[:, 0].to(torch.float32)
-            ggamma = sums[:, 1].to(torch.float32)
+            consts = torch.empty((o, 7), dtype=torch.float32, device=dev)
+            gparam = torch.empty((2, o), dtype=torch.float32, device=dev)
+            _cabi.check(L.rag_cv_stem_bwd_consts(sums.data_ptr(), bn.data_ptr(), consts.data_ptr(), gparam.data_ptr(), o, float(n), int(ctx.batch_stats), st),
+                        "rag_cv_stem_bwd_consts")
             gx = gy = gw = None
             if need_in or need_w:
-                m = (sums / n).to(torch.float32) if ctx.batch_stats else torch.zeros((o, 2), dtype=torch.float32, device=dev)
-                consts = torch.stack([scale, m[:, 0], m[:, 1], betac, ginv], dim=1).contiguous()
                 ws = torch.empty(int(L.rag_cv_stem_bwd_workspace_bytes(b, c, o, hf, wf)) // 4, dtype=torch.float32, device=dev)
                 if need_in:
                     gx, gy = torch.empty_like(x), torch.empty_like(y)
                 if need_w:
                     gw = torch.empty_like(weight)
-                rc = L.rag_cv_stem_bwd(g.data_ptr(), pre.data_ptr(), consts.data_ptr(), x.data_ptr(), y.data_ptr(), weight.data_ptr(),
+                rc = L.rag_cv_stem_bwd(g.data_ptr(), z.data_ptr(), consts.data_ptr(), x.data_ptr(), y.data_ptr(), weight.data_ptr(),
                                        gx.data_ptr() if gx is not None else None, gy.data_ptr() if gy is not None else None,
-                                       gw.data_ptr() if gw is not None else None, ws.data_ptr(), b, c, o, df, hf, wf, _stream(x))
+                                       gw.data_ptr() if gw is not None else None, ws.data_ptr(), b, c, o, df, hf, wf, st)
                 _cabi.check(rc, "rag_cv_stem_bwd")
         return (gx if ctx.needs_input_grad[0] else None, gy if ctx.needs_input_grad[1] else None, gw,
-                ggamma if ctx.needs_input_grad[3] else None, gbeta if ctx.needs_input_grad[4] else None, None, None, None, None)
+                gparam[0] if ctx.needs_input_grad[3] else None, gparam[1] if ctx.needs_input_grad[4] else None,
+                None, None, None, None, None, None, None)
 
 
 def _train_fusable(self, vol: VirtualCostVolume) -> bool:
@@ -179,23 +202,17 @@ def stem_train_forward(self, vol: VirtualCostVolume) -> torch.Tensor:
     """ConvBR_3d.forward on a VirtualCostVolume with autograd (train() or eval() BatchNorm), fused.  Updates the running
     statistics exactly like nn.BatchNorm3d does in train() (momentum / cumulative average, unbiased variance)."""
     bn = self.bn
-    x, y, w = vol.x.contiguous(), vol.y.contiguous(), self.conv.weight
+    x, y = vol.x.contiguous(), vol.y.contiguous()
     use_batch = bn.training or not bn.track_running_stats
-    if use_batch:
-        mean64, var64, n = cv_stem_batch_stats(x.detach(), y.detach(), w.detach(), vol.maxdisp)
-        if bn.training and bn.track_running_stats:
-            with torch.no_grad():
-                if bn.num_batches_tracked is not None:
-                    bn.num_batches_tracked.add_(1)
-                f = (1.0 / float(bn.num_batches_tracked)) if bn.momentum is None else bn.momentum
-                bn.running_mean.mul_(1 - f).add_(mean64.to(bn.running_mean.dtype), alpha=f)
-                bn.running_var.mul_(1 - f).add_((var64 * (n / max(n - 1, 1))).to(bn.running_var.dtype), alpha=f)
-        mean = mean64.to(torch.float32)
-        rstd = torch.rsqrt(var64 + bn.eps).to(torch.float32)
-    else:
-        mean = bn.running_mean
-        rstd = torch.rsqrt(bn.running_var + bn.eps)
-    return FusedStemFn.apply(x, y, w, bn.weight, bn.bias, mean, rstd, use_batch, vol.maxdisp)
+    update = use_batch and bn.training and bn.track_running_stats
+    f = 0.0
+    if update:
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        f = (1.0 / float(bn.num_batches_tracked)) if bn.momentum is None else float(bn.momentum)
+    out, _stats = FusedStemFn.apply(x, y, self.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                    use_batch, update, f, bn.eps, vol.maxdisp)
+    return out
 
 
 def _fusable(conv: nn.Conv3d, vol: VirtualCostVolume) -> bool:

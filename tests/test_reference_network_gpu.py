@@ -76,15 +76,18 @@ def _grads(net):
     return {n: p.grad.detach().clone() for n, p in net.named_parameters() if p.grad is not None}
 
 
-def _compare_grads(got, want, noise=None, tol=1e-4):
+def _compare_grads(got, want, noise=None, tol=1e-4, l2=False):
+    """Per parameter tensor: relative max-norm error (default) or, with l2=True, relative L2 error.  The L2 form is for the
+    fused-stem comparisons: there the two forwards differ by ~1e-7 before ~30 layers of ReLUs, a handful of ReLU decisions
+    flip, and each flip is worth ~1e-3..1e-2 of the max-norm of some small weight tensor while leaving its L2 norm intact."""
     assert set(got) == set(want) and len(got) > 20
     worst = 0.0
     for n in want:
-        den = want[n].abs().max().item()
+        den = want[n].norm().item() if l2 else want[n].abs().max().item()
         if den == 0.0:
             assert got[n].abs().max().item() == 0.0, n
             continue
-        rel = (got[n] - want[n]).abs().max().item() / den
+        rel = ((got[n] - want[n]).norm().item() if l2 else (got[n] - want[n]).abs().max().item()) / den
         allow = tol + (3 * noise.get(n, 0.0) if noise else 0.0)
         assert rel <= allow, f"{n}: rel max-norm {rel:.3e} > {allow:.3e}"
         worst = max(worst, rel)
@@ -281,10 +284,30 @@ def test_fuse_stem_on_the_real_network(ref):
     got_o, got_g = _fwd_bwd(net, call, w)
     assert _cabi.launch_count() - n0 >= 20, "fused training stem (moments, forward, recompute, backward kernels), upsample_12/6 and last_3_3d fwd+bwd, head fwd+bwd did not all run"
     # The fused layer itself is held to 1e-5 of fp64 in tests/test_fused_stem_gpu.py.  Here its output differs from cuDNN's by
-    # ~1e-7 relative (another summation order), which ~30 layers with batch-statistics BatchNorm and ReLUs carry to the matching
-    # cost: the same 1e-3 px / 2e-3 max-norm the eval-mode fused path is held to above (wiring test, not a numerics test).
+    # ~1e-7 relative (another summation order), which ~30 layers with batch-statistics BatchNorm and ReLUs amplify: the gradient of
+    # this random-init network is ill-conditioned in fp32 -- the UNPATCHED fp32 reference is itself 1e-2 (worst tensor) / 1e-3
+    # (median) in relative L2 from the gradient of the same network evaluated in fp64.  So the wiring is checked against that fp64
+    # network: the patched path must be as close to it as the fp32 reference is, within a factor 4 (measured: 2x).
     assert (got_o - ref_o).abs().max().item() <= 1e-3
-    _compare_grads(got_g, ref_g, tol=2e-3)
+    N.uninstall()
+    net64 = deepcopy(net).double()
+    net64.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in state.items()})
+    net64.zero_grad(set_to_none=True)
+    o64 = net64.forward(left.double(), right.double(), 0, net64.arch_init)
+    (o64 * w.double()).sum().backward()
+    g64 = {n: p.grad for n, p in net64.named_parameters() if p.grad is not None}
+    assert set(g64) == set(got_g) == set(ref_g)
+
+    def errs(gg):
+        e = sorted(((gg[n].double() - g64[n]).norm() / g64[n].norm().clamp_min(1e-30)).item() for n in g64)
+        return e[len(e) // 2], e[-1]
+
+    (ref_med, ref_max), (got_med, got_max) = errs(ref_g), errs(got_g)
+    print(f"\nfused training path vs fp64 network: median / worst relative L2 error {got_med:.2e} / {got_max:.2e} "
+          f"(unpatched fp32 reference: {ref_med:.2e} / {ref_max:.2e})")
+    assert got_med <= 4 * ref_med + 1e-5 and got_max <= 4 * ref_max + 1e-4
+    del net64, g64, o64
+    N.install(ref.rag_model, ref.mdenas_basicmodel, ref.operations_3d, fuse_stem=True, upsample=True)
     # only the BatchNorm bias of stem3d0 trainable: its gradient must not be dropped
     for p in net.parameters():
         p.requires_grad_(False)
@@ -293,6 +316,6 @@ def test_fuse_stem_on_the_real_network(ref):
     net.zero_grad(set_to_none=True)
     (call() * w).sum().backward()
     gb = net.stem3d0[0].bn.bias.grad
-    assert gb is not None and (gb - ref_g["stem3d0.0.bn.bias"]).abs().max().item() <= 2e-3 * ref_g["stem3d0.0.bn.bias"].abs().max().item()
+    assert gb is not None and (gb - got_g["stem3d0.0.bn.bias"]).norm().item() <= 1e-5 * got_g["stem3d0.0.bn.bias"].norm().item()   # same as with everything trainable
     N.uninstall()
     assert ref.operations_3d.ConvBR_3d.forward.__module__ != "rag_b200.fused_stem" and ref.rag_model.nn is torch.nn
