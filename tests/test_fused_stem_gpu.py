@@ -445,3 +445,26 @@ def test_training_stem_at_the_training_config_without_the_volume():
     assert our_peak < 0.45 * ref_peak, (our_peak, ref_peak)
     assert our_peak < 3 * vol_bytes // 2 + (64 << 20), (our_peak, vol_bytes)
     print(f"\ntraining stem at B=4 288x576: peak extra memory fused {our_peak / 2**20:.0f} MiB vs materialised {ref_peak / 2**20:.0f} MiB")
+
+
+def test_training_stem_falls_back_where_the_kernels_do_not_apply():
+    """Widths that are not a multiple of 4, a layer without ReLU or without BatchNorm: stem_forward must materialise the volume
+    and run the reference layer (same result as the reference composition, gradients through autograd), never raise."""
+    from rag_b200 import _cabi
+    from rag_b200.fused_stem import VirtualCostVolume, stem_forward
+
+    g = gen(12)
+    for (wf, bn, relu) in [(38, True, True), (40, True, False), (40, False, True)]:
+        layer = ConvBR_3d(24, 12, bn=bn, relu=relu).cuda().train()
+        x0, y0 = randn((1, 12, 4, wf), g).cuda(), randn((1, 12, 4, wf), g).cuda()
+        x, y = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        state = copy.deepcopy(layer.state_dict())
+        out = stem_forward(layer, VirtualCostVolume(x, y, 30))
+        assert "FusedStemFn" not in type(out.grad_fn).__name__
+        out.sum().backward()
+        layer.load_state_dict(state)
+        xr, yr = x0.clone().requires_grad_(True), y0.clone().requires_grad_(True)
+        ref = ref_stem(xr, yr, layer, 30)
+        ref.sum().backward()
+        assert _mx(out.detach(), ref.detach()) <= 1e-5 and _mx(x.grad, xr.grad) <= 1e-4 and _mx(y.grad, yr.grad) <= 1e-4
+    assert _cabi.launch_count() > 0

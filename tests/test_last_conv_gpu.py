@@ -69,10 +69,15 @@ def test_convbr_dropin_and_fallbacks():
         ref = last.conv(x)
         assert (y - ref).abs().max().item() <= 4e-6 * ref.abs().max().item()
         n0 = _cabi.launch_count()
-        yg = last(x.requires_grad_(True))                           # gradient wanted -> reference path
-        assert _cabi.launch_count() == n0 and yg.requires_grad
+        yg = last(x.requires_grad_(True))                           # gradient wanted -> Conv3dC1Fn (kernels in both directions)
+        assert _cabi.launch_count() == n0 + 1 and yg.requires_grad and "Conv3dC1Fn" in type(yg.grad_fn).__name__
         yg.sum().backward()
-        assert last.conv.weight.grad is not None
+        assert _cabi.launch_count() == n0 + 4                       # + data gradient, weight partials, weight final
+        assert last.conv.weight.grad is not None and x.grad is not None
+        xr = x.detach().clone().requires_grad_(True)
+        last.conv.weight.grad = None
+        last.conv(xr).sum().backward()                              # the reference's own nn.Conv3d (fp32 cuDNN)
+        assert (x.grad - xr.grad).abs().max().item() <= 1e-5 * xr.grad.abs().max().item()
         other = ConvBR_3d(12, 12, 3, 1, 1).cuda().eval()
         with torch.no_grad():
             assert not qualifies(other.conv, x)

@@ -185,6 +185,19 @@ def test_growth_loop_with_patch_installed(ref):
     # eval-free comparison: train() BatchNorm uses batch statistics, so both calls see the same numbers
     assert (d_new - d_new_ref).abs().max().item() <= 1e-4
     N.install(ref.rag_model, ref.mdenas_basicmodel)
+    # Scene-router dispatch over the two grown paths of the REAL network (BASELINE config 4): each pair goes through the path of
+    # its scene and lands in input order; per-sample forwards are the reference semantics (run.py:175-180 evaluates task u with
+    # archis[u]).  eval(): BatchNorm must not couple the pairs of a sub-batch.
+    net.eval()
+    l4, r4 = torch.cat([left, right, left.flip(-1), right]), torch.cat([right, left, right.flip(-1), left])
+    scenes = [1, 0, 0, 1]
+    routed = N.PathRouter(net, [net.arch_init, arch]).route(l4, r4, scenes)
+    assert routed.shape == (4, H, W)
+    with torch.no_grad():
+        for i, u in enumerate(scenes):
+            one = net.forward(l4[i:i + 1], r4[i:i + 1], u, [net.arch_init, arch][u])
+            assert (routed[i] - one[0]).abs().max().item() <= 2e-3 * max(1.0, one.abs().max().item()), i   # cuDNN picks algorithms per batch size
+    net.train()
     clone = deepcopy(net)                                             # approaches/rag.py:225
     snap = ref.utils.get_model(net)                                   # utils.py:64-66
     assert not any(k.startswith("disp.") for k in snap)
