@@ -783,28 +783,46 @@ def run_gpu(args):
     barrier()
     h2d, d2h = last.h2d_bytes, last.d2h_bytes
     # the box's copy ceiling with the same ranks active: the same bytes, one plain pinned copy per direction, no kernels
-    def ceiling(n_bytes, to_device):
-        """Best of 12 single plain pinned copies of the step's bytes (per-copy CUDA events): the PCIe uplink is shared with
-        other GPUs of the box (profiles/r2_h2d_ceiling.md), so a mean over consecutive copies measures the neighbours too."""
-        hbuf = torch.empty(n_bytes // 4, dtype=torch.float32).pin_memory()
-        hbuf.zero_()
-        dbuf = torch.empty(n_bytes // 4, dtype=torch.float32, device=dev)
-        fn = (lambda: dbuf.copy_(hbuf, non_blocking=True)) if to_device else (lambda: hbuf.copy_(dbuf, non_blocking=True))
-        for _ in range(2):
-            fn()
-        barrier()
-        best = float("inf")
-        for _ in range(12):
-            c0, c1 = ev(), ev()
-            c0.record()
-            fn()
-            c1.record()
-            torch.cuda.synchronize()
-            best = min(best, c0.elapsed_time(c1))
-        barrier()
-        return best
-    h2d_ms = ceiling(h2d, True)
-    e2e_ms, h2d_ms = max_over_ranks([e2e_ms, h2d_ms])
+    def copy_floor(h2d_bytes, d2h_bytes):
+        """What the box's PCIe fabric allows for one step's copies with the same ranks active: the step's H2D bytes as ONE plain
+        pinned copy (`h2d_ms`), and the H2D and D2H copies of a step issued together on two streams as the pipeline does
+        (`both_ms`: the duplex floor of a step), each the MEDIAN of 12 repetitions timed individually with CUDA events (the
+        uplink is shared with the other GPUs of the box and with whoever else is on it: profiles/r2_h2d_ceiling.md)."""
+        hin = torch.empty(h2d_bytes // 4, dtype=torch.float32).pin_memory(); hin.zero_()
+        din = torch.empty(h2d_bytes // 4, dtype=torch.float32, device=dev)
+        hout = torch.empty(d2h_bytes // 4, dtype=torch.float32).pin_memory(); hout.zero_()
+        dout = torch.zeros(d2h_bytes // 4, dtype=torch.float32, device=dev)
+        sa, sb = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        cur = torch.cuda.current_stream(dev)
+
+        def h2d_only():
+            din.copy_(hin, non_blocking=True)
+
+        def both():
+            sa.wait_stream(cur); sb.wait_stream(cur)
+            with torch.cuda.stream(sa):
+                din.copy_(hin, non_blocking=True)
+            with torch.cuda.stream(sb):
+                hout.copy_(dout, non_blocking=True)
+            cur.wait_stream(sa); cur.wait_stream(sb)
+
+        res = []
+        for fn in (h2d_only, both):
+            for _ in range(2):
+                fn()
+            barrier()
+            ts = []
+            for _ in range(12):
+                c0, c1 = ev(), ev()
+                c0.record(); fn(); c1.record()
+                torch.cuda.synchronize()
+                ts.append(c0.elapsed_time(c1))
+            barrier()
+            res.append(sorted(ts)[len(ts) // 2])
+        return res
+
+    h2d_ms, both_ms = copy_floor(h2d, d2h)
+    e2e_ms, h2d_ms, both_ms = max_over_ranks([e2e_ms, h2d_ms, both_ms])
     checksum = float(last.result["disp"].double().mean())
     e2e_step = e2e_ms / Ke
     e2e = {"value": world * b * Ke / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -817,8 +835,10 @@ def run_gpu(args):
            "h2d_ceiling_GBps_per_rank": round(max(h2d / (h2d_ms * 1e-3), h2d / (e2e_step * 1e-3)) / 1e9, 2),
            "h2d_plain_copy_sample_GBps": round(h2d / (h2d_ms * 1e-3) / 1e9, 2),
            "frac_of_h2d_ceiling": round(min(1.0, h2d_ms / e2e_step), 4),
-           "ceiling_note": "ceiling = the same bytes as one plain pinned cudaMemcpyAsync per step on every rank at once, measured in this run (slowest rank); "
-                           "the box's PCIe fabric, not the kernels, bounds e2e (profiles/r2_h2d_ceiling.md)",
+           "copy_floor_ms_per_step": round(both_ms, 4), "frac_of_copy_floor": round(min(1.0, both_ms / e2e_step), 4),
+           "ceiling_note": "h2d ceiling = the step's H2D bytes as one plain pinned cudaMemcpyAsync on every rank at once; copy floor = the step's H2D and D2H "
+                           "copies issued together on two streams, no kernels; medians of 12, slowest rank, measured in this run.  The box's PCIe "
+                           "fabric, not the kernels, bounds e2e (profiles/r2_h2d_ceiling.md)",
            "numa_binding": numa, "mean_disp": checksum}
     del pipe
     torch.cuda.empty_cache()
