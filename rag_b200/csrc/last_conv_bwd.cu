@@ -81,20 +81,23 @@ conv3d_c1_bwd_data_kernel(const float* __restrict__ g, const float* __restrict__
     }
 }
 
-// grid (n_groups, C); 256 threads; CTA (grp, c) walks tiles grp, grp + n_groups, ... and accumulates its channel's 27 sums.
+// grid (n_groups, ceil(C/2)); 256 threads; CTA (grp, cp) walks tiles grp, grp + n_groups, ... and accumulates the 27 sums of
+// channels 2cp and 2cp+1: one staging of the g tile and one register window feed 216 FMAs instead of 108 (the kernel is
+// bound by the instructions around the FMAs: staging, barriers, 54 shared-memory loads per window).
 // part [C][n_groups][27]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 conv3d_c1_bwd_weight_kernel(const float* __restrict__ g, const float* __restrict__ in, float* __restrict__ part,
                             int B, int C, int D, int H, int W, int n_wt, int n_ht, int n_dt) {
     extern __shared__ __align__(16) float lbw_smem[];
-    __shared__ float red[8][27];
-    const int c = blockIdx.y, n_groups = gridDim.x;
+    __shared__ float red[8][54];
+    const int c0 = 2 * blockIdx.y, n_groups = gridDim.x;
+    const bool two = c0 + 1 < C;
     const int tw = threadIdx.x & 7, th = (threadIdx.x >> 3) & 7, td = threadIdx.x >> 6;
     const size_t vol = (size_t)D * H * W;
     const int n_tiles = B * n_dt * n_ht * n_wt;
-    float acc[27];
+    float acc[2][27];
 #pragma unroll
-    for (int k = 0; k < 27; ++k) acc[k] = 0.f;
+    for (int k = 0; k < 27; ++k) { acc[0][k] = 0.f; acc[1][k] = 0.f; }
     for (int t = blockIdx.x; t < n_tiles; t += n_groups) {
         const int wt = t % n_wt, ht = (t / n_wt) % n_ht, dt = (t / (n_wt * n_ht)) % n_dt, b = t / (n_wt * n_ht * n_dt);
         const int d0 = dt * kLbD, h0 = ht * kLbH, w0 = wt * kLbW;
@@ -105,7 +108,9 @@ conv3d_c1_bwd_weight_kernel(const float* __restrict__ g, const float* __restrict
         if (d < D && h < H && w < W) {
             float win[3][3][6];
             lb_window(lbw_smem, td, th, tw, win);
-            const float4 x = __ldg(reinterpret_cast<const float4*>(in + ((size_t)b * C + c) * vol + ((size_t)d * H + h) * W + w));
+            const float* ip = in + ((size_t)b * C + c0) * vol + ((size_t)d * H + h) * W + w;
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(ip));
+            const float4 x1 = two ? __ldg(reinterpret_cast<const float4*>(ip + vol)) : make_float4(0.f, 0.f, 0.f, 0.f);
             // gW[k] += in[p] g[p - k + 1]: for input position i (0..3) tap (kd,kh,kw) pairs with window (2-kd, 2-kh, i + 2 - kw)
 #pragma unroll
             for (int kd = 0; kd < 3; ++kd)
@@ -114,29 +119,31 @@ conv3d_c1_bwd_weight_kernel(const float* __restrict__ g, const float* __restrict
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
                         const float* r = win[2 - kd][2 - kh];
-                        float a = acc[(kd * 3 + kh) * 3 + kw];
-                        a = __fmaf_rn(x.x, r[0 + 2 - kw], a);
-                        a = __fmaf_rn(x.y, r[1 + 2 - kw], a);
-                        a = __fmaf_rn(x.z, r[2 + 2 - kw], a);
-                        a = __fmaf_rn(x.w, r[3 + 2 - kw], a);
-                        acc[(kd * 3 + kh) * 3 + kw] = a;
+                        const int k = (kd * 3 + kh) * 3 + kw;
+                        float a0 = acc[0][k], a1 = acc[1][k];
+                        a0 = __fmaf_rn(x0.x, r[0 + 2 - kw], a0); a1 = __fmaf_rn(x1.x, r[0 + 2 - kw], a1);
+                        a0 = __fmaf_rn(x0.y, r[1 + 2 - kw], a0); a1 = __fmaf_rn(x1.y, r[1 + 2 - kw], a1);
+                        a0 = __fmaf_rn(x0.z, r[2 + 2 - kw], a0); a1 = __fmaf_rn(x1.z, r[2 + 2 - kw], a1);
+                        a0 = __fmaf_rn(x0.w, r[3 + 2 - kw], a0); a1 = __fmaf_rn(x1.w, r[3 + 2 - kw], a1);
+                        acc[0][k] = a0; acc[1][k] = a1;
                     }
         }
     }
     // CTA reduction, fixed order: lanes by shuffle tree, then the 8 warps in order
 #pragma unroll
-    for (int k = 0; k < 27; ++k) {
-        float v = acc[k];
+    for (int k = 0; k < 54; ++k) {
+        float v = acc[k / 27][k % 27];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
     }
     __syncthreads();
-    if (threadIdx.x < 27) {
+    if (threadIdx.x < 54 && (threadIdx.x < 27 || two)) {
         float v = 0.f;
 #pragma unroll
         for (int wv = 0; wv < 8; ++wv) v += red[wv][threadIdx.x];
-        part[((size_t)c * n_groups + blockIdx.x) * 27 + threadIdx.x] = v;
+        const int c = c0 + threadIdx.x / 27, k = threadIdx.x % 27;
+        part[((size_t)c * n_groups + blockIdx.x) * 27 + k] = v;
     }
 }
 
@@ -149,7 +156,7 @@ __global__ void conv3d_c1_bwd_weight_final_kernel(const float* __restrict__ part
     gw[c * 27 + k] = (float)a;
 }
 
-constexpr int kLbGroups = 148;
+constexpr int kLbGroups = 296;
 
 size_t conv3d_c1_bwd_workspace_bytes(int C) { return C > 0 ? (size_t)C * kLbGroups * 27 * sizeof(float) : 0; }
 
@@ -177,7 +184,7 @@ int conv3d_c1_bwd(const float* g, const float* in, const float* w, float* gin, f
         if (int rc = check_launch("conv3d_c1_bwd(data)")) return rc;
     }
     if (gw) {
-        conv3d_c1_bwd_weight_kernel<<<dim3(kLbGroups, C), 256, tile_bytes, st>>>(g, in, workspace, B, C, D, H, W, n_wt, n_ht, n_dt);
+        conv3d_c1_bwd_weight_kernel<<<dim3(kLbGroups, (C + 1) / 2), 256, tile_bytes, st>>>(g, in, workspace, B, C, D, H, W, n_wt, n_ht, n_dt);
         if (int rc = check_launch("conv3d_c1_bwd(weight)")) return rc;
         conv3d_c1_bwd_weight_final_kernel<<<C, 32, 0, st>>>(workspace, gw, kLbGroups);
         if (int rc = check_launch("conv3d_c1_bwd(weight final)")) return rc;
