@@ -116,21 +116,35 @@ RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int 
  * Variant ids (-1 = the default; ids outside a range return RAG_E_VARIANT):
  *   rag_cost_volume_fwd_v  0 = any width / alignment (items dealt to threads); 1 = lean thread-stationary kernel, one CTA
  *                          per item (default without a workspace when Wf % 4 == 0); 2 = lean persistent, 256 threads, one
- *                          CTA per SM (default with a workspace); 3 = lean persistent, 512 threads (SM sharing);
- *                          4 = TMA bulk-store kernel (cp.async.bulk shared->global).  2-4 need the workspace.
+ *                          CTA per SM (default with a workspace); 3 = lean persistent, 512 threads (SM sharing, launch order);
+ *                          4 = TMA bulk-store kernel (cp.async.bulk shared->global); 5 = lean persistent, 256 threads x 1
+ *                          vector at <= 64 registers (co-resident SM sharing).  2-5 need the workspace.
  *   rag_cost_volume_bwd_v  0 = 128-bit vector kernel (default when Wf % 4 == 0), 1 = scalar (any width),
- *                          2 = the vector kernel as a persistent grid of 4 CTAs per SM (SM sharing with the head backward)
+ *                          2 = the vector kernel as a persistent grid of 4 CTAs per SM (SM sharing, launch order);
+ *                          3 = cp.async ring in shared memory, one 256-thread CTA per SM at 64 registers (co-resident SM
+ *                          sharing); 4, 5 = A/B geometries of 3 (3 stages; 128 threads x 6 stages)
  *   rag_disp_head_fwd_v    0 = any (Dl, maxdisp); 1 = first x3 kernel (any width); 2 = cube-root tiled kernel (default when
- *                          maxdisp == 3*Dl and Wl % 4 == 0); 3 = as 2 with the lambda correction at every step + TwoSum totals
+ *                          maxdisp == 3*Dl and Wl % 4 == 0); 3 = as 2 with the lambda correction at every step + TwoSum totals;
+ *                          4 = 2 as a persistent grid of 3 CTAs per SM (co-resident SM sharing)
  *   rag_disp_head_bwd_v    0 = any-ratio gather; 1 = block-row tasks, parts added in place (default when maxdisp == 3*Dl);
- *                          2 = same with scratch + combine kernel
+ *                          2 = same with scratch + combine kernel; 3 = 1 as a persistent grid of 3 CTAs per SM (co-resident)
  *   rag_cv_stem_fwd_v      0 = direct (any shape); 1 = collapsed, scalar; 2 = default (packed phase 1)
- * Callers that overlap the two kernels of the path on two streams (the cost volume of one batch with the disparity head
- * of another, rag_b200.pipeline.OverlappedPath) launch the cost volume FIRST with RAG_CV_FWD_SHARED -- a persistent grid
- * of one 512-thread CTA per SM whose store stream leaves most of the SM to the FP32-bound head. */
+ * SM sharing.  The volume kernels are HBM bound and need few issue slots, the head kernels are FP32 bound and need little
+ * bandwidth: on two streams they can share the SMs (rag_b200.pipeline).  Two ways:
+ *  - launch order (inference): the cost volume is launched FIRST with RAG_CV_FWD_SHARED -- a persistent grid of one
+ *    512-thread CTA per SM that is resident at once -- and the head's CTAs are dispatched beside it;
+ *  - co-resident (training step; free-running streams cannot control the launch order): ALL four kernels run as persistent
+ *    grids whose CTAs fit an SM together -- the volume kernel in a quarter of the register file (RAG_CV_FWD_SLIM: 256 threads
+ *    x 48 registers; RAG_CV_BWD_SLIM: 256 threads x 64 registers, its ~96 KB of in-flight reads parked in SHARED memory by
+ *    cp.async instead of in registers), three 128-thread x 128-register head CTAs in the rest (RAG_HEAD_FWD_SHARED,
+ *    RAG_HEAD_BWD_SHARED) -- so they overlap whichever is launched first.  Every variant gives the same bits as the default. */
 #define RAG_CV_FWD_LEAN 2     /* default with a workspace: persistent, one 256-thread CTA per SM                  */
-#define RAG_CV_FWD_SHARED 3   /* same kernel, one 512-thread CTA per SM: best when sharing SMs with the head        */
+#define RAG_CV_FWD_SHARED 3   /* same kernel, one 512-thread CTA per SM: best when launched before the head forward */
+#define RAG_CV_FWD_SLIM 5     /* same kernel, 256 threads x 1 vector: a quarter of the register file (co-resident)  */
 #define RAG_CV_BWD_SHARED 2   /* backward as a persistent grid: launched first, it leaves room for the head backward */
+#define RAG_CV_BWD_SLIM 3     /* backward through a shared-memory cp.async ring: a quarter of the register file     */
+#define RAG_HEAD_FWD_SHARED 4 /* head forward as a persistent grid of 3 CTAs per SM                                 */
+#define RAG_HEAD_BWD_SHARED 3 /* head backward as a persistent grid of 3 CTAs per SM                                */
 RAG_API int rag_cost_volume_fwd_v(const float* x, const float* y, float* cost,
                           int B, int C, int Df, int Hf, int Wf, void* workspace, int variant, void* stream);
 RAG_API int rag_cost_volume_bwd_v(const float* gcost, float* gx, float* gy,

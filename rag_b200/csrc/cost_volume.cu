@@ -16,6 +16,8 @@
 //   Df-1 down to 0 accumulating in fp32 -- exactly the order in which autograd accumulates the
 //   CopySlices gradients -- so the result is bit-identical to the reference; loads are 128-bit,
 //   coalesced, and issued U disparities ahead of the dependent adds.  No atomics, no reduction tree.
+#include <cuda_pipeline.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -221,6 +223,144 @@ cv_bwd_v4_persistent_kernel(const float* __restrict__ g, float* __restrict__ gx,
     }
 }
 
+// RAG_CV_BWD_SLIM: the same sums with the in-flight bytes in SHARED MEMORY instead of registers.  The vector kernel
+// above keeps 12 x 16 bytes per thread in flight in 48 registers, so saturating HBM takes ~37 K registers per SM and
+// the FP32-bound head backward (128 registers x 128 threads per CTA) finds room for one CTA beside it.  Here a CTA of NT
+// threads streams its items (b*C + c, block of NT vectors) through a ring of S stages of four disparities each with
+// cp.async (LDGSTS: global -> shared, no register staging): ~(S-1) x 4 x (2 NT + 1) x 16 bytes in flight per CTA at
+// 64 registers per thread, i.e. ONE 256-thread CTA per SM (a quarter of the register file, 96 KB in flight) carries the
+// read stream and three head-backward CTAs fit beside it.  The ring runs across item boundaries (stage n of the CTA's flattened (item, q) sequence), one block barrier
+// per stage.  Same arithmetic as cv_bwd_v4_unit -- per output element a sequential fp32 sum over d descending, the same
+// predicates -- so the result is bit-identical.
+// shared: float4 [S][4][2 NT + 2]: per disparity NT left vectors | NT + 1 right vectors (the block's window shifted by q) | pad
+template <int NT, int S>
+__global__ void __launch_bounds__(NT)
+cv_bwd_staged_kernel(const float* __restrict__ g, float* __restrict__ gx, float* __restrict__ gy,
+                     int BC, int C, int Df, int Hf, int Wf, int n_blk) {
+    constexpr int ROW = 2 * NT + 2;
+    extern __shared__ __align__(16) float4 cbs_smem[];
+    const int t = threadIdx.x;
+    const int Wv = Wf >> 2, PV = Hf * Wv, nq = (Df + 3) >> 2;
+    const long long n_items = (long long)BC * n_blk;
+    if ((long long)blockIdx.x >= n_items) return;
+    const int n_my = (int)((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    const float4* gv = reinterpret_cast<const float4*>(g);
+    const size_t PV4 = (size_t)4 * PV;
+
+    // ---- producer side: the CTA's stages in order -- items blockIdx.x + k * gridDim.x, inside an item q = nq-1 .. 0
+    // (disparities 4q .. 4q+3).  All per-stage state advances incrementally: no division outside the item set-up.
+    int i_left = n_my * nq, i_slot = 0, i_q = 0, i_wv = 0, i_wvx = 0, i_p = 0, i_px = 0;
+    long long i_item = (long long)blockIdx.x - gridDim.x;
+    const float4* i_pl = gv;      // left  vector p       of disparity 4 i_q
+    const float4* i_pr = gv;      // right vector p + i_q of disparity 4 i_q
+    const float4* i_prx = gv;     // right vector (block end) + i_q: the window's extra vector, fetched by thread 0
+    auto issue_item = [&]() {
+        i_item += gridDim.x;
+        const int bc = (int)(i_item / n_blk), blk = (int)(i_item - (long long)bc * n_blk);
+        const int b = bc / C, c = bc - b * C;
+        i_p = blk * NT + t;
+        i_wv = i_p % Wv;
+        i_px = blk * NT + NT;
+        i_wvx = i_px % Wv;
+        i_q = nq - 1;
+        const float4* gl = gv + (size_t)(b * 2 * C + c) * Df * PV + (size_t)i_q * PV4;
+        i_pl = gl + i_p;
+        i_pr = gl + (size_t)C * Df * PV + i_p + i_q;
+        i_prx = gl + (size_t)C * Df * PV + i_px + i_q;
+    };
+    issue_item();
+    auto issue = [&]() {
+        if (i_left > 0) {
+            float4* st = cbs_smem + (size_t)i_slot * 4 * ROW;
+            const bool lf = i_p < PV && i_q <= i_wv;                     // some w of the vector has w >= d in this stage
+            const bool rA = i_p + i_q < PV && i_wv + i_q < Wv;          // vector p + q is somebody's in-row "A" or "B" vector
+            const bool rX = t == 0 && i_px + i_q < PV && i_wvx + i_q < Wv;
+            const int nd = min(4, Df - 4 * i_q);
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd) {
+                if (dd < nd) {
+                    if (lf) __pipeline_memcpy_async(st + dd * ROW + t, i_pl + (size_t)dd * PV, 16);
+                    if (rA) __pipeline_memcpy_async(st + dd * ROW + NT + t, i_pr + (size_t)dd * PV, 16);
+                    if (rX) __pipeline_memcpy_async(st + dd * ROW + 2 * NT, i_prx + (size_t)dd * PV, 16);
+                }
+            }
+            --i_left;
+            i_slot = i_slot + 1 == S ? 0 : i_slot + 1;
+            if (i_q == 0) {
+                if (i_left > 0) issue_item();
+            } else {
+                --i_q;
+                i_pl -= PV4; i_pr -= PV4 + 1; i_prx -= PV4 + 1;
+            }
+        }
+        __pipeline_commit();
+    };
+#pragma unroll 1
+    for (int n = 0; n < S - 1; ++n) issue();
+
+    // ---- consumer side ----
+    float4 ax = make_float4(0.f, 0.f, 0.f, 0.f), ay = ax;
+    int c_wv = 0, c_q = 0, c_slot = 0;
+    bool c_valid = false;
+    size_t c_out = 0;
+    long long c_item = (long long)blockIdx.x - gridDim.x;
+#pragma unroll 1
+    for (int n = n_my * nq; n > 0; --n) {
+        if (c_q == 0) {                                   // first stage of the next item
+            c_item += gridDim.x;
+            const int bc = (int)(c_item / n_blk), blk = (int)(c_item - (long long)bc * n_blk);
+            const int p = blk * NT + t;
+            c_valid = p < PV;
+            c_wv = p % Wv;
+            c_out = (size_t)bc * PV + p;
+            c_q = nq;
+            ax = make_float4(0.f, 0.f, 0.f, 0.f);
+            ay = ax;
+        }
+        --c_q;
+        __pipeline_wait_prior(S - 2);                 // this thread's copies of the stage have landed ...
+        __syncthreads();                              // ... and everybody's; the previous stage is consumed
+        issue();                                      // refills the previous stage's buffer
+        const float4* st = cbs_smem + (size_t)c_slot * 4 * ROW;
+        c_slot = c_slot + 1 == S ? 0 : c_slot + 1;
+        const bool inA = c_valid && (c_wv + c_q) < Wv;
+        const bool inB = c_valid && (c_wv + c_q + 1) < Wv;
+        const bool lf = c_valid && c_q <= c_wv;
+        const bool diag = c_q == c_wv;                // the vector straddles w == d: element e counts when e >= d & 3
+        const int nd = min(4, Df - 4 * c_q);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int sft = 3 - u;                    // d = 4 c_q + sft, descending
+            if (sft < nd) {
+                if (lf) {
+                    const float4 tl = st[sft * ROW + t];
+                    if (!diag || sft <= 0) ax.x = ax.x + tl.x;
+                    if (!diag || sft <= 1) ax.y = ax.y + tl.y;
+                    if (!diag || sft <= 2) ax.z = ax.z + tl.z;
+                    ax.w = ax.w + tl.w;
+                }
+                if (inA) {
+                    const float4 ta = st[sft * ROW + NT + t];
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 tb = (inB && sft > 0) ? st[sft * ROW + NT + t + 1] : z;
+                    const float e0 = sft == 0 ? ta.x : sft == 1 ? ta.y : sft == 2 ? ta.z : ta.w;
+                    const float e1 = sft == 0 ? ta.y : sft == 1 ? ta.z : sft == 2 ? ta.w : tb.x;
+                    const float e2 = sft == 0 ? ta.z : sft == 1 ? ta.w : sft == 2 ? tb.x : tb.y;
+                    const float e3 = sft == 0 ? ta.w : sft == 1 ? tb.x : sft == 2 ? tb.y : tb.z;
+                    ay.x = ay.x + e0;
+                    if (sft + 1 <= 3 || inB) ay.y = ay.y + e1;
+                    if (sft + 2 <= 3 || inB) ay.z = ay.z + e2;
+                    if (sft + 3 <= 3 || inB) ay.w = ay.w + e3;
+                }
+            }
+        }
+        if (c_q == 0 && c_valid) {
+            reinterpret_cast<float4*>(gx)[c_out] = ax;
+            reinterpret_cast<float4*>(gy)[c_out] = ay;
+        }
+    }
+}
+
 // Scalar path (any Wf).  grid: x over Hf*Wf elements, y = c, z = b.
 template <int NT>
 __global__ void __launch_bounds__(NT)
@@ -303,7 +443,7 @@ static int arm_counter(void* workspace, cudaStream_t st, const char* who) {
 // disparity head share the SMs on a second stream).
 template <int NT, int VPT>
 static int launch_cv_fwd_lean(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
-                              int per_sm, unsigned int* ctr, cudaStream_t st) {
+                              int per_sm, unsigned int* ctr, cudaStream_t st, int dchunk_max = 16) {
     const int Wv = Wf / 4, Df4 = (Df + 3) & ~3;
     const size_t row_bytes = (size_t)16 * (Df4 + Wf + 4);          // four images of one row
     int R = std::min(Hf, (NT * VPT) / Wv);
@@ -319,7 +459,7 @@ static int launch_cv_fwd_lean(const float* x, const float* y, float* cost, int B
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return fail((int)e, "cost_volume_fwd(lean): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const int n_tiles = (Hf + R - 1) / R;
-    const int dchunk = std::min(16, (Df + 3) & ~3);
+    const int dchunk = std::min(dchunk_max, (Df + 3) & ~3);
     const int n_dchunks = (Df + dchunk - 1) / dchunk;
     const long long n_items = (long long)B * C * n_tiles * n_dchunks;
     if (n_items >= (1LL << 31)) return fail(RAG_E_SHAPE, "cost_volume_fwd(lean): too many work items");
@@ -357,20 +497,23 @@ static int launch_cv_fwd_tma(const float* x, const float* y, float* cost, int B,
 
 // variant: -1 = default (lean persistent when a workspace is given, lean one-CTA-per-item without, generic when the
 // lean preconditions fail); 0 = generic; 1 = lean one CTA per item; 2 = lean persistent 256 threads (needs workspace);
-// 3 = lean persistent 512 threads, RAG_CV_FWD_SHARED (needs workspace); 4 = TMA bulk-store kernel (needs workspace)
+// 3 = lean persistent 512 threads, RAG_CV_FWD_SHARED (needs workspace); 4 = TMA bulk-store kernel (needs workspace);
+// 5 = lean persistent 256 threads x 1 vector, RAG_CV_FWD_SLIM (needs workspace)
 int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, int Df, int Hf, int Wf,
                     void* workspace, int variant, cudaStream_t st) {
     if (int e = check_cv_args(x, y, cost, B, C, Df, Hf, Wf)) return e;
-    if (variant < -1 || variant > 4) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 5) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
     unsigned int* ctr = static_cast<unsigned int*>(workspace);
     const bool lean = cv_lean_ok(x, y, cost, Wf) && (Wf / 4) <= 512;
     if (variant == -1) variant = lean ? (ctr ? RAG_CV_FWD_LEAN : 1) : 0;
     if (variant >= 2 && !ctr) return fail(RAG_E_NULL, "cost_volume_fwd: variant %d needs a workspace of RAG_CV_FWD_WORKSPACE_BYTES", variant);
-    if (variant >= 1 && variant <= 3 && !lean)
+    if (((variant >= 1 && variant <= 3) || variant == 5) && !lean)
         return fail(RAG_E_VARIANT, "cost_volume_fwd: lean variants need Wf %% 4 == 0, Wf <= 2048 and 16-byte aligned pointers");
     if (variant == 1) return launch_cv_fwd_lean<256, 2>(x, y, cost, B, C, Df, Hf, Wf, 0, nullptr, st);
     if (variant == 2) return launch_cv_fwd_lean<256, 2>(x, y, cost, B, C, Df, Hf, Wf, 1, ctr, st);
     if (variant == 3) return launch_cv_fwd_lean<512, 1>(x, y, cost, B, C, Df, Hf, Wf, 1, ctr, st);
+    // RAG_CV_FWD_SLIM: 256 threads x 1 vector (at most 64 registers: a quarter of the register file per SM), 32 disparities per item
+    if (variant == 5) return launch_cv_fwd_lean<256, 1>(x, y, cost, B, C, Df, Hf, Wf, 1, ctr, st, 32);
     if (variant == 4) {
         if (!cv_tma_ok(x, y, cost, Df, Wf))
             return fail(RAG_E_VARIANT, "cost_volume_fwd: the TMA variant needs Wf %% 4 == 0, Df %% 4 == 0, Df <= Wf and 16-byte aligned pointers");
@@ -384,17 +527,37 @@ int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, i
 }
 
 // variant: 0 = default (128-bit vector kernel when Wf % 4 == 0 and aligned, else scalar); 1 = scalar;
-// 2 = RAG_CV_BWD_SHARED: the vector kernel as a persistent grid of 4 x 128-thread CTAs per SM (SM sharing)
+// 2 = RAG_CV_BWD_SHARED: the vector kernel as a persistent grid of 4 x 128-thread CTAs per SM (SM sharing);
+// 3 = RAG_CV_BWD_SLIM: cp.async ring in shared memory, one 256-thread CTA per SM with 4 stages (4: 3 stages, 5: 128 threads x
+// 6 stages -- A/B geometries of the same kernel)
 int cost_volume_bwd(const float* g, float* gx, float* gy, int B, int C, int Df, int Hf, int Wf,
                     int variant, cudaStream_t st) {
     if (int e = check_cv_args(g, gx, gy, B, C, Df, Hf, Wf)) return e;
-    if (variant < 0 || variant > 2) return fail(RAG_E_VARIANT, "cost_volume_bwd: unknown variant %d", variant);
+    if (variant < 0 || variant > 5) return fail(RAG_E_VARIANT, "cost_volume_bwd: unknown variant %d", variant);
     const bool a16 = aligned(g, 16) && aligned(gx, 16) && aligned(gy, 16);
-    if (variant == 2) {
-        if (!(Wf % 4 == 0 && a16)) return fail(RAG_E_VARIANT, "cost_volume_bwd: variant 2 needs Wf %% 4 == 0 and 16-byte aligned pointers");
+    if (variant >= 2) {
+        if (!(Wf % 4 == 0 && a16)) return fail(RAG_E_VARIANT, "cost_volume_bwd: variant %d needs Wf %% 4 == 0 and 16-byte aligned pointers", variant);
         constexpr int NT = 128;
         const int PV = Hf * (Wf / 4), n_blk = (PV + NT - 1) / NT;
         const long long n_items = (long long)B * C * n_blk;
+        if (variant >= 3) {   // RAG_CV_BWD_SLIM and its A/B geometries: cp.async ring in shared memory, one CTA per SM
+            auto launch = [&](auto kern, int nt, int stages) -> int {
+                const size_t smem = (size_t)stages * 4 * (2 * nt + 2) * sizeof(float4);
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                if (e != cudaSuccess) return fail((int)e, "cost_volume_bwd(staged): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                const int nb = (PV + nt - 1) / nt;
+                const long long items = (long long)B * C * nb;
+                const int grid = (int)std::min<long long>(items, (long long)num_sms());
+                kern<<<grid, nt, smem, st>>>(g, gx, gy, B * C, C, Df, Hf, Wf, nb);
+                return RAG_OK;
+            };
+            int rc = variant == 3 ? launch(cv_bwd_staged_kernel<256, 4>, 256, 4)
+                   : variant == 4 ? launch(cv_bwd_staged_kernel<256, 3>, 256, 3)
+                                  : launch(cv_bwd_staged_kernel<128, 6>, 128, 6);
+            if (rc) return rc;
+            return check_launch("cost_volume_bwd(staged)");
+        }
         const int grid = (int)std::min<long long>(n_items, (long long)num_sms() * 4);
         cv_bwd_v4_persistent_kernel<NT, 4><<<grid, NT, 0, st>>>(g, gx, gy, B * C, C, Df, Hf, Wf, n_blk);
     } else if (variant != 1 && Wf % 4 == 0 && a16) {

@@ -239,15 +239,18 @@ int upsample_trilinear(const float* cost, float* out, int B, int Dl, int Hl, int
 
 // variant: -1 = default; 0 = any (Dl, maxdisp) (one thread per output pixel, fp64 sums); 1 = first x3 kernel (any width);
 // 2 = cube-root tiled kernel (default when maxdisp == 3*Dl, Wl % 4 == 0, 16-byte aligned input); 3 = as 2 with the
-// fp32-lambda correction at every step and TwoSum totals (most accurate, A/B)
+// fp32-lambda correction at every step and TwoSum totals (most accurate, A/B); 4 = RAG_HEAD_FWD_SHARED: variant 2 as a
+// persistent grid of 3 CTAs per SM (SM sharing)
 int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, int Hl, int Wl, int D,
                   int variant, cudaStream_t st) {
     if (!cost || !disp) return fail(RAG_E_NULL, "disp_head_fwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 3) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 4) return fail(RAG_E_VARIANT, "disp_head_fwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
     if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl", variant);
+    const bool persistent = variant == 4;      // RAG_HEAD_FWD_SHARED: variant 2 as a persistent grid of 3 CTAs per SM
+    if (persistent) variant = 2;
     const bool tiled_ok = x3 && (Wl % 4 == 0) && aligned(cost, 16);
     if (variant >= 2 && !tiled_ok) return fail(RAG_E_VARIANT, "disp_head_fwd: variant %d needs maxdisp == 3*Dl, Wl %% 4 == 0 and 16-byte aligned cost_lr", variant);
     if (variant == -1) variant = tiled_ok ? 2 : (x3 ? 1 : 0);
@@ -255,13 +258,16 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
         // (5 block rows per CTA would fill the last wave of the 480x960 B=8 grid better, but 5 warps do not
         // spread evenly over the 4 SM sub-partitions: measured 202 us vs 165 us.)
         constexpr int warps = 4;
-        dim3 grid((Wl + 31) / 32, (Hl + warps - 1) / warps, B);
+        const int nbx = (Wl + 31) / 32, nby = (Hl + warps - 1) / warps;
+        const long long n_tl = (long long)nbx * nby * B;
+        if (n_tl >= (1LL << 31)) return fail(RAG_E_SHAPE, "disp_head_fwd: too many tiles");
+        const int grid = (int)(persistent ? std::min<long long>(n_tl, (long long)num_sms() * 3) : n_tl);
         const size_t smem = (size_t)2 * 16 * (warps + 2) * kTCols * sizeof(float) + ((size_t)18 * 32 * warps + 2 * Dl) * sizeof(float2);
         auto launch = [&](auto kern) -> int {
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return fail((int)e, "disp_head_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            kern<<<grid, 32 * warps, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd);
+            kern<<<grid, 32 * warps, smem, st>>>(cost, disp, stats, Dl, Hl, Wl, sd, nbx, nby, (int)n_tl);
             return RAG_OK;
         };
         const int e = variant == 3 ? launch(head_fwd_x3r_kernel<4, 4, 16, 2, 1, true>) : launch(head_fwd_x3r_kernel<4, 4, 16, 2, 2, false>);
@@ -280,22 +286,26 @@ int disp_head_fwd(const float* cost, float* disp, float* stats, int B, int Dl, i
 
 // variant: -1 = default; 0 = any-ratio gather; 1 = block-row tasks, one exp2 per pixel and k-block, both parts added
 // in place with red.global.add (default when maxdisp == 3*Dl); 2 = same with the "B" part to `scratch` + a combine
-// kernel (A/B; needs scratch)
+// kernel (A/B; needs scratch); 3 = RAG_HEAD_BWD_SHARED: variant 1 as a persistent grid of 3 CTAs per SM (SM sharing)
 int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, const float* stats, float* gcost, float* scratch,
                   int B, int Dl, int Hl, int Wl, int D, int variant, cudaStream_t st) {
     if (!cost || !gdisp || !disp || !stats || !gcost) return fail(RAG_E_NULL, "disp_head_bwd: null pointer");
     if (int e = check_head_args(B, Dl, Hl, Wl, D)) return e;
-    if (variant < -1 || variant > 2) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
+    if (variant < -1 || variant > 3) return fail(RAG_E_VARIANT, "disp_head_bwd: unknown variant %d", variant);
     const float sd = (float)Dl / (float)D, sh = (float)Hl / (float)(3 * Hl), sw = (float)Wl / (float)(3 * Wl);
     const bool x3 = (D == 3 * Dl);
     if (variant >= 1 && !x3) return fail(RAG_E_VARIANT, "disp_head_bwd: variant %d needs maxdisp == 3*Dl", variant);
     if (variant == 2 && !scratch) return fail(RAG_E_NULL, "disp_head_bwd: variant 2 needs a scratch buffer");
     if (variant == -1) variant = x3 ? 1 : 0;
     if (variant >= 1) {
+        const bool persistent = variant == 3;
+        if (persistent) variant = 1;
         const int nJ = (Dl + kBwJ - 1) / kBwJ;
         const int strips = (Wl + 30) / 31;
         const int n_tasks = (Hl + 1) * nJ;
-        dim3 grid(strips, (n_tasks + 3) / 4, B);
+        const long long n_ct = (long long)strips * ((n_tasks + 3) / 4) * B;
+        if (n_ct >= (1LL << 31)) return fail(RAG_E_SHAPE, "disp_head_bwd: too many tasks");
+        const int grid = (int)(persistent ? std::min<long long>(n_ct, (long long)num_sms() * 3) : n_ct);
         const size_t smem = (size_t)3 * (D + 3) * sizeof(float2) + (size_t)4 * kBwWin * sizeof(float);
         auto kern = variant == 1 ? head_bwd_x3w_kernel<true, true> : head_bwd_x3w_kernel<true, false>;
         if (variant == 1) {   // two commutative contributions per element into a zeroed buffer (see the kernel's header)
@@ -306,7 +316,7 @@ int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, cons
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "disp_head_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         }
-        kern<<<grid, 128, smem, st>>>(cost, gdisp, disp, stats, gcost, scratch, Dl, Hl, Wl, sd, nJ, n_tasks);
+        kern<<<grid, 128, smem, st>>>(cost, gdisp, disp, stats, gcost, scratch, Dl, Hl, Wl, sd, nJ, n_tasks, strips, (int)n_ct);
         if (int e = check_launch("disp_head_bwd(main)")) return e;
         if (variant == 1) return 0;
         const size_t n = (size_t)B * Dl * Hl * Wl;

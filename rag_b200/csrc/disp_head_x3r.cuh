@@ -99,13 +99,13 @@ __device__ __forceinline__ void x3r_step(const float& c, float& cn, float& c2, f
     q = __fmaf_rn(nk3, s2, c);
 }
 
-// grid: x = ceil(Wl/32), y = ceil(Hl/WARPS), z = B; 32*WARPS threads (a CTA owns WARPS block rows x 32 block
-// columns; the host picks WARPS in {4, 5} for the fuller last wave).
+// tiles: ceil(Wl/32) x ceil(Hl/WARPS) x B; 32*WARPS threads (a tile is WARPS block rows x 32 block columns); 1-D grid,
+// one tile per CTA or a persistent grid (see the tile loop).
 // smem: tile[STAGES][BINS][WARPS+2][kTCols] | float2 tot[18][NT] | float2 kap[Dl][2] ((k1,k1),(k2,k2))
 template <int WARPS, int MINB, int BINS, int STAGES, int CORR, bool TWOSUM>
 __global__ void __launch_bounds__(32 * WARPS, MINB)
 head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, float* __restrict__ stats,
-                    int Dl, int Hl, int Wl, float scale) {
+                    int Dl, int Hl, int Wl, float scale, int nbx, int nby, int n_tl) {
     static_assert(BINS % 2 == 0, "two bins are staged per pass");
     constexpr int NT = 32 * WARPS, ROWS = WARPS + 2, HALF = NT / 2;
     static_assert(HALF >= ROWS * (kTCols / 4), "half a CTA stages one bin slab per pass");
@@ -118,8 +118,31 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     float2* tot = reinterpret_cast<float2*>(x3r_smem + STAGES * kStageFloats);   // [18][128]
     float2* kap = tot + 18 * NT;                                                   // [Dl][2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.z;
-    const int C0 = blockIdx.x * 32, R0 = blockIdx.y * WARPS;
+    // kappa_q(j) = 3 ln2 (lambda_fp32(3j+1+q) - q/3), q = 1, 2: the 3 converts du (z/3 domain) to dz.
+    // lambda - fl(q/3) is exact in fp32 (Sterbenz); fl(1/3) - 1/3 = 2^-25/3, fl(2/3) - 2/3 = 2^-24/3.
+    // Once per CTA; published by the first chunk barrier of the first tile.
+    for (int j = tid; j < Dl; j += NT) {
+        float k12[2];
+#pragma unroll
+        for (int q = 1; q <= 2; ++q) {
+            int t0, t1;
+            float l0, l1;
+            src_index<true>(scale, min(3 * j + 1 + q, D - 1), Dl, t0, t1, l0, l1);
+            const float third = q == 1 ? 0.333333343267440796f : 0.666666686534881592f;
+            const float resid = q == 1 ? 9.934107e-9f : 1.9868214e-8f;
+            const float d = (t1 > t0) ? (l1 - third) + resid : 0.f;   // clamped top bin: no interval
+            k12[q - 1] = 2.0794415416798357f * d;
+        }
+        kap[2 * j + 0] = f2b(k12[0]);
+        kap[2 * j + 1] = f2b(k12[1]);
+    }
+    // tiles (32 block columns x WARPS block rows x image) tl = (b * nby + by) * nbx + bx; CTA blockIdx.x works on
+    // tl = blockIdx.x, blockIdx.x + gridDim.x, ...: one tile per CTA by default, a persistent grid of a few CTAs per SM
+    // (resident at once: RAG_HEAD_FWD_SHARED, rag_b200.pipeline) when the kernel shares the SMs with a volume kernel
+    for (int tl = blockIdx.x; tl < n_tl; tl += gridDim.x) {
+    const int tq = tl / nbx;
+    const int b = tq / nby;
+    const int C0 = (tl - tq * nbx) * 32, R0 = (tq - b * nby) * WARPS;
     const int T0 = C0 - 4;
     const size_t plane = (size_t)Hl * Wl;
     const float* base = cost + (size_t)b * Dl * plane;
@@ -150,23 +173,6 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     };
     issue_chunk(0);
     if (STAGES > 2) issue_chunk(1);
-    // kappa_q(j) = 3 ln2 (lambda_fp32(3j+1+q) - q/3), q = 1, 2: the 3 converts du (z/3 domain) to dz.
-    // lambda - fl(q/3) is exact in fp32 (Sterbenz); fl(1/3) - 1/3 = 2^-25/3, fl(2/3) - 2/3 = 2^-24/3.
-    for (int j = tid; j < Dl; j += NT) {
-        float k12[2];
-#pragma unroll
-        for (int q = 1; q <= 2; ++q) {
-            int t0, t1;
-            float l0, l1;
-            src_index<true>(scale, min(3 * j + 1 + q, D - 1), Dl, t0, t1, l0, l1);
-            const float third = q == 1 ? 0.333333343267440796f : 0.666666686534881592f;
-            const float resid = q == 1 ? 9.934107e-9f : 1.9868214e-8f;
-            const float d = (t1 > t0) ? (l1 - third) + resid : 0.f;   // clamped top bin: no interval
-            k12[q - 1] = 2.0794415416798357f * d;
-        }
-        kap[2 * j + 0] = f2b(k12[0]);
-        kap[2 * j + 1] = f2b(k12[1]);
-    }
     float2* mytot = tot + tid;
 #pragma unroll
     for (int s = 0; s < 18; ++s) mytot[s * NT] = f2b(0.f);
@@ -397,8 +403,7 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
         so.T = so.c2 * __fmaf_rn(nk1, so.c[0], so.q);
     }
     fold();
-    if (!active) return;
-
+    if (active) {
     const size_t img = (size_t)3 * Hl * W;
     float* dp = disp + (size_t)b * img + (size_t)(3 * r) * W + 3 * c;
     float* sp = stats ? stats + (size_t)b * 2 * img + (size_t)(3 * r) * W + 3 * c : nullptr;
@@ -434,6 +439,8 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
         const float2 d = mytot[16 * NT], n = mytot[17 * NT];
         emit(1, 1, d.x, d.y, n.x, n.y, mnegS);
     }
+    }   // active
+    }   // tile loop
 }
 
 }  // namespace rag

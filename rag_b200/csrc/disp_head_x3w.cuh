@@ -12,7 +12,7 @@
 //     loop reads it at compile-time offsets;
 //   * the per-bin arithmetic runs on packed FP32 (FFMA2/FMUL2) with the pixel pairing of the forward
 //     (P0=(p00,p01) P1=(p10,p11) P2=(p20,p21) P3=(p02,p12) S=p22).
-// grid: x = ceil(Wl/31) strips, y = ceil((Hl+1)*nJ / 4), z = B; 128 threads (4 independent warp tasks).
+// CTA-tasks: ceil(Wl/31) strips x ceil((Hl+1)*nJ / 4) task groups x B; 128 threads (4 independent warp tasks).
 #pragma once
 #include <cuda_pipeline.h>
 
@@ -40,11 +40,18 @@ constexpr int kBwWin = kBwBins * 2 * kBwCols;
 // exact), so the result does not depend on the order the two arrive in: still bitwise deterministic.
 // (red.global.add.f32 flushes subnormal addends and sums to zero, as PyTorch's own atomicAdd backward does;
 // against the scratch + combine variant the result differs at most by that and by the sign of a zero.)
+//
+// Grid: 1-D.  CTA-task ct = (b * ny + task group) * strips + strip, ny = ceil(n_tasks / 4); CTA `blockIdx.x` works on
+// ct = blockIdx.x, blockIdx.x + gridDim.x, ...: with gridDim.x = the number of CTA-tasks that is one CTA per CTA-task (the
+// default), with a grid of a few CTAs per SM it is a PERSISTENT grid that is resident at once -- what lets the kernel
+// share the SMs with a cost-volume kernel on another stream whichever of the two is launched first
+// (RAG_HEAD_BWD_SHARED, rag_b200.pipeline).  The warps of a CTA walk their task lists independently: the depth tables
+// are built once per CTA, nothing else is shared between tasks.
 template <bool CUBE, bool RED>
 __global__ void __launch_bounds__(128, 4)
 head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gdisp, const float* __restrict__ disp,
                     const float* __restrict__ stats, float* __restrict__ gcost, float* __restrict__ scratch,
-                    int Dl, int Hl, int Wl, float scale, int nJ, int n_tasks) {
+                    int Dl, int Hl, int Wl, float scale, int nJ, int n_tasks, int strips, int n_ct) {
     extern __shared__ __align__(16) float x3w_smem[];
     const int D = 3 * Dl, H = 3 * Hl, W = 3 * Wl;
     float2* lzb = reinterpret_cast<float2*>(x3w_smem);   // [D+3] (lambda1, lambda1) of bin k
@@ -71,15 +78,19 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int task = blockIdx.y * 4 + warp;
-    if (task >= n_tasks) return;
     float* win = win_all + warp * kBwWin;
+    const int ny = (n_tasks + 3) >> 2;
+    for (int ct = blockIdx.x; ct < n_ct; ct += gridDim.x) {
+    const int cq = ct / strips, strip = ct - cq * strips;
+    const int b = cq / ny;
+    const int task = (cq - b * ny) * 4 + warp;
+    if (task >= n_tasks) continue;
+    __syncwarp();                                         // the previous task's window reads are done
     const int rbi = task / nJ, jc = task - rbi * nJ;
     const int rb = rbi - 1;                               // block row, -1 .. Hl-1
     const int j0 = jc * kBwJ, j1 = min(j0 + kBwJ, Dl);
     const int jb0 = max(j0 - 1, 0);                       // first k-block (its B part feeds cell j0)
-    const int b = blockIdx.z;
-    const int c_first = blockIdx.x * 31 - 1;
+    const int c_first = strip * 31 - 1;
     const int c_raw = c_first + lane;
     const bool lane_on = c_raw <= Wl - 1;
     const int c = min(c_raw, Wl - 1);
@@ -163,7 +174,7 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
                 if (has_a) gout[(size_t)jb * plane + (size_t)rb * Wl + c] = 0.f;
                 if (has_b) sout[(size_t)jb * plane + (size_t)(rb + 1) * Wl + c] = 0.f;
             }
-        return;
+        continue;
     }
 
     // packed weights
@@ -334,6 +345,7 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
         for (int i = 0; i < 4; ++i) pg[i] = g1[i];
         pgS = g1S;
     }
+    }   // CTA-task loop
 }
 
 // gcost += scratch, with the rows that never receive a "B" part (row 0 gets block row -1's; all rows are

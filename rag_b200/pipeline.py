@@ -15,6 +15,21 @@ from . import functional as F_
 
 CV_FWD_SHARED = 3    # include/rag_b200.h RAG_CV_FWD_SHARED
 CV_BWD_SHARED = 2    # include/rag_b200.h RAG_CV_BWD_SHARED
+CV_FWD_SLIM = 5      # RAG_CV_FWD_SLIM
+CV_BWD_SLIM = 3      # RAG_CV_BWD_SLIM
+HEAD_FWD_SHARED = 4  # RAG_HEAD_FWD_SHARED
+HEAD_BWD_SHARED = 3  # RAG_HEAD_BWD_SHARED
+
+# kernel variants of a schedule: (cost-volume forward, head forward, cost-volume backward, head backward); None = default.
+# "launch-order": the volume kernels are persistent grids and must be launched before the head kernels they share the SMs
+# with (the head grids are not resident at once).  "coresident": all four are persistent grids whose CTAs fit an SM
+# TOGETHER -- volume kernel <= a quarter of the register file, three 128-register head CTAs in the rest -- so they share
+# the SMs whichever is launched first (free-running streams cannot control that order).
+SCHEDULES = {
+    "launch-order": (CV_FWD_SHARED, None, CV_BWD_SHARED, None),
+    "coresident": (CV_FWD_SLIM, HEAD_FWD_SHARED, CV_BWD_SLIM, HEAD_BWD_SHARED),
+    "slim-volume": (CV_FWD_SLIM, None, CV_BWD_SLIM, None),
+}
 
 
 class OverlappedPath:
@@ -28,11 +43,16 @@ class OverlappedPath:
     what lets the head's CTAs be dispatched next to it instead of behind it.
     """
 
-    def __init__(self, maxdisp: int = 192, device: torch.device | str = "cuda"):
+    schedule = "launch-order"
+
+    def __init__(self, maxdisp: int = 192, device: torch.device | str = "cuda", schedule: str | tuple | None = None):
         self.device = torch.device(device)
         self.maxdisp = maxdisp
         self.s_cv = torch.cuda.Stream(self.device)
         self.s_head = torch.cuda.Stream(self.device)
+        if schedule is not None:
+            self.schedule = schedule
+        self.variants = SCHEDULES[self.schedule] if isinstance(self.schedule, str) else tuple(self.schedule)
 
     def _fork(self):
         cur = torch.cuda.current_stream(self.device)
@@ -45,10 +65,11 @@ class OverlappedPath:
         Returns (cost, disp, stats_or_None); cost is valid on ``self.s_cv``, disp/stats on ``self.s_head``."""
         cur = self._fork()
         with torch.no_grad():
+            vcf, vhf = self._variants(x, cost_lr)[:2]
             with torch.cuda.stream(self.s_cv):
-                cost = F_.cost_volume_forward(x, y, int(self.maxdisp / 3), variant=CV_FWD_SHARED if x.shape[-1] % 4 == 0 else None)
+                cost = F_.cost_volume_forward(x, y, int(self.maxdisp / 3), variant=vcf)
             with torch.cuda.stream(self.s_head):
-                disp, stats = F_.disp_head_forward(cost_lr, self.maxdisp, want_stats=want_stats)
+                disp, stats = F_.disp_head_forward(cost_lr, self.maxdisp, want_stats=want_stats, variant=vhf)
         for t in (x, y):
             t.record_stream(self.s_cv)
         cost_lr.record_stream(self.s_head)
@@ -58,6 +79,17 @@ class OverlappedPath:
             if t is not None:
                 t.record_stream(cur)
         return cost, disp, stats
+
+    def _variants(self, x, cost_lr):
+        """The schedule's kernel variants where their preconditions hold (vector widths, x3 ratio), else the defaults."""
+        vcf, vhf, vcb, vhb = self.variants
+        if x.shape[-1] % 4 != 0:
+            vcf = vcb = None
+        if cost_lr.shape[-1] % 4 != 0 or self.maxdisp != 3 * cost_lr.shape[2]:
+            vhf = None
+        if self.maxdisp != 3 * cost_lr.shape[2]:
+            vhb = None
+        return vcf, vhf, vcb, vhb
 
     def join(self):
         """Make the current stream wait for everything enqueued so far."""
@@ -96,14 +128,14 @@ class OverlappedTrainPath(OverlappedPath):
     def step(self, x, y, cost_lr, gcost, gdisp):
         cur = self._fork()
         c = x.shape[1]
-        shared = x.shape[-1] % 4 == 0
+        vcf, vhf, vcb, vhb = self._variants(x, cost_lr)
         with torch.no_grad():
             with torch.cuda.stream(self.s_cv):
-                cost = F_.cost_volume_forward(x, y, int(self.maxdisp / 3), variant=CV_FWD_SHARED if shared else None)
-                gx, gy = F_.cost_volume_backward(gcost, c, variant=CV_BWD_SHARED if shared else None)
+                cost = F_.cost_volume_forward(x, y, int(self.maxdisp / 3), variant=vcf)
+                gx, gy = F_.cost_volume_backward(gcost, c, variant=vcb)
             with torch.cuda.stream(self.s_head):
-                disp, stats = F_.disp_head_forward(cost_lr, self.maxdisp, want_stats=True)
-                gcl = F_.disp_head_backward(cost_lr, gdisp, disp, stats, self.maxdisp)
+                disp, stats = F_.disp_head_forward(cost_lr, self.maxdisp, want_stats=True, variant=vhf)
+                gcl = F_.disp_head_backward(cost_lr, gdisp, disp, stats, self.maxdisp, variant=vhb)
         for t in (x, y, gcost):
             t.record_stream(self.s_cv)
         for t in (cost_lr, gdisp):

@@ -58,7 +58,7 @@ def test_forward_bit_exact(F_, shape):
     df = int(md / 3)
     tma = (4,) if (wf % 4 == 0 and df % 4 == 0 and df <= wf) else ()
     # None = default with a workspace (persistent lean kernel), "plain" = the stateless entry point without one
-    for variant in (None, "plain", 0) + ((1, 2, 3) if wf % 4 == 0 else ()) + tma:
+    for variant in (None, "plain", 0) + ((1, 2, 3, 5) if wf % 4 == 0 else ()) + tma:
         if variant == "plain":
             out = F_.cost_volume_forward(x.cuda(), y.cuda(), int(md / 3), workspace=False)
         else:
@@ -72,7 +72,8 @@ def test_backward_bit_exact(F_, shape):
     g = gen(1 + hash(shape) % 1000)
     gc = wide_grad((b, 2 * c, int(md / 3), hf, wf), g)
     gx_ref, gy_ref = O.cost_volume_grad_closed(gc.numpy(), c)
-    for variant in (None, 0, 1):
+    # 2 = persistent grid, 3-5 = the shared-memory cp.async ring (RAG_CV_BWD_SLIM and its A/B geometries)
+    for variant in (None, 0, 1) + ((2, 3, 4, 5) if wf % 4 == 0 else ()):
         gx, gy = F_.cost_volume_backward(gc.cuda(), c, variant=variant)
         assert np.array_equal(gx.cpu().numpy(), gx_ref), f"gx variant {variant}"
         assert np.array_equal(gy.cpu().numpy(), gy_ref), f"gy variant {variant}"

@@ -92,7 +92,7 @@ def test_forward_parity(F_, case):
     ref_cpu = O.disp_head_ref(cost, md).numpy()
     ref_gpu = O.disp_head_ref(cost.cuda(), md).cpu().numpy()
     d64, _ = O.disp_head_f64(cost[:, 0].numpy(), md)
-    variants = [None, 0] + ([1] if md == 3 * dl else []) + ([2, 3] if md == 3 * dl and wl % 4 == 0 else [])
+    variants = [None, 0] + ([1] if md == 3 * dl else []) + ([2, 3, 4] if md == 3 * dl and wl % 4 == 0 else [])
     for v in variants:
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=v)
         out = disp.cpu().numpy()
@@ -120,7 +120,7 @@ def test_backward_parity(F_, case):
         gd[0, 0, 0] = 1.0
     _, gref = O.disp_head_grad_ref(cost, gd, md)
     _, g64 = O.disp_head_grad_f64(cost[:, 0].numpy(), gd.numpy(), md)
-    variants = [None, 0] + ([1, 2] if md == 3 * dl else [])
+    variants = [None, 0] + ([1, 2, 3] if md == 3 * dl else [])
     for vf in ([None, 0] if md != 3 * dl else [None, 0, 1] + ([2, 3] if wl % 4 == 0 else [])):
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=vf)
         for v in variants:
@@ -156,14 +156,14 @@ def test_large_magnitude_costs_exercise_the_rescale_path(F_, sigma):
     # well conditioned = a 1-ulp change of the logits cannot move the result by more than ~1e-4
     top2 = np.sort(p64, axis=1)[:, -2:]
     clear = (top2[:, 1] > 0.999) | (sigma <= 30.0)
-    for v in (None, 0, 1, 2, 3):
+    for v in (None, 0, 1, 2, 3, 4):
         disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True, variant=v)
         out = disp.cpu().numpy()
         assert np.isfinite(out).all() and out.min() >= 0 and out.max() <= md - 1, f"variant {v}"
         tol = 2e-3 if sigma <= 30.0 else 1e-2
         assert np.abs(out - d64)[clear].max() <= tol, f"variant {v}: {np.abs(out - d64)[clear].max()}"
         assert torch.isfinite(stats).all()
-        for vb in (0, 1, 2):
+        for vb in (0, 1, 2, 3):
             gc = F_.disp_head_backward(cost.cuda(), gd.cuda(), disp, stats, md, variant=vb).cpu().numpy()
             assert np.isfinite(gc).all(), f"fwd {v} bwd {vb}"
             if sigma <= 30.0:
@@ -181,7 +181,7 @@ def test_backward_with_spatially_coherent_zero_gradient(F_):
     _, g64 = O.disp_head_grad_f64(cost[:, 0].numpy(), gd.numpy(), md)
     disp, stats = F_.disp_head_forward(cost.cuda(), md, want_stats=True)
     out0 = F_.disp_head_backward(cost.cuda(), gd.cuda(), disp, stats, md, variant=0)
-    for v in (1, 2):
+    for v in (1, 2, 3):
         out1 = F_.disp_head_backward(cost.cuda(), gd.cuda(), disp, stats, md, variant=v)
         assert maxnorm_rel(out1.cpu().numpy()[:, 0], g64) <= TOL_GRAD
         assert maxnorm_rel(out1.cpu().numpy(), out0.cpu().numpy()) <= TOL_GRAD

@@ -39,7 +39,7 @@ def test_cost_volume_guards(L, shape):
     g = gen(1)
     x, y = randn((b, c, hf, wf), g).cuda(), randn((b, c, hf, wf), g).cuda()
     n = b * 2 * c * df * hf * wf
-    variants = [-1, 0] + ([1, 2, 3] if wf % 4 == 0 else []) + ([4] if (wf % 4 == 0 and df % 4 == 0 and df <= wf) else [])
+    variants = [-1, 0] + ([1, 2, 3, 5] if wf % 4 == 0 else []) + ([4] if (wf % 4 == 0 and df % 4 == 0 and df <= wf) else [])
     for v in variants:
         buf, out = window(n)
         wbuf, ws = window(4)                       # the 16-byte work-counter workspace, itself behind guard bands
@@ -51,7 +51,7 @@ def test_cost_volume_guards(L, shape):
         assert not (out == CANARY).any(), f"cv_fwd variant {v} left output elements unwritten"
     gc = randn((b, 2 * c, df, hf, wf), g).cuda()
     m = b * c * hf * wf
-    for v in (0, 1):
+    for v in (0, 1) + ((2, 3, 4, 5) if wf % 4 == 0 else ()):
         bx, gx = window(m)
         by, gy = window(m)
         assert L.rag_cost_volume_bwd_v(gc.data_ptr(), gx.data_ptr(), gy.data_ptr(), b, c, df, hf, wf, v, st()) == 0
@@ -67,7 +67,7 @@ def test_head_guards(L, shape):
     cl = randn((b, 1, dl, hl, wl), g).cuda()
     npx = b * 9 * hl * wl
     x3 = md == 3 * dl
-    fv = [0] + ([1] if x3 else []) + ([2, 3] if x3 and wl % 4 == 0 else [])
+    fv = [0] + ([1] if x3 else []) + ([2, 3, 4] if x3 and wl % 4 == 0 else [])
     for v in fv:
         bd, disp = window(npx)
         bs, stats = window(2 * npx)
@@ -77,7 +77,7 @@ def test_head_guards(L, shape):
         assert not (disp == CANARY).any() and not (stats == CANARY).any(), f"head_fwd variant {v} left outputs unwritten"
     gd = randn((b, 3 * hl, 3 * wl), g).cuda()
     nv = b * dl * hl * wl
-    for v in [0] + ([1, 2] if x3 else []):
+    for v in [0] + ([1, 2, 3] if x3 else []):
         bg, gcl = window(nv)
         bsc, scr = window(nv)
         assert L.rag_disp_head_bwd_v(cl.data_ptr(), gd.data_ptr(), disp.data_ptr(), stats.data_ptr(), gcl.data_ptr(), scr.data_ptr(), b, dl, hl, wl, md, v, st()) == 0

@@ -212,13 +212,16 @@ def test_host_train_pipeline_matches_the_functions(dev):
     assert np.array_equal(r["gx"].numpy(), gx_ref) and np.array_equal(r["gy"].numpy(), gy_ref)
 
 
-def test_overlapped_train_path_matches_the_serial_functions(dev):
+@pytest.mark.parametrize("schedule", ["launch-order", "coresident", "slim-volume"])
+def test_overlapped_train_path_matches_the_serial_functions(dev, schedule):
+    """Every schedule of the two-stream training step (rag_b200.pipeline.SCHEDULES: persistent / co-resident kernel
+    variants) gives the bits of the plain serial calls."""
     from rag_b200 import functional as F_
     from rag_b200.pipeline import OverlappedTrainPath
 
     g = gen(37)
     md = 96
-    op = OverlappedTrainPath(md, dev)
+    op = OverlappedTrainPath(md, dev, schedule=schedule)
     x, y = randn((2, 12, 9, 64), g).to(dev), randn((2, 12, 9, 64), g).to(dev)
     cl = randn((2, 1, 32, 9, 64), g).to(dev)
     gd = randn((2, 27, 192), g).to(dev)

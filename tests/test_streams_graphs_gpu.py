@@ -82,7 +82,8 @@ def test_non_current_device():
         CostVolume(48)(x.to("cuda:0"), y.to("cuda:1"))
 
 
-def test_overlapped_path_matches_the_serial_modules():
+@pytest.mark.parametrize("schedule", ["launch-order", "coresident"])
+def test_overlapped_path_matches_the_serial_modules(schedule):
     """Two-stream schedule (cost volume on one stream, head on another, many steps in flight): every step's
     outputs are bit-identical to the serial modules' (every launch of the persistent cost-volume kernel gets its own
     freshly zeroed work counter; a stale or shared counter would leave rows unwritten)."""
@@ -91,7 +92,7 @@ def test_overlapped_path_matches_the_serial_modules():
 
     g = gen(8)
     md = 96
-    op = OverlappedPath(md)
+    op = OverlappedPath(md, schedule=schedule)
     batches = [(randn((2, 12, 9, 64), g).cuda(), randn((2, 12, 9, 64), g).cuda(), randn((2, 1, 32, 9, 64), g).cuda()) for _ in range(4)]
     outs = []
     for rep in range(40):                       # far more launches than counter slots in flight
