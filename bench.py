@@ -642,7 +642,7 @@ def run_gpu(args):
             del out
             return t0.elapsed_time(t1)
 
-        opath = OverlappedTrainPath(md, dev) if bwd else OverlappedPath(md, dev)
+        opath = OverlappedTrainPath(md, dev, schedule=args.schedule) if bwd else OverlappedPath(md, dev, schedule=args.schedule)
 
         def overlapped_step():
             if bwd:
@@ -709,7 +709,7 @@ def run_gpu(args):
         cv_ms = seg_ms[0] / n_sub                       # average duration of ONE cost-volume launch
         achieved = cvb * sub / (cv_ms * 1e-3) / 1e9
         lean = wf % 4 == 0
-        kname = "cv_fwd_lean_kernel<256,2,true>" if lean else "cv_fwd_kernel"
+        kname = "cv_fwd_lean_kernel<256,1,true>" if lean else "cv_fwd_kernel"
         roofline = {
             "bound": "hbm", "kernel": kname + " (cost-volume forward)",
             "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
@@ -739,9 +739,13 @@ def run_gpu(args):
             "serial": {"ms_per_step": round(sstep_ms, 5), "pairs_per_s": round(world * b / (sstep_ms * 1e-3), 1), "frac_of_hbm_peak": frac(sstep_ms)},
             "kernel_ms": {k: round(v, 5) for k, v in kernels.items()},
             "kernel_frac_of_hbm_peak": {k: round(v, 4) for k, v in kfrac.items()},
-            "schedule_note": ("overlapped = the volume kernels on one stream (persistent grids, launched first) and the head kernels on another "
-                              "(rag_b200.pipeline.%s); the kernels of a step have no data dependence on each other (in the network the Matching Net "
-                              "sits between them), so a stream of batches overlaps them; serial = back to back on one stream" % type(opath).__name__),
+            "kernel_schedule": {"name": args.schedule, "variants(cv_fwd, head_fwd, cv_bwd, head_bwd)": list(opath.variants)},
+            "schedule_note": ("overlapped = the volume kernels on one stream and the head kernels on another (rag_b200.pipeline.%s, schedule '%s': "
+                              "'coresident' = all kernels as persistent grids whose CTAs fit an SM together -- the volume kernel in a quarter of the "
+                              "register file, its in-flight reads in shared memory, three head CTAs in the rest -- so they share the SMs whichever "
+                              "is launched first; 'launch-order' = persistent volume kernels launched before plain head grids); the kernels of a step "
+                              "have no data dependence on each other (in the network the Matching Net sits between them), so a stream of batches "
+                              "overlaps them; serial = back to back on one stream" % (type(opath).__name__, args.schedule)),
             "note": "the head kernels are FP32-pipe bound (one exp2 + 7-12 FP32 ops per pixel per low-res bin), not HBM bound; see DESIGN.md",
         }
         rec = {"value": world * b * K / (total_ms * 1e-3), "value_serial": world * b * K / (serial_ms * 1e-3), "ms_per_step": step_ms,
@@ -891,6 +895,8 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="infer")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the host-side legs (cpu_baseline, parity, torch_cuda_reference, next_rows)")
+    ap.add_argument("--schedule", choices=["coresident", "launch-order", "slim-volume"], default="coresident",
+                    help="kernel variants of the two-stream schedule (rag_b200.pipeline.SCHEDULES)")
     ap.add_argument("--graph", action="store_true", help="additionally time the two-stream step as CUDA-graph replays (path.overlapped_graph)")
     ap.add_argument("--no-train-record", action="store_true", help="default workload only: skip the configs[2] training sub-record")
     args = ap.parse_args()

@@ -115,10 +115,11 @@ RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int 
 /* ---- variants (A/B measurement and fallbacks; the functions above pick the default) ----------
  * Variant ids (-1 = the default; ids outside a range return RAG_E_VARIANT):
  *   rag_cost_volume_fwd_v  0 = any width / alignment (items dealt to threads); 1 = lean thread-stationary kernel, one CTA
- *                          per item (default without a workspace when Wf % 4 == 0); 2 = lean persistent, 256 threads, one
- *                          CTA per SM (default with a workspace); 3 = lean persistent, 512 threads (SM sharing, launch order);
+ *                          per item (default without a workspace when Wf % 4 == 0); 2 = lean persistent, 256 threads x 2
+ *                          vectors, one CTA per SM; 3 = lean persistent, 512 threads (SM sharing, launch order);
  *                          4 = TMA bulk-store kernel (cp.async.bulk shared->global); 5 = lean persistent, 256 threads x 1
- *                          vector at <= 64 registers (co-resident SM sharing).  2-5 need the workspace.
+ *                          vector at 48 registers, 32 disparities per item (default with a workspace; co-resident SM
+ *                          sharing).  2-5 need the workspace.
  *   rag_cost_volume_bwd_v  0 = 128-bit vector kernel (default when Wf % 4 == 0), 1 = scalar (any width),
  *                          2 = the vector kernel as a persistent grid of 4 CTAs per SM (SM sharing, launch order);
  *                          3 = cp.async ring in shared memory, one 256-thread CTA per SM at 64 registers (co-resident SM
@@ -138,9 +139,10 @@ RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int 
  *    x 48 registers; RAG_CV_BWD_SLIM: 256 threads x 64 registers, its ~96 KB of in-flight reads parked in SHARED memory by
  *    cp.async instead of in registers), three 128-thread x 128-register head CTAs in the rest (RAG_HEAD_FWD_SHARED,
  *    RAG_HEAD_BWD_SHARED) -- so they overlap whichever is launched first.  Every variant gives the same bits as the default. */
-#define RAG_CV_FWD_LEAN 2     /* default with a workspace: persistent, one 256-thread CTA per SM                  */
+#define RAG_CV_FWD_LEAN 2     /* persistent, one 256-thread CTA per SM, 2 vectors per thread (the default of round 1) */
 #define RAG_CV_FWD_SHARED 3   /* same kernel, one 512-thread CTA per SM: best when launched before the head forward */
-#define RAG_CV_FWD_SLIM 5     /* same kernel, 256 threads x 1 vector: a quarter of the register file (co-resident)  */
+#define RAG_CV_FWD_SLIM 5     /* default with a workspace: 256 threads x 1 vector, 32 disparities per item -- a quarter of
+                               * the register file (co-resident SM sharing) and the fastest geometry alone as well    */
 #define RAG_CV_BWD_SHARED 2   /* backward as a persistent grid: launched first, it leaves room for the head backward */
 #define RAG_CV_BWD_SLIM 3     /* backward through a shared-memory cp.async ring: a quarter of the register file     */
 #define RAG_HEAD_FWD_SHARED 4 /* head forward as a persistent grid of 3 CTAs per SM                                 */

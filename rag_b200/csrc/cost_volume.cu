@@ -495,7 +495,7 @@ static int launch_cv_fwd_tma(const float* x, const float* y, float* cost, int B,
     return check_launch("cost_volume_fwd(tma)");
 }
 
-// variant: -1 = default (lean persistent when a workspace is given, lean one-CTA-per-item without, generic when the
+// variant: -1 = default (lean persistent (variant 5) when a workspace is given, lean one-CTA-per-item without, generic when the
 // lean preconditions fail); 0 = generic; 1 = lean one CTA per item; 2 = lean persistent 256 threads (needs workspace);
 // 3 = lean persistent 512 threads, RAG_CV_FWD_SHARED (needs workspace); 4 = TMA bulk-store kernel (needs workspace);
 // 5 = lean persistent 256 threads x 1 vector, RAG_CV_FWD_SLIM (needs workspace)
@@ -505,7 +505,7 @@ int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, i
     if (variant < -1 || variant > 5) return fail(RAG_E_VARIANT, "cost_volume_fwd: unknown variant %d", variant);
     unsigned int* ctr = static_cast<unsigned int*>(workspace);
     const bool lean = cv_lean_ok(x, y, cost, Wf) && (Wf / 4) <= 512;
-    if (variant == -1) variant = lean ? (ctr ? RAG_CV_FWD_LEAN : 1) : 0;
+    if (variant == -1) variant = lean ? (ctr ? RAG_CV_FWD_SLIM : 1) : 0;   // the slim geometry is also the fastest alone
     if (variant >= 2 && !ctr) return fail(RAG_E_NULL, "cost_volume_fwd: variant %d needs a workspace of RAG_CV_FWD_WORKSPACE_BYTES", variant);
     if (((variant >= 1 && variant <= 3) || variant == 5) && !lean)
         return fail(RAG_E_VARIANT, "cost_volume_fwd: lean variants need Wf %% 4 == 0, Wf <= 2048 and 16-byte aligned pointers");

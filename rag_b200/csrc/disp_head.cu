@@ -307,7 +307,7 @@ int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, cons
         if (n_ct >= (1LL << 31)) return fail(RAG_E_SHAPE, "disp_head_bwd: too many tasks");
         const int grid = (int)(persistent ? std::min<long long>(n_ct, (long long)num_sms() * 3) : n_ct);
         const size_t smem = (size_t)3 * (D + 3) * sizeof(float2) + (size_t)4 * kBwWin * sizeof(float);
-        auto kern = variant == 1 ? head_bwd_x3w_kernel<true, true> : head_bwd_x3w_kernel<true, false>;
+        auto kern = persistent ? head_bwd_x3w_kernel<true, true, true> : variant == 1 ? head_bwd_x3w_kernel<true, true> : head_bwd_x3w_kernel<true, false>;
         if (variant == 1) {   // two commutative contributions per element into a zeroed buffer (see the kernel's header)
             cudaError_t e = cudaMemsetAsync(gcost, 0, (size_t)B * Dl * Hl * Wl * sizeof(float), st);
             if (e != cudaSuccess) return fail((int)e, "disp_head_bwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
@@ -316,7 +316,8 @@ int disp_head_bwd(const float* cost, const float* gdisp, const float* disp, cons
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "disp_head_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         }
-        kern<<<grid, 128, smem, st>>>(cost, gdisp, disp, stats, gcost, scratch, Dl, Hl, Wl, sd, nJ, n_tasks, strips, (int)n_ct);
+        if (persistent) kern<<<grid, 128, smem, st>>>(cost, gdisp, disp, stats, gcost, scratch, Dl, Hl, Wl, sd, nJ, n_tasks, strips, (int)n_ct);
+        else kern<<<dim3(strips, (n_tasks + 3) / 4, B), 128, smem, st>>>(cost, gdisp, disp, stats, gcost, scratch, Dl, Hl, Wl, sd, nJ, n_tasks, strips, (int)n_ct);
         if (int e = check_launch("disp_head_bwd(main)")) return e;
         if (variant == 1) return 0;
         const size_t n = (size_t)B * Dl * Hl * Wl;

@@ -41,13 +41,12 @@ constexpr int kBwWin = kBwBins * 2 * kBwCols;
 // (red.global.add.f32 flushes subnormal addends and sums to zero, as PyTorch's own atomicAdd backward does;
 // against the scratch + combine variant the result differs at most by that and by the sign of a zero.)
 //
-// Grid: 1-D.  CTA-task ct = (b * ny + task group) * strips + strip, ny = ceil(n_tasks / 4); CTA `blockIdx.x` works on
-// ct = blockIdx.x, blockIdx.x + gridDim.x, ...: with gridDim.x = the number of CTA-tasks that is one CTA per CTA-task (the
-// default), with a grid of a few CTAs per SM it is a PERSISTENT grid that is resident at once -- what lets the kernel
-// share the SMs with a cost-volume kernel on another stream whichever of the two is launched first
-// (RAG_HEAD_BWD_SHARED, rag_b200.pipeline).  The warps of a CTA walk their task lists independently: the depth tables
-// are built once per CTA, nothing else is shared between tasks.
-template <bool CUBE, bool RED>
+// Grid.  Default: 3-D, one CTA per CTA-task (strip, group of 4 warp tasks, image).  <PERSIST>: 1-D, CTA blockIdx.x walks the
+// flattened CTA-tasks ct = (b * ny + group) * strips + strip, ny = ceil(n_tasks / 4), with stride gridDim.x -- a grid of a
+// few CTAs per SM that is resident at once, which is what lets the kernel share the SMs with a cost-volume kernel on
+// another stream whichever of the two is launched first (RAG_HEAD_BWD_SHARED, rag_b200.pipeline).  The warps of a CTA
+// walk their task lists independently: the depth tables are built once per CTA, nothing else is shared between tasks.
+template <bool CUBE, bool RED, bool PERSIST = false>
 __global__ void __launch_bounds__(128, 4)
 head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gdisp, const float* __restrict__ disp,
                     const float* __restrict__ stats, float* __restrict__ gcost, float* __restrict__ scratch,
@@ -80,10 +79,13 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* win = win_all + warp * kBwWin;
     const int ny = (n_tasks + 3) >> 2;
-    for (int ct = blockIdx.x; ct < n_ct; ct += gridDim.x) {
-    const int cq = ct / strips, strip = ct - cq * strips;
-    const int b = cq / ny;
-    const int task = (cq - b * ny) * 4 + warp;
+    int ct = blockIdx.x;
+    do {                                                  // !PERSIST: exactly one pass, the loop folds away
+    // !PERSIST: 3-D grid (strip, task group, image); PERSIST: 1-D grid over the flattened CTA-tasks
+    const int cq = PERSIST ? ct / strips : 0;
+    const int strip = PERSIST ? ct - cq * strips : (int)blockIdx.x;
+    const int b = PERSIST ? cq / ny : (int)blockIdx.z;
+    const int task = (PERSIST ? cq - b * ny : (int)blockIdx.y) * 4 + warp;
     if (task >= n_tasks) continue;
     __syncwarp();                                         // the previous task's window reads are done
     const int rbi = task / nJ, jc = task - rbi * nJ;
@@ -345,7 +347,7 @@ head_bwd_x3w_kernel(const float* __restrict__ cost, const float* __restrict__ gd
         for (int i = 0; i < 4; ++i) pg[i] = g1[i];
         pgS = g1S;
     }
-    }   // CTA-task loop
+    } while (PERSIST && (ct += gridDim.x) < n_ct);        // CTA-task loop
 }
 
 // gcost += scratch, with the rows that never receive a "B" part (row 0 gets block row -1's; all rows are

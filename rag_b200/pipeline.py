@@ -38,12 +38,13 @@ class OverlappedPath:
     the SMs with the FP32-bound head kernel of another (in the network the Matching Net sits between the
     two operators of a batch, so what overlaps in deployment is head(batch i) with volume(batch i+1)).
 
-    ``step`` only enqueues; results are ordered on the returned events (or ``join()``).  The volume kernel
-    is launched first with the SM-sharing variant (a persistent grid that is resident at once), which is
-    what lets the head's CTAs be dispatched next to it instead of behind it.
+    ``step`` only enqueues; results are ordered on the returned events (or ``join()``).  ``schedule`` picks the kernel
+    variants (SCHEDULES): "coresident" (default) runs every kernel as a persistent grid sized so that a volume CTA and three
+    head CTAs fit an SM together, so the two streams overlap whichever kernel is launched first; "launch-order" is the
+    earlier form (persistent volume kernel launched first, the head's plain grid dispatched beside it).
     """
 
-    schedule = "launch-order"
+    schedule = "coresident"
 
     def __init__(self, maxdisp: int = 192, device: torch.device | str = "cuda", schedule: str | tuple | None = None):
         self.device = torch.device(device)

@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--full", action="store_true", help="also sweep mixed variant sets")
+    ap.add_argument("--infer-only", action="store_true", help="sweep the inference step only (volume forward x head forward variants)")
+    ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--cvb", default="3,4,5", help="cost-volume backward variants to A/B (beside the default and RAG_CV_BWD_SHARED)")
     a = ap.parse_args()
     hf, wf, df, md = CFGS[a.cfg]
@@ -104,16 +106,18 @@ def main():
         return round(e0.elapsed_time(e1) / K, 4)
 
     sets = dict(P_.SCHEDULES)
-    if a.full:
+    if a.infer_only:
+        sets = {f"cf{vcf} hf{vhf}": (vcf, vhf, None, None) for vcf in (2, P_.CV_FWD_SHARED, P_.CV_FWD_SLIM) for vhf in (None, P_.HEAD_FWD_SHARED)}
+    elif a.full:
         for vcf, vhf, vcb, vhb in itertools.product((P_.CV_FWD_SLIM,), (None, P_.HEAD_FWD_SHARED),
                                                     (None,) + cvbs, (None, P_.HEAD_BWD_SHARED)):
             sets[f"cf{vcf} hf{vhf} cb{vcb} hb{vhb}"] = (vcf, vhf, vcb, vhb)
     res_t, res_i = {}, {}
     for name, vs in sets.items():
         tp = P_.OverlappedTrainPath(md, dev, schedule=vs)
-        res_t[name] = [timed(tp, lambda: tp.step(x, y, cl, gc, gd), a.steps) for _ in range(2)]
+        res_t[name] = [] if a.infer_only else [timed(tp, lambda: tp.step(x, y, cl, gc, gd), a.steps) for _ in range(a.reps)]
         ip = P_.OverlappedPath(md, dev, schedule=vs)
-        res_i[name] = [timed(ip, lambda: ip.step(x, y, cl), a.steps) for _ in range(2)]
+        res_i[name] = [timed(ip, lambda: ip.step(x, y, cl), a.steps) for _ in range(a.reps)]
         print(json.dumps({"schedule": name, "train_ms": res_t[name], "infer_ms": res_i[name]}), flush=True)
     out["train_step_ms"] = res_t
     out["infer_step_ms"] = res_i
