@@ -713,7 +713,8 @@ def run_gpu(args):
         roofline = {
             "bound": "hbm", "kernel": kname + " (cost-volume forward)",
             "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-            "traffic": ncu_traffic("cv_fwd_lean_kernel" if lean else "cv_fwd_kernel") if workload in ("infer", "router") else None,
+            "traffic": (ncu_traffic("cv_fwd_lean_kernel" if lean else "cv_fwd_kernel") if workload in ("infer", "router")
+                        else ncu_traffic("cv_fwd_lean_kernel@B4_288x576") if (workload == "train" and lean) else None),
             "peak_source": peak_src, "alg_bytes_per_launch": cvb * sub, "avg_launch_ms": round(cv_ms, 5),
             "timed_in": "serial pass of %d steps in this run (kernels back to back on one stream, CUDA events around each)" % K,
             "note": "a write-only stream: the measured peak is a COPY (read+write) figure, a pure fill of the same bytes runs at ~7.45 TB/s",
