@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RAG_B200_ABI_VERSION 12
+#define RAG_B200_ABI_VERSION 13
 
 #if defined(__GNUC__)
 #define RAG_API __attribute__((visibility("default")))
