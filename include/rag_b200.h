@@ -123,7 +123,7 @@ RAG_API int rag_upsample_trilinear(const float* cost_lr, float* out, int B, int 
  *   rag_cost_volume_bwd_v  0 = 128-bit vector kernel (default when Wf % 4 == 0), 1 = scalar (any width),
  *                          2 = the vector kernel as a persistent grid of 4 CTAs per SM (SM sharing, launch order);
  *                          3 = cp.async ring in shared memory, one 256-thread CTA per SM at 64 registers (co-resident SM
- *                          sharing); 4, 5 = A/B geometries of 3 (3 stages; 128 threads x 6 stages)
+ *                          sharing)
  *   rag_disp_head_fwd_v    0 = any (Dl, maxdisp); 1 = first x3 kernel (any width); 2 = cube-root tiled kernel (default when
  *                          maxdisp == 3*Dl and Wl % 4 == 0); 3 = as 2 with the lambda correction at every step + TwoSum totals;
  *                          4 = 2 as a persistent grid of 3 CTAs per SM (co-resident SM sharing)

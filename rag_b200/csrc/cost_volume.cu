@@ -528,19 +528,19 @@ int cost_volume_fwd(const float* x, const float* y, float* cost, int B, int C, i
 
 // variant: 0 = default (128-bit vector kernel when Wf % 4 == 0 and aligned, else scalar); 1 = scalar;
 // 2 = RAG_CV_BWD_SHARED: the vector kernel as a persistent grid of 4 x 128-thread CTAs per SM (SM sharing);
-// 3 = RAG_CV_BWD_SLIM: cp.async ring in shared memory, one 256-thread CTA per SM with 4 stages (4: 3 stages, 5: 128 threads x
-// 6 stages -- A/B geometries of the same kernel)
+// 3 = RAG_CV_BWD_SLIM: cp.async ring in shared memory, one 256-thread CTA per SM with 4 stages (3 stages: 0.078 instead of
+// 0.076 ms at B=4 288x576; 128 threads x 6 stages: 0.119 ms -- profiles/r2_coresident_sweep_288x576_b4.jsonl)
 int cost_volume_bwd(const float* g, float* gx, float* gy, int B, int C, int Df, int Hf, int Wf,
                     int variant, cudaStream_t st) {
     if (int e = check_cv_args(g, gx, gy, B, C, Df, Hf, Wf)) return e;
-    if (variant < 0 || variant > 5) return fail(RAG_E_VARIANT, "cost_volume_bwd: unknown variant %d", variant);
+    if (variant < 0 || variant > 3) return fail(RAG_E_VARIANT, "cost_volume_bwd: unknown variant %d", variant);
     const bool a16 = aligned(g, 16) && aligned(gx, 16) && aligned(gy, 16);
     if (variant >= 2) {
         if (!(Wf % 4 == 0 && a16)) return fail(RAG_E_VARIANT, "cost_volume_bwd: variant %d needs Wf %% 4 == 0 and 16-byte aligned pointers", variant);
         constexpr int NT = 128;
         const int PV = Hf * (Wf / 4), n_blk = (PV + NT - 1) / NT;
         const long long n_items = (long long)B * C * n_blk;
-        if (variant >= 3) {   // RAG_CV_BWD_SLIM and its A/B geometries: cp.async ring in shared memory, one CTA per SM
+        if (variant == 3) {   // RAG_CV_BWD_SLIM: cp.async ring in shared memory, one CTA per SM
             auto launch = [&](auto kern, int nt, int stages) -> int {
                 const size_t smem = (size_t)stages * 4 * (2 * nt + 2) * sizeof(float4);
                 cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -552,10 +552,7 @@ int cost_volume_bwd(const float* g, float* gx, float* gy, int B, int C, int Df, 
                 kern<<<grid, nt, smem, st>>>(g, gx, gy, B * C, C, Df, Hf, Wf, nb);
                 return RAG_OK;
             };
-            int rc = variant == 3 ? launch(cv_bwd_staged_kernel<256, 4>, 256, 4)
-                   : variant == 4 ? launch(cv_bwd_staged_kernel<256, 3>, 256, 3)
-                                  : launch(cv_bwd_staged_kernel<128, 6>, 128, 6);
-            if (rc) return rc;
+            if (int rc = launch(cv_bwd_staged_kernel<256, 4>, 256, 4)) return rc;
             return check_launch("cost_volume_bwd(staged)");
         }
         const int grid = (int)std::min<long long>(n_items, (long long)num_sms() * 4);

@@ -51,7 +51,7 @@ def test_cost_volume_guards(L, shape):
         assert not (out == CANARY).any(), f"cv_fwd variant {v} left output elements unwritten"
     gc = randn((b, 2 * c, df, hf, wf), g).cuda()
     m = b * c * hf * wf
-    for v in (0, 1) + ((2, 3, 4, 5) if wf % 4 == 0 else ()):
+    for v in (0, 1) + ((2, 3) if wf % 4 == 0 else ()):
         bx, gx = window(m)
         by, gy = window(m)
         assert L.rag_cost_volume_bwd_v(gc.data_ptr(), gx.data_ptr(), gy.data_ptr(), b, c, df, hf, wf, v, st()) == 0

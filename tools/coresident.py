@@ -31,7 +31,7 @@ def main():
     ap.add_argument("--full", action="store_true", help="also sweep mixed variant sets")
     ap.add_argument("--infer-only", action="store_true", help="sweep the inference step only (volume forward x head forward variants)")
     ap.add_argument("--reps", type=int, default=2)
-    ap.add_argument("--cvb", default="3,4,5", help="cost-volume backward variants to A/B (beside the default and RAG_CV_BWD_SHARED)")
+    ap.add_argument("--cvb", default="3", help="cost-volume backward variants to A/B (beside the default and RAG_CV_BWD_SHARED)")
     a = ap.parse_args()
     hf, wf, df, md = CFGS[a.cfg]
     b, c = a.batch, 12
