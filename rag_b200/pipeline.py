@@ -113,9 +113,11 @@ class OverlappedPath:
         cur.wait_stream(side)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
+        self._cv_step_done = None                   # no dependency of the captured step on an event from outside the capture
         with torch.cuda.graph(graph, stream=side):
             outs = self.step(*args, **kw)
             self.join()
+        self._cv_step_done = None
         return graph, outs
 
 
@@ -126,15 +128,28 @@ class OverlappedTrainPath(OverlappedPath):
     its backward between their backwards); what the schedule shows is that the two kinds of kernel do not compete for
     the same resource, so a training step costs ~max(volume stream, head stream) instead of their sum."""
 
+    # The two chains take about the same time, so two FREE-running streams settle into whatever phase the start-up left
+    # them in, and the step time depends on it (0.196 - 0.224 ms at B=4 288x576 from box to box and run to run:
+    # head_fwd beside cv_fwd and head_bwd beside cv_bwd share an SM better than the crossed pairs, tools/corun_rates.py).
+    # phase_lock: the head stream starts step k when the volume stream has finished step k-1 -- one event per step, no
+    # join -- which pins the aligned pairing: 0.207 - 0.214 ms on every box (tools/couple_probe.py).
+    phase_lock = True
+
     def step(self, x, y, cost_lr, gcost, gdisp):
         cur = self._fork()
         c = x.shape[1]
         vcf, vhf, vcb, vhb = self._variants(x, cost_lr)
+        prev = getattr(self, "_cv_step_done", None)
         with torch.no_grad():
             with torch.cuda.stream(self.s_cv):
                 cost = F_.cost_volume_forward(x, y, int(self.maxdisp / 3), variant=vcf)
                 gx, gy = F_.cost_volume_backward(gcost, c, variant=vcb)
+                if self.phase_lock:
+                    self._cv_step_done = torch.cuda.Event()
+                    self._cv_step_done.record(self.s_cv)
             with torch.cuda.stream(self.s_head):
+                if self.phase_lock and prev is not None:
+                    self.s_head.wait_event(prev)
                 disp, stats = F_.disp_head_forward(cost_lr, self.maxdisp, want_stats=True, variant=vhf)
                 gcl = F_.disp_head_backward(cost_lr, gdisp, disp, stats, self.maxdisp, variant=vhb)
         for t in (x, y, gcost):
