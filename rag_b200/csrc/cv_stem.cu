@@ -270,21 +270,32 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
     const int NP = Wf >> 1;
 
     // phase-1 prefetch: every thread fetches ITS OWN column pair of the three input rows of channel c into its
-    // private ring slots, so no block barrier is needed between producer and consumer (same thread)
-    auto fetch_c = [&](const float* src, int c, int stage) {
+    // private ring slots, so no block barrier is needed between producer and consumer (same thread).  The three source
+    // pointers just walk from channel to channel (no per-copy 64-bit index arithmetic), and a row outside the image is a
+    // copy of zero source bytes (zero fill) instead of a predicated copy: every cp.async of the loop is unconditional.
+    const float* f_mid = x;                        // row h, row h-1 (or h again), row h+1 (or h again) of the next channel to fetch
+    const float* f_up = x;
+    const float* f_dn = x;
+    const int zf_up = up ? 0 : 8, zf_dn = dn ? 0 : 8;
+    auto fetch_begin = [&](const float* src) {
+        f_mid = src;
+        f_up = up ? src - Wf : src;
+        f_dn = dn ? src + Wf : src;
+    };
+    auto fetch_next = [&](int stage) {             // the next channel's three rows -> ring stage `stage`
         float2* slot = ring + (size_t)stage * 3 * NT + tid;
-        const float* p = src + (size_t)c * img;
-        __pipeline_memcpy_async(slot + NT, p, 8);
-        if (up) __pipeline_memcpy_async(slot, p - Wf, 8);
-        if (dn) __pipeline_memcpy_async(slot + 2 * NT, p + Wf, 8);
+        __pipeline_memcpy_async(slot + NT, f_mid, 8);
+        __pipeline_memcpy_async(slot, f_up, 8, zf_up);
+        __pipeline_memcpy_async(slot + 2 * NT, f_dn, 8, zf_dn);
+        f_mid += img; f_up += img; f_dn += img;
     };
     {   // first item of this thread: start its loads before the (latency-bound) weight regrouping below
         const int item = tid;
         if (item < 2 * NP) {
             const int side = item >= NP ? 1 : 0;
-            const float* src = (side ? y : x) + (size_t)b * C * img + (size_t)h * Wf + ((item - side * NP) << 1);
+            fetch_begin((side ? y : x) + (size_t)b * C * img + (size_t)h * Wf + ((item - side * NP) << 1));
 #pragma unroll
-            for (int c = 0; c < kStemStages - 1; ++c) { fetch_c(src, c, c); __pipeline_commit(); }
+            for (int c = 0; c < kStemStages - 1; ++c) { fetch_next(c); __pipeline_commit(); }
         }
     }
 
@@ -312,10 +323,10 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
     for (int item = tid; item < 2 * NP; item += NT) {
         const int side = item >= NP ? 1 : 0;
         const int col = (item - side * NP) << 1;
-        const float* src = (side ? y : x) + (size_t)b * C * img + (size_t)h * Wf + col;
         if (item != tid) {                         // later passes (NT < Wf): restart the pipeline for this item
+            fetch_begin((side ? y : x) + (size_t)b * C * img + (size_t)h * Wf + col);
 #pragma unroll
-            for (int c = 0; c < kStemStages - 1; ++c) { fetch_c(src, c, c); __pipeline_commit(); }
+            for (int c = 0; c < kStemStages - 1; ++c) { fetch_next(c); __pipeline_commit(); }
         }
         const float4* wp = reinterpret_cast<const float4*>(wsm + side * C * 36);
         float2 acc[9];
@@ -323,14 +334,11 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
         for (int i = 0; i < 9; ++i) acc[i] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            if (c + kStemStages - 1 < C) fetch_c(src, c + kStemStages - 1, (c + kStemStages - 1) % kStemStages);
+            if (c + kStemStages - 1 < C) fetch_next((c + kStemStages - 1) % kStemStages);
             __pipeline_commit();
             __pipeline_wait_prior(kStemStages - 1);        // channel c has landed
             const float2* slot = ring + (size_t)(c % kStemStages) * 3 * NT + tid;
-            const float2 z2 = make_float2(0.f, 0.f);
-            const float2 v1 = slot[NT];
-            const float2 v0 = up ? slot[0] : z2;
-            const float2 v2 = dn ? slot[2 * NT] : z2;
+            const float2 v0 = slot[0], v1 = slot[NT], v2 = slot[2 * NT];   // rows outside the image were zero-filled
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
                 const float2 v = kh == 0 ? v0 : kh == 1 ? v1 : v2;
