@@ -13,6 +13,6 @@ python bench.py --impl reference --steps 20 --warmup 3 > $O/r2_bench_reference.j
 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r2_bench_infer_launches.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $O/ncu_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"cv_fwd_lean|head_fwd_x3r|head_bwd_x3w|cv_bwd_v4" -s 40 -c 8 -o $O/r2_bench_kernels \
+ncu --set full --clock-control none --import-source on -k regex:"cv_fwd_lean|head_fwd_x3r|head_bwd_x3w|cv_bwd_v4|cv_bwd_staged" -s 40 -c 8 -o $O/r2_bench_kernels \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $O/ncu_full.log 2>&1
 ls -la $O/*.ncu-rep
