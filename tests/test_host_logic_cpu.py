@@ -202,3 +202,34 @@ def test_fp64_torch_evaluator_matches_the_numpy_evaluator():
         assert np.abs(gg - g2.numpy()).max() <= 1e-12 * max(1.0, np.abs(gg).max())
         d3, none = O.disp_head_f64_torch(cl, md)
         assert none is None and torch.equal(d3, d2)
+
+
+def test_schedule_variant_ids_match_the_header():
+    """rag_b200.pipeline's variant constants are the ones include/rag_b200.h defines, and every schedule names four of them."""
+    import re
+
+    from rag_b200 import pipeline as P_
+
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "rag_b200.h")).read()
+    macros = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define (RAG_[A-Z_]+) (\d+)\b", hdr)}
+    for name in ("CV_FWD_SHARED", "CV_BWD_SHARED", "CV_FWD_SLIM", "CV_BWD_SLIM", "HEAD_FWD_SHARED", "HEAD_BWD_SHARED"):
+        assert getattr(P_, name) == macros["RAG_" + name], name
+    assert set(P_.SCHEDULES) >= {"coresident", "launch-order"}
+    for vs in P_.SCHEDULES.values():
+        assert len(vs) == 4 and all(v is None or isinstance(v, int) for v in vs)
+    assert P_.SCHEDULES["coresident"] == (P_.CV_FWD_SLIM, P_.HEAD_FWD_SHARED, P_.CV_BWD_SLIM, P_.HEAD_BWD_SHARED)
+
+
+def test_schedule_falls_back_to_default_kernels_outside_their_preconditions():
+    """Widths that are not a multiple of four or a ratio other than 3 take the default entry points (variant None)."""
+    from rag_b200.pipeline import OverlappedPath
+
+    class _Shape:                                   # only .shape is read
+        def __init__(self, *s):
+            self.shape = s
+
+    p = OverlappedPath.__new__(OverlappedPath)     # no CUDA streams on the CPU box
+    p.maxdisp, p.variants = 192, (5, 4, 3, 3)
+    assert p._variants(_Shape(1, 12, 8, 48), _Shape(1, 1, 64, 8, 48)) == (5, 4, 3, 3)
+    assert p._variants(_Shape(1, 12, 8, 46), _Shape(1, 1, 64, 8, 46)) == (None, None, None, 3)
+    assert p._variants(_Shape(1, 12, 8, 48), _Shape(1, 1, 48, 8, 48)) == (5, None, 3, None)
