@@ -6,6 +6,8 @@
 // gradient re-uses the window for all C channels (1296 FMAs per window, output streamed with 128-bit stores: the C-times
 // larger tensor is written once), the weight gradient keeps 27 running sums per thread for one channel over many tiles and
 // reduces once per CTA (fixed order, fp64 final pass: deterministic).  cuDNN has no good kernel for a 1-channel side.
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 
 namespace rag {
@@ -25,6 +27,19 @@ __device__ __forceinline__ void lb_stage(float* sm, const float* __restrict__ g,
         if (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W)   // W % 4 == 0: a quad is inside or outside as a whole
             val = __ldg(reinterpret_cast<const float4*>(g + (size_t)b * vol + ((size_t)gd * H + gh) * W + gw));
         *reinterpret_cast<float4*>(sm + row * kLbSW + 4 * v) = val;
+    }
+}
+
+// the same tile through cp.async (no register staging; quads outside the volume are zero-filled copies of no source bytes)
+__device__ __forceinline__ void lb_stage_async(float* sm, const float* __restrict__ g, int b, int d0, int h0, int w0, int D, int H, int W) {
+    const size_t vol = (size_t)D * H * W;
+    for (int i = threadIdx.x; i < kLbRows * (kLbSW / 4); i += 256) {
+        const int row = i / (kLbSW / 4), v = i - row * (kLbSW / 4);
+        const int dz = row / (kLbH + 2), hy = row - dz * (kLbH + 2);
+        const int gd = d0 - 1 + dz, gh = h0 - 1 + hy, gw = w0 - 4 + 4 * v;
+        const bool in = gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W;
+        const float* src = in ? g + (size_t)b * vol + ((size_t)gd * H + gh) * W + gw : g;
+        __pipeline_memcpy_async(sm + row * kLbSW + 4 * v, src, 16, in ? 0 : 16);
     }
 }
 
@@ -98,19 +113,45 @@ conv3d_c1_bwd_weight_kernel(const float* __restrict__ g, const float* __restrict
     float acc[2][27];
 #pragma unroll
     for (int k = 0; k < 27; ++k) { acc[0][k] = 0.f; acc[1][k] = 0.f; }
-    for (int t = blockIdx.x; t < n_tiles; t += n_groups) {
-        const int wt = t % n_wt, ht = (t / n_wt) % n_ht, dt = (t / (n_wt * n_ht)) % n_dt, b = t / (n_wt * n_ht * n_dt);
-        const int d0 = dt * kLbD, h0 = ht * kLbH, w0 = wt * kLbW;
-        __syncthreads();
-        lb_stage(lbw_smem, g, b, d0, h0, w0, D, H, W);
-        __syncthreads();
+    // The tile of g and the thread's two input vectors of tile k+1 are copied (cp.async) into the second buffer while tile k
+    // is worked on: the first version staged through registers between two barriers and loaded the inputs on demand, so every
+    // tile exposed an L2 and a DRAM round trip to 216 FMAs (15 % of the FP32 peak).
+    float* tiles = lbw_smem;                                          // [2][kLbRows * kLbSW]
+    float4* xs = reinterpret_cast<float4*>(lbw_smem + 2 * kLbRows * kLbSW);   // [2 buffers][2 channels][256 threads]
+    auto tile_of = [&](int t, int& b, int& d0, int& h0, int& w0) {
+        const int wt = t % n_wt, ht = (t / n_wt) % n_ht, dt = (t / (n_wt * n_ht)) % n_dt;
+        b = t / (n_wt * n_ht * n_dt);
+        d0 = dt * kLbD; h0 = ht * kLbH; w0 = wt * kLbW;
+    };
+    auto issue = [&](int t, int buf) {
+        if (t < n_tiles) {
+            int b, d0, h0, w0;
+            tile_of(t, b, d0, h0, w0);
+            lb_stage_async(tiles + buf * kLbRows * kLbSW, g, b, d0, h0, w0, D, H, W);
+            const int d = d0 + td, h = h0 + th, w = w0 + 4 * tw;
+            const bool on = d < D && h < H && w < W;
+            const float* ip = on ? in + ((size_t)b * C + c0) * vol + ((size_t)d * H + h) * W + w : in;
+            __pipeline_memcpy_async(xs + (buf * 2 + 0) * 256 + threadIdx.x, ip, 16, on ? 0 : 16);
+            __pipeline_memcpy_async(xs + (buf * 2 + 1) * 256 + threadIdx.x, (on && two) ? ip + vol : in, 16, (on && two) ? 0 : 16);
+        }
+        __pipeline_commit();
+    };
+    issue(blockIdx.x, 0);
+    int it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += n_groups, ++it) {
+        const int buf = it & 1;
+        __syncthreads();                                              // everybody is done with the other buffer (tile k-1)
+        issue(t + n_groups, buf ^ 1);
+        __pipeline_wait_prior(1);                                     // this thread's copies of tile k have landed ...
+        __syncthreads();                                              // ... and everybody's
+        int b, d0, h0, w0;
+        tile_of(t, b, d0, h0, w0);
         const int d = d0 + td, h = h0 + th, w = w0 + 4 * tw;
         if (d < D && h < H && w < W) {
             float win[3][3][6];
-            lb_window(lbw_smem, td, th, tw, win);
-            const float* ip = in + ((size_t)b * C + c0) * vol + ((size_t)d * H + h) * W + w;
-            const float4 x0 = __ldg(reinterpret_cast<const float4*>(ip));
-            const float4 x1 = two ? __ldg(reinterpret_cast<const float4*>(ip + vol)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            lb_window(tiles + buf * kLbRows * kLbSW, td, th, tw, win);
+            const float4 x0 = xs[(buf * 2 + 0) * 256 + threadIdx.x];
+            const float4 x1 = xs[(buf * 2 + 1) * 256 + threadIdx.x];
             // gW[k] += in[p] g[p - k + 1]: for input position i (0..3) tap (kd,kh,kw) pairs with window (2-kd, 2-kh, i + 2 - kw)
 #pragma unroll
             for (int kd = 0; kd < 3; ++kd)
@@ -184,7 +225,8 @@ int conv3d_c1_bwd(const float* g, const float* in, const float* w, float* gin, f
         if (int rc = check_launch("conv3d_c1_bwd(data)")) return rc;
     }
     if (gw) {
-        conv3d_c1_bwd_weight_kernel<<<dim3(kLbGroups, (C + 1) / 2), 256, tile_bytes, st>>>(g, in, workspace, B, C, D, H, W, n_wt, n_ht, n_dt);
+        const size_t wsmem = 2 * tile_bytes + (size_t)2 * 2 * 256 * sizeof(float4);   // two tile buffers + two input-vector buffers
+        conv3d_c1_bwd_weight_kernel<<<dim3(kLbGroups, (C + 1) / 2), 256, wsmem, st>>>(g, in, workspace, B, C, D, H, W, n_wt, n_ht, n_dt);
         if (int rc = check_launch("conv3d_c1_bwd(weight)")) return rc;
         conv3d_c1_bwd_weight_final_kernel<<<C, 32, 0, st>>>(workspace, gw, kLbGroups);
         if (int rc = check_launch("conv3d_c1_bwd(weight final)")) return rc;
