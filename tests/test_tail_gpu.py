@@ -50,6 +50,9 @@ RESIZE_CASES = [
     (1, 1, (1, 4, 4), (1, 9, 7), True),            # singleton axis (scale 0 with align_corners)
     (2, 2, (6, 5, 8), (18, 15, 24), False),        # align_corners=False, x3 (the head's convention)
     (1, 1, (3, 3, 3), (3, 3, 3), True),            # identity
+    (1, 1, (3, 4, 132), (5, 7, 264), True),        # row kernels, wide rows: two input vectors per lane, loads one row ahead
+    (1, 2, (4, 4, 16), (8, 8, 32), False),         # row kernels with align_corners=False (x2)
+    (1, 1, (2, 3, 8), (3, 5, 12), True),           # row kernels, ragged: 3 output vectors, one lane in four busy
 ]
 
 
