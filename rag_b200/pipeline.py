@@ -84,9 +84,14 @@ class OverlappedPath:
     def _variants(self, x, cost_lr):
         """The schedule's kernel variants where their preconditions hold (vector widths, x3 ratio), else the defaults."""
         vcf, vhf, vcb, vhb = self.variants
-        if x.shape[-1] % 4 != 0:
+
+        def misaligned(t):                          # the vector kernels want 16-byte aligned bases (views may not be)
+            ptr = getattr(t, "data_ptr", None)
+            return ptr is not None and ptr() % 16 != 0
+
+        if x.shape[-1] % 4 != 0 or misaligned(x):
             vcf = vcb = None
-        if cost_lr.shape[-1] % 4 != 0 or self.maxdisp != 3 * cost_lr.shape[2]:
+        if cost_lr.shape[-1] % 4 != 0 or self.maxdisp != 3 * cost_lr.shape[2] or misaligned(cost_lr):
             vhf = None
         if self.maxdisp != 3 * cost_lr.shape[2]:
             vhb = None
