@@ -118,35 +118,66 @@ conv3d_c1_bwd_weight_kernel(const float* __restrict__ g, const float* __restrict
     // tile exposed an L2 and a DRAM round trip to 216 FMAs (15 % of the FP32 peak).
     float* tiles = lbw_smem;                                          // [2][kLbRows * kLbSW]
     float4* xs = reinterpret_cast<float4*>(lbw_smem + 2 * kLbRows * kLbSW);   // [2 buffers][2 channels][256 threads]
-    auto tile_of = [&](int t, int& b, int& d0, int& h0, int& w0) {
-        const int wt = t % n_wt, ht = (t / n_wt) % n_ht, dt = (t / (n_wt * n_ht)) % n_dt;
-        b = t / (n_wt * n_ht * n_dt);
-        d0 = dt * kLbD; h0 = ht * kLbH; w0 = wt * kLbW;
+    // No division per tile: the tile index advances by n_groups, i.e. by fixed digits in the mixed radix (n_wt, n_ht, n_dt, B),
+    // and the (up to three) quads of the g window a thread stages keep their place inside the window from tile to tile.
+    const int gq = n_groups / n_wt, inc_w = n_groups - gq * n_wt;
+    const int gq2 = gq / n_ht, inc_h = gq - gq2 * n_ht;
+    const int inc_b = gq2 / n_dt, inc_d = gq2 - inc_b * n_dt;
+    int i_wt, i_ht, i_dt, i_b;                                        // digits of the tile being ISSUED
+    {
+        const int t0 = blockIdx.x;
+        i_wt = t0 % n_wt; i_ht = (t0 / n_wt) % n_ht; i_dt = (t0 / (n_wt * n_ht)) % n_dt; i_b = t0 / (n_wt * n_ht * n_dt);
+    }
+    auto advance = [&]() {
+        i_wt += inc_w; if (i_wt >= n_wt) { i_wt -= n_wt; ++i_ht; }
+        i_ht += inc_h; if (i_ht >= n_ht) { i_ht -= n_ht; ++i_dt; }
+        i_dt += inc_d; if (i_dt >= n_dt) { i_dt -= n_dt; ++i_b; }
+        i_b += inc_b;
     };
-    auto issue = [&](int t, int buf) {
-        if (t < n_tiles) {
-            int b, d0, h0, w0;
-            tile_of(t, b, d0, h0, w0);
-            lb_stage_async(tiles + buf * kLbRows * kLbSW, g, b, d0, h0, w0, D, H, W);
+    int s_dz[3], s_hy[3], s_v[3];                                     // the thread's quads of the window: (depth, row, vector)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int i = threadIdx.x + 256 * k;
+        const int row = i / (kLbSW / 4);
+        s_v[k] = i - row * (kLbSW / 4);
+        s_dz[k] = row / (kLbH + 2);
+        s_hy[k] = row - s_dz[k] * (kLbH + 2);
+    }
+    auto issue = [&](bool live, int buf) {                            // tile (i_b, i_dt, i_ht, i_wt) -> buffer buf
+        if (live) {
+            const int d0 = i_dt * kLbD, h0 = i_ht * kLbH, w0 = i_wt * kLbW;
+            float* sm = tiles + buf * kLbRows * kLbSW;
+            const float* gb = g + (size_t)i_b * vol;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (threadIdx.x + 256 * k < kLbRows * (kLbSW / 4)) {
+                    const int gd = d0 - 1 + s_dz[k], gh = h0 - 1 + s_hy[k], gw = w0 - 4 + 4 * s_v[k];
+                    const bool in_vol = gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W;   // W % 4 == 0
+                    const float* src = in_vol ? gb + ((size_t)gd * H + gh) * W + gw : g;
+                    __pipeline_memcpy_async(sm + (s_dz[k] * (kLbH + 2) + s_hy[k]) * kLbSW + 4 * s_v[k], src, 16, in_vol ? 0 : 16);
+                }
+            }
             const int d = d0 + td, h = h0 + th, w = w0 + 4 * tw;
             const bool on = d < D && h < H && w < W;
-            const float* ip = on ? in + ((size_t)b * C + c0) * vol + ((size_t)d * H + h) * W + w : in;
+            const float* ip = on ? in + ((size_t)i_b * C + c0) * vol + ((size_t)d * H + h) * W + w : in;
             __pipeline_memcpy_async(xs + (buf * 2 + 0) * 256 + threadIdx.x, ip, 16, on ? 0 : 16);
             __pipeline_memcpy_async(xs + (buf * 2 + 1) * 256 + threadIdx.x, (on && two) ? ip + vol : in, 16, (on && two) ? 0 : 16);
         }
         __pipeline_commit();
     };
-    issue(blockIdx.x, 0);
+    int c_d0 = i_dt * kLbD, c_h0 = i_ht * kLbH, c_w0 = i_wt * kLbW;  // origin of the tile being COMPUTED
+    issue(blockIdx.x < n_tiles, 0);
     int it = 0;
     for (int t = blockIdx.x; t < n_tiles; t += n_groups, ++it) {
         const int buf = it & 1;
         __syncthreads();                                              // everybody is done with the other buffer (tile k-1)
-        issue(t + n_groups, buf ^ 1);
+        advance();
+        issue(t + n_groups < n_tiles, buf ^ 1);
+        const int n_d0 = i_dt * kLbD, n_h0 = i_ht * kLbH, n_w0 = i_wt * kLbW;
         __pipeline_wait_prior(1);                                     // this thread's copies of tile k have landed ...
         __syncthreads();                                              // ... and everybody's
-        int b, d0, h0, w0;
-        tile_of(t, b, d0, h0, w0);
-        const int d = d0 + td, h = h0 + th, w = w0 + 4 * tw;
+        const int d = c_d0 + td, h = c_h0 + th, w = c_w0 + 4 * tw;
+        c_d0 = n_d0; c_h0 = n_h0; c_w0 = n_w0;
         if (d < D && h < H && w < W) {
             float win[3][3][6];
             lb_window(tiles + buf * kLbRows * kLbSW, td, th, tw, win);
@@ -188,13 +219,17 @@ conv3d_c1_bwd_weight_kernel(const float* __restrict__ g, const float* __restrict
     }
 }
 
-// gw[c][k] = sum over groups of part[c][grp][k], fixed order, fp64.  grid C, 32 threads (lanes = taps)
-__global__ void conv3d_c1_bwd_weight_final_kernel(const float* __restrict__ part, float* __restrict__ gw, int n_groups) {
-    const int c = blockIdx.x, k = threadIdx.x;
-    if (k >= 27) return;
+// gw[c][k] = sum over groups of part[c][grp][k], fixed order, fp64.  grid C; 27 warps (one per tap): the lanes take every
+// 32nd group, then a shuffle tree in a fixed order (the first version walked the 296 partials of a tap with ONE thread:
+// 23 us of dependent loads).
+__global__ void __launch_bounds__(27 * 32)
+conv3d_c1_bwd_weight_final_kernel(const float* __restrict__ part, float* __restrict__ gw, int n_groups) {
+    const int c = blockIdx.x, k = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double a = 0.0;
-    for (int i = 0; i < n_groups; ++i) a += (double)part[((size_t)c * n_groups + i) * 27 + k];
-    gw[c * 27 + k] = (float)a;
+    for (int i = lane; i < n_groups; i += 32) a += (double)part[((size_t)c * n_groups + i) * 27 + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+    if (lane == 0) gw[c * 27 + k] = (float)a;
 }
 
 constexpr int kLbGroups = 296;
@@ -228,7 +263,7 @@ int conv3d_c1_bwd(const float* g, const float* in, const float* w, float* gin, f
         const size_t wsmem = 2 * tile_bytes + (size_t)2 * 2 * 256 * sizeof(float4);   // two tile buffers + two input-vector buffers
         conv3d_c1_bwd_weight_kernel<<<dim3(kLbGroups, (C + 1) / 2), 256, wsmem, st>>>(g, in, workspace, B, C, D, H, W, n_wt, n_ht, n_dt);
         if (int rc = check_launch("conv3d_c1_bwd(weight)")) return rc;
-        conv3d_c1_bwd_weight_final_kernel<<<C, 32, 0, st>>>(workspace, gw, kLbGroups);
+        conv3d_c1_bwd_weight_final_kernel<<<C, 27 * 32, 0, st>>>(workspace, gw, kLbGroups);
         if (int rc = check_launch("conv3d_c1_bwd(weight final)")) return rc;
     }
     return RAG_OK;
