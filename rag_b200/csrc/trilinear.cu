@@ -224,11 +224,22 @@ trilinear_fwd_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
         float4 a[NVI], b[NVI], c[NVI], e[NVI];
         float t0, t1, e0, e1;
     };
-    auto fetch = [&](long long row, RowCtx& r) {
-        const int h = (int)(row % Ho);
-        const long long r2 = row / Ho;
-        const int d = (int)(r2 % Do);
-        const size_t bc = (size_t)(r2 / Do);
+    // the row index advances by `stride` rows, i.e. by fixed digits in the mixed radix (Ho, Do, BC): no division per row
+    const int sq = (int)(stride / Ho), inc_h = (int)(stride - (long long)sq * Ho);
+    const int inc_bc = sq / Do, inc_d = sq - inc_bc * Do;
+    int f_h, f_d, f_bc;                            // digits of the next row to FETCH
+    {
+        const long long r0 = (long long)blockIdx.x * kTriWarps + warp;
+        f_h = (int)(r0 % Ho);
+        f_d = (int)((r0 / Ho) % Do);
+        f_bc = (int)(r0 / ((long long)Ho * Do));
+    }
+    auto fetch = [&](RowCtx& r) {                  // fetches row (f_bc, f_d, f_h) and advances the digits
+        const int h = f_h, d = f_d;
+        const size_t bc = (size_t)f_bc;
+        f_h += inc_h; if (f_h >= Ho) { f_h -= Ho; ++f_d; }
+        f_d += inc_d; if (f_d >= Do) { f_d -= Do; ++f_bc; }
+        f_bc += inc_bc;
         int d0, d1, h0, h1;
         tri_src<AC>(sd, d, Di, d0, d1, r.t0, r.t1);
         tri_src<AC>(sh, h, Hi, h0, h1, r.e0, r.e1);
@@ -245,12 +256,12 @@ trilinear_fwd_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
     };
     long long row = (long long)blockIdx.x * kTriWarps + warp;
     RowCtx cur, nxt;
-    if (PF && row < n_rows) fetch(row, cur);
+    if (PF && row < n_rows) fetch(cur);
     for (; row < n_rows; row += stride) {
         if (PF) {
-            if (row + stride < n_rows) fetch(row + stride, nxt);
+            if (row + stride < n_rows) fetch(nxt);
         } else {
-            fetch(row, cur);
+            fetch(cur);
         }
         __syncwarp();                              // the previous row's reads of rb are done
 #pragma unroll
@@ -323,21 +334,28 @@ trilinear_bwd_rows_kernel(const float* __restrict__ gout, float* __restrict__ gi
     const int Wov = Wo >> 2;
     const size_t out_plane = (size_t)Ho * Wo, out_vol = (size_t)Do * out_plane;
     const long long n_rows = (long long)BC * Di * Hi;
-    for (long long row = (long long)blockIdx.x * kTriWarps + warp; row < n_rows; row += (long long)gridDim.x * kTriWarps) {
-        const int ih = (int)(row % Hi);
-        const long long r2 = row / Hi;
-        const int id = (int)(r2 % Di);
-        const size_t bc = (size_t)(r2 / Di);
+    // the row index advances by fixed digits in the mixed radix (Hi, Di, BC): no division per row
+    const long long stride = (long long)gridDim.x * kTriWarps;
+    const int sq = (int)(stride / Hi), inc_h = (int)(stride - (long long)sq * Hi);
+    const int inc_bc = sq / Di, inc_d = sq - inc_bc * Di;
+    long long row = (long long)blockIdx.x * kTriWarps + warp;
+    int ih = (int)(row % Hi), id = (int)((row / Hi) % Di), ibc = (int)(row / ((long long)Hi * Di));
+    for (; row < n_rows; row += stride) {
+        const size_t bc = (size_t)ibc;
         const int dl = d_first[max(id - 1, 0)], dh = d_first[id + 1];      // destinations with i0 in {id-1, id}
         const int hl = h_first[max(ih - 1, 0)], hh = h_first[ih + 1];
         const float* gp = gout + bc * out_vol;
+        const int c_id = id, c_ih = ih;
+        ih += inc_h; if (ih >= Hi) { ih -= Hi; ++id; }
+        id += inc_d; if (id >= Di) { id -= Di; ++ibc; }
+        ibc += inc_bc;
         float4 acc[NPER];
 #pragma unroll
         for (int pp = 0; pp < NPER; ++pp) acc[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int d = dl; d < dh; ++d) {
-            const float wd = wgt(id, d_i0[d], d_l1[d], Di);
+            const float wd = wgt(c_id, d_i0[d], d_l1[d], Di);
             for (int h = hl; h < hh; ++h) {
-                const float c = wd * wgt(ih, h_i0[h], h_l1[h], Hi);
+                const float c = wd * wgt(c_ih, h_i0[h], h_l1[h], Hi);
                 const float4* g4 = reinterpret_cast<const float4*>(gp + (size_t)d * out_plane + (size_t)h * Wo);
 #pragma unroll
                 for (int pp = 0; pp < NPER; ++pp) {
