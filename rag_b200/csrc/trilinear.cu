@@ -203,17 +203,17 @@ trilinear_fwd_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* rb = tri_rows + warp * (Wi + 4);
     const int Wiv = Wi >> 2, Wov = Wo >> 2;
-    // the lane's output columns: source index and weight, once
-    int ci[NPER][4];
-    float cl[NPER][4];
+    // the lane's output columns: where they read the blended row and both weights, once
+    const float* cp[NPER][4];
+    float cl0[NPER][4], cl[NPER][4];
 #pragma unroll
     for (int p = 0; p < NPER; ++p)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int w = min(4 * (lane + 32 * p) + k, Wo - 1);
-            int i1;
-            float l0;
-            tri_src<AC>(sw, w, Wi, ci[p][k], i1, l0, cl[p][k]);
+            int i0, i1;
+            tri_src<AC>(sw, w, Wi, i0, i1, cl0[p][k], cl[p][k]);
+            cp[p][k] = rb + i0;
         }
     const size_t in_plane = (size_t)Hi * Wi, in_vol = (size_t)Di * in_plane;
     const long long n_rows = (long long)BC * Do * Ho;
@@ -287,10 +287,7 @@ trilinear_fwd_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
             if (q < Wov) {
                 float v[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float l1 = cl[pp][k];
-                    v[k] = (1.f - l1) * rb[ci[pp][k]] + l1 * rb[ci[pp][k] + 1];
-                }
+                for (int k = 0; k < 4; ++k) v[k] = cl0[pp][k] * cp[pp][k][0] + cl[pp][k] * cp[pp][k][1];
                 st_stream(o4 + q, make_float4(v[0], v[1], v[2], v[3]));
             }
         }
