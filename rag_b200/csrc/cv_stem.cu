@@ -261,8 +261,12 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
     float* RF = LF + 3 * Wp;
     float* band = RF + 12 * Wp;
     float* lastcol = band + 4 * Df;
-    // per-thread cp.async ring for phase 1: [kStemStages][3 rows][NT] float2, 8-byte aligned
+    // per-thread cp.async ring for phase 1: [NT][kStemStages][3 rows] float2, 8-byte aligned.  Thread-major, so that every slot
+    // of a thread is a compile-time offset from ONE pointer (stage-major cost an address multiply-add per copy and per load:
+    // 137 IMADs around the 324 packed FMAs of a thread-item); a stride of 9 float2 per thread keeps the 64-bit accesses of a
+    // half-warp on distinct banks (18 t mod 32 runs through the 16 even banks).
     float2* ring = reinterpret_cast<float2*>(lastcol + ((Df + 3) & ~3));
+    float2* const my_ring = ring + (size_t)threadIdx.x * (kStemStages * 3);
     const int h = blockIdx.x, o = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, NT = blockDim.x;
     const size_t img = (size_t)Hf * Wf;
@@ -283,10 +287,10 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
         f_dn = dn ? src + Wf : src;
     };
     auto fetch_next = [&](int stage) {             // the next channel's three rows -> ring stage `stage`
-        float2* slot = ring + (size_t)stage * 3 * NT + tid;
-        __pipeline_memcpy_async(slot + NT, f_mid, 8);
+        float2* slot = my_ring + stage * 3;
+        __pipeline_memcpy_async(slot + 1, f_mid, 8);
         __pipeline_memcpy_async(slot, f_up, 8, zf_up);
-        __pipeline_memcpy_async(slot + 2 * NT, f_dn, 8, zf_dn);
+        __pipeline_memcpy_async(slot + 2, f_dn, 8, zf_dn);
         f_mid += img; f_up += img; f_dn += img;
     };
     {   // first item of this thread: start its loads before the (latency-bound) weight regrouping below
@@ -337,8 +341,8 @@ cv_stem_fwd2_kernel(const float* __restrict__ x, const float* __restrict__ y, co
             if (c + kStemStages - 1 < C) fetch_next((c + kStemStages - 1) % kStemStages);
             __pipeline_commit();
             __pipeline_wait_prior(kStemStages - 1);        // channel c has landed
-            const float2* slot = ring + (size_t)(c % kStemStages) * 3 * NT + tid;
-            const float2 v0 = slot[0], v1 = slot[NT], v2 = slot[2 * NT];   // rows outside the image were zero-filled
+            const float2* slot = my_ring + (c % kStemStages) * 3;
+            const float2 v0 = slot[0], v1 = slot[1], v2 = slot[2];        // rows outside the image were zero-filled
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
                 const float2 v = kh == 0 ? v0 : kh == 1 ? v1 : v2;
