@@ -190,6 +190,7 @@ trilinear_bwd_kernel(const float* __restrict__ gout, float* __restrict__ gin, in
 // The order of the roundings differs from ATen's (depth/height first instead of width first): 1e-7 relative.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kTriWarps = 8;
+constexpr int kTriList = 32;              // output rows per input row the backward row kernel lists at a time (5 x 5 fit)
 
 // grid-stride over output rows; smem: float [kTriWarps][Wi + 4]
 // NPER / NVI = 128-bit vectors per lane of an output row (ceil(Wo / 128)) / of an input row; PF: fetch the input rows one
@@ -309,6 +310,9 @@ trilinear_bwd_rows_kernel(const float* __restrict__ gout, float* __restrict__ gi
     int* wfirst = w_first + Wi + 1;
     float* wk = reinterpret_cast<float*>(wfirst + Wi);
     float* rows = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(wk + 5 * Wi) + 15) & ~(uintptr_t)15);
+    // per warp: the output rows that reference the current input row as a flat list (row offset in vectors, depth x height weight)
+    int* lst_off = reinterpret_cast<int*>(rows + kTriWarps * (Wo + 4)) + (threadIdx.x >> 5) * kTriList;
+    float* lst_w = reinterpret_cast<float*>(reinterpret_cast<int*>(rows + kTriWarps * (Wo + 4)) + kTriWarps * kTriList) + (threadIdx.x >> 5) * kTriList;
     tri_tables<AC>(sd, Di, Do, d_i0, d_l1, d_first);
     tri_tables<AC>(sh, Hi, Ho, h_i0, h_l1, h_first);
     tri_tables<AC>(sw, Wi, Wo, w_i0, w_l1, w_first);
@@ -349,16 +353,48 @@ trilinear_bwd_rows_kernel(const float* __restrict__ gout, float* __restrict__ gi
         float4 acc[NPER];
 #pragma unroll
         for (int pp = 0; pp < NPER; ++pp) acc[pp] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int d = dl; d < dh; ++d) {
-            const float wd = wgt(c_id, d_i0[d], d_l1[d], Di);
-            for (int h = hl; h < hh; ++h) {
-                const float c = wd * wgt(c_ih, h_i0[h], h_l1[h], Hi);
-                const float4* g4 = reinterpret_cast<const float4*>(gp + (size_t)d * out_plane + (size_t)h * Wo);
+        // The (dh - dl) x (hh - hl) referencing output rows as ONE flat list in shared memory -- a lane computes one entry
+        // (row offset, depth x height weight) --, walked two or four entries at a time with all their loads issued first: the
+        // nested loops recomputed the height weight for every depth and exposed one L2 round trip per output row.
+        const int nh = hh - hl, n_ref = (dh - dl) * nh;
+        for (int base = 0; base < n_ref; base += kTriList) {
+            const int n_here = min(kTriList, n_ref - base);
+            __syncwarp();
+            if (lane < n_here) {
+                const int e = base + lane, dd = e / nh, d = dl + dd, h = hl + (e - dd * nh);
+                lst_off[lane] = (int)(((size_t)d * out_plane + (size_t)h * Wo) >> 2);
+                lst_w[lane] = wgt(c_id, d_i0[d], d_l1[d], Di) * wgt(c_ih, h_i0[h], h_l1[h], Hi);
+            }
+            __syncwarp();
+            const float4* g4 = reinterpret_cast<const float4*>(gp) + lane;
+            constexpr int U = NPER >= 3 ? 2 : 4;   // entries in flight: 8 vectors per lane at most (more costs occupancy)
+            int e = 0;
+            for (; e + U <= n_here; e += U) {
+                float4 g[U][NPER];
+                float c[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    c[u] = lst_w[e + u];
+                    const float4* r4 = g4 + lst_off[e + u];
+#pragma unroll
+                    for (int pp = 0; pp < NPER; ++pp)
+                        g[u][pp] = lane + 32 * pp < Wov ? ld_stream(r4 + 32 * pp) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int pp = 0; pp < NPER; ++pp) {
+                        acc[pp].x = __fmaf_rn(c[u], g[u][pp].x, acc[pp].x); acc[pp].y = __fmaf_rn(c[u], g[u][pp].y, acc[pp].y);
+                        acc[pp].z = __fmaf_rn(c[u], g[u][pp].z, acc[pp].z); acc[pp].w = __fmaf_rn(c[u], g[u][pp].w, acc[pp].w);
+                    }
+            }
+            for (; e < n_here; ++e) {
+                const float c = lst_w[e];
+                const float4* r4 = g4 + lst_off[e];
 #pragma unroll
                 for (int pp = 0; pp < NPER; ++pp) {
-                    const int q = lane + 32 * pp;
-                    if (q < Wov) {
-                        const float4 g = ld_stream(g4 + q);
+                    if (lane + 32 * pp < Wov) {
+                        const float4 g = ld_stream(r4 + 32 * pp);
                         acc[pp].x = __fmaf_rn(c, g.x, acc[pp].x); acc[pp].y = __fmaf_rn(c, g.y, acc[pp].y);
                         acc[pp].z = __fmaf_rn(c, g.z, acc[pp].z); acc[pp].w = __fmaf_rn(c, g.w, acc[pp].w);
                     }
@@ -458,7 +494,7 @@ int trilinear_resize_bwd(const float* gout, float* gin, int BC, int Di, int Hi, 
     // up-sampling by a factor <= 2)
     if (Wo % 4 == 0 && Wo <= 512 && aligned(gout, 16) && tri_max_refs(Wi, Wo, ac) <= 5) {
         const int nper = (Wo / 4 + 31) / 32;
-        const size_t smem2 = smem + (size_t)6 * Wi * 4 + 16 + (size_t)kTriWarps * (Wo + 4) * sizeof(float);
+        const size_t smem2 = smem + (size_t)6 * Wi * 4 + 16 + (size_t)kTriWarps * (Wo + 4) * sizeof(float) + (size_t)kTriWarps * kTriList * 8;
         const long long n_rows = (long long)BC * Di * Hi;
         const unsigned grid = (unsigned)std::min<long long>((n_rows + kTriWarps - 1) / kTriWarps, (long long)num_sms() * 8);
         auto launch = [&](auto kern) -> int {
