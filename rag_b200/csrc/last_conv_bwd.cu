@@ -57,7 +57,7 @@ __device__ __forceinline__ void lb_window(const float* sm, int td, int th, int t
         }
 }
 
-// grid (ceil(W/32), ceil(H/8), B*ceil(D/4)); 256 threads.  smem: tile | weights [C][27]
+// grid (ceil(W/32), ceil(H/8), B*ceil(D/4)); 256 threads.  smem: tile | weights [C][28]
 __global__ void __launch_bounds__(256)
 conv3d_c1_bwd_data_kernel(const float* __restrict__ g, const float* __restrict__ wgt, float* __restrict__ gin,
                           int C, int D, int H, int W, int n_dt) {
@@ -65,7 +65,11 @@ conv3d_c1_bwd_data_kernel(const float* __restrict__ g, const float* __restrict__
     float* tile = lbd_smem;
     float* ws = tile + kLbRows * kLbSW;
     const int b = blockIdx.z / n_dt, d0 = (blockIdx.z - b * n_dt) * kLbD, h0 = blockIdx.y * kLbH, w0 = blockIdx.x * kLbW;
-    for (int i = threadIdx.x; i < C * 27; i += 256) ws[i] = __ldg(wgt + i);
+    // weights padded to 28 per channel: the 27 taps of a channel are seven broadcast LDS.128 instead of 27 scalar loads
+    for (int i = threadIdx.x; i < C * 28; i += 256) {
+        const int c = i / 28, k = i - c * 28;
+        ws[i] = k < 27 ? __ldg(wgt + c * 27 + k) : 0.f;
+    }
     lb_stage(tile, g, b, d0, h0, w0, D, H, W);
     __syncthreads();
     const int tw = threadIdx.x & 7, th = (threadIdx.x >> 3) & 7, td = threadIdx.x >> 6;
@@ -76,7 +80,12 @@ conv3d_c1_bwd_data_kernel(const float* __restrict__ g, const float* __restrict__
     const size_t vol = (size_t)D * H * W;
     float* o = gin + (size_t)b * C * vol + ((size_t)d * H + h) * W + w;
     for (int c = 0; c < C; ++c) {
-        const float* wc = ws + c * 27;
+        float wc[28];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(ws + c * 28 + 4 * q);
+            wc[4 * q] = v.x; wc[4 * q + 1] = v.y; wc[4 * q + 2] = v.z; wc[4 * q + 3] = v.w;
+        }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         // gin[p] = sum_k W[k] g[p - k + 1]: tap (kd,kh,kw) reads the window at (2-kd, 2-kh, i + 2 - kw) for output i
 #pragma unroll
@@ -251,7 +260,7 @@ int conv3d_c1_bwd(const float* g, const float* in, const float* w, float* gin, f
         return fail(RAG_E_SHAPE, "conv3d_c1_bwd: B*ceil(D/4) and ceil(H/8) must be <= 65535");
     const size_t tile_bytes = (size_t)kLbRows * kLbSW * sizeof(float);
     if (gin) {
-        const size_t smem = tile_bytes + (size_t)C * 27 * sizeof(float);
+        const size_t smem = tile_bytes + (size_t)C * 28 * sizeof(float);
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(conv3d_c1_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return fail((int)e, "conv3d_c1_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
