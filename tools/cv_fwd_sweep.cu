@@ -16,6 +16,8 @@ std::atomic<uint64_t> g_launches{0};
 int main(int argc, char** argv) {
     int B = 8, C = 12, Df = 64, Hf = 160, Wf = 320;
     if (argc > 1 && atoi(argv[1]) == 1) { B = 4; Hf = 96; Wf = 192; }
+    if (argc > 1 && atoi(argv[1]) == 2) { B = 4; Hf = 128; Wf = 416; }
+    if (argc > 1 && atoi(argv[1]) == 3) { B = 4; Hf = 128; Wf = 416; Df = 96; }
     const size_t nf = (size_t)B * C * Hf * Wf, nv = (size_t)B * 2 * C * Df * Hf * Wf;
     float *x, *y, *cost;
     unsigned int* ctr;
