@@ -17,6 +17,7 @@
 #include <cuda_pipeline.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -28,7 +29,9 @@ constexpr int kLcRowVecs = (kLcWT + 8) / 4;                 // ... w in [w0-4, w
 // Shared-memory rows are SKEWED: 4 floats of padding after every 32, so that the eight 8-float segments of
 // a row start in distinct bank groups and the threads' LDS.128 are conflict-free (unskewed: 2-way).
 constexpr int kLcSW = kLcWT + 8 + 8;                        // row stride (80 floats)
-__host__ __device__ constexpr int lc_skew(int col) { return col + 4 * (col >> 5); }
+// (columns 64-67, the ninth vector a thread row reads, sit IN the first gap: after the plain skew they would share bank
+// group 2 with columns 8-11, a 2-way conflict on every second LDS.128)
+__host__ __device__ constexpr int lc_skew(int col) { return col < 64 ? col + 4 * (col >> 5) : (col < 68 ? col - 32 : col + 8); }
 constexpr int kLcRows = kLcSD * kLcSH;                      // 180 rows per stage
 constexpr int kLcStage = kLcRows * kLcSW;                   // floats per stage (14400)
 
@@ -43,7 +46,7 @@ constexpr int kLcStage = kLcRows * kLcSW;                   // floats per stage 
 // event chain cannot be expressed inside a stream capture: a capturing stream is refused with RAG_E_CAPTURE
 // (callers fall back to the reference's own nn.Conv3d there).
 constexpr int kLcMaxC = 64, kLcSlotsW = 8;
-__constant__ float c_lcw[kLcSlotsW][kLcMaxC * 27];
+__constant__ __align__(16) float c_lcw[kLcSlotsW][kLcMaxC * 28];   // 27 weights per channel, padded to 28 (16-byte rows)
 struct LcRing {
     std::mutex mu;
     unsigned next = 0;
@@ -128,7 +131,7 @@ conv3d_c1_kernel(const float* __restrict__ in, const float* __restrict__ w, floa
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) wr[kd][kh][kw] = c_lcw[wslot][c * 27 + (kd * 3 + kh) * 3 + kw];
+                for (int kw = 0; kw < 3; ++kw) wr[kd][kh][kw] = c_lcw[wslot][c * 28 + (kd * 3 + kh) * 3 + kw];
 #pragma unroll
         for (int dz = 0; dz < 6; ++dz) {
 #pragma unroll
@@ -180,6 +183,198 @@ conv3d_c1_kernel(const float* __restrict__ in, const float* __restrict__ w, floa
     }
 }
 
+// The march kernel: ONE warp per CTA owns an 8 (h) x 64 (w) column of DT output planes and walks the input planes d0-1 ..
+// d0+DT in order; a thread keeps THREE rotating accumulator sets (2 h x 8 w each) for the output planes d-1, d, d+1 that the
+// current input plane feeds (kd = 2, 1, 0), loops over the channels inside the plane, and stores the oldest set when the
+// plane is done.  A unit of work is one channel of one plane (10 x 72 inputs, 432 FFMA per thread); the warp's units stream
+// through a private ring of R shared-memory slots filled by cp.async R-1 units ahead -- no block barrier anywhere, one
+// __syncwarp per unit.  The inner loop (one unit) is ~9 KB of code run C times in a row, where the tile kernel's unrolled
+// channel body is 47 KB that twelve warps walk at different places (no_instruction stalls).
+//
+// Shared-memory layout: a cp.async lands in shared memory one wavefront per (global 128-byte line, shared 128-byte chunk)
+// pair it touches (tools/ldgsts_probe.cu: 4 wavefronts per warp instruction when lines map onto chunks, 12 when the run is
+// shifted by 16 bytes), and with the tile kernel's layout those wavefronts -- not issue slots -- are the bound.  So a staged
+// row is three chunks that mirror global lines: columns w0..w0+31, w0+32..w0+63, and an edge chunk with w0+64..w0+67 at its
+// front and w0-4..w0-1 further back.  The vector pairs of the second chunk are swapped (lm_swz), so that the eight lanes of a
+// row, which own columns 8tw..8tw+7, hit eight different bank groups with each of their LDS.128.
+constexpr int kLmSW = 96, kLmPlane = kLcSH * kLmSW;           // row stride (floats), floats per staged plane
+__host__ __device__ constexpr int lm_swz(int v) { return v < 8 || v > 15 ? v : v ^ 1; }
+__device__ __forceinline__ void lm_cp16(float* smem, const float* g) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(32, 12)
+conv3d_c1_march_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int D, int H, int W, int DT, int n_dt, int wslot) {
+    extern __shared__ __align__(128) float lc_smem[];
+    const int lane = threadIdx.x;
+    const int b = blockIdx.z / n_dt, dt = blockIdx.z - b * n_dt;
+    const int d0 = dt * DT, h0 = blockIdx.y * kLcHT, w0 = blockIdx.x * kLcWT;
+    const int dend = min(d0 + DT, D), nplanes = dend - d0 + 2;
+    const size_t chan = (size_t)D * H * W, plane = (size_t)H * W;
+    const float* inb = in + (size_t)b * C * chan;
+
+    // Copy slots of a lane: i < 5 -> the two full chunks of rows 2i and 2i+1 (16 lanes per row: shared and global offsets
+    // are a per-lane base plus i times a constant); slot 5 -> the two edge vectors of the ten rows (lanes 0-19).  Vectors
+    // outside the image are zeroed once in every ring slot and never copied; a plane outside the volume is not copied at
+    // all (its units are skipped).
+    const int mrow = lane >> 4, mvec = lane & 15, erow = lane >> 1, eright = lane & 1;
+    int m_s = mrow * kLmSW + 4 * lm_swz(mvec), e_s = erow * kLmSW + 64 + (eright ? 0 : 24);
+    int m_g = (h0 - 1 + mrow) * W + w0 + 4 * mvec, e_g = (h0 - 1 + erow) * W + w0 + (eright ? 64 : -4);
+    unsigned okmask = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int row = i < 5 ? 2 * i + mrow : erow;
+        const int gh = h0 - 1 + row, gw = i < 5 ? w0 + 4 * mvec : w0 + (eright ? 64 : -4);
+        const bool mine = i < 5 || lane < 20;
+        const bool ok = mine && gh >= 0 && gh < H && gw >= 0 && gw < W;                  // W % 4 == 0
+        okmask |= ok ? 1u << i : 0u;
+        if (mine && !ok) {
+#pragma unroll
+            for (int q = 0; q < R; ++q)
+                *reinterpret_cast<float4*>(lc_smem + q * kLmPlane + (i < 5 ? m_s + i * 2 * kLmSW : e_s)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    __syncwarp();
+    asm volatile("" : "+r"(m_s), "+r"(e_s), "+r"(m_g), "+r"(e_g));   // keep them in registers (the compiler would re-derive them per unit)
+    const bool ok0 = okmask & 1u, ok1 = okmask & 2u, ok2 = okmask & 4u, ok3 = okmask & 8u, ok4 = okmask & 16u, ok5 = okmask & 32u;
+    const int W2 = 2 * W;
+    // producer state: the next unit to copy is channel pc of plane pj (d = d0 - 1 + pj), into ring slot ps
+    int pj = 0, pc = 0, ps = 0;
+    const float* psrc = inb + (ptrdiff_t)(d0 - 1) * (ptrdiff_t)plane;       // points before the volume while the plane is outside (not read)
+    // a unit's copy is issued in three pairs of vectors, spread over the consumer's row blocks (six LDGSTS back to back fill
+    // the shared-memory queue the row loads wait in)
+    bool cv = false;
+    const float* cg = nullptr;
+    float* cdst = nullptr;
+    auto copy_prep = [&]() {
+        const int gd = d0 - 1 + pj;
+        cv = pj < nplanes && gd >= 0 && gd < D;
+        cg = psrc + m_g;
+        cdst = lc_smem + ps * kLmPlane + m_s;
+    };
+    auto copy_pair = [&](int k) {
+        if (!cv) return;
+        if (k == 0) {
+            if (ok0) lm_cp16(cdst, cg);
+            if (ok1) lm_cp16(cdst + 2 * kLmSW, cg + W2);
+        } else if (k == 1) {
+            if (ok2) lm_cp16(cdst + 4 * kLmSW, cg + 2 * W2);
+            if (ok3) lm_cp16(cdst + 6 * kLmSW, cg + 3 * W2);
+        } else {
+            if (ok4) lm_cp16(cdst + 8 * kLmSW, cg + 4 * W2);
+            if (ok5) lm_cp16(lc_smem + ps * kLmPlane + e_s, psrc + e_g);
+        }
+    };
+    auto copy_done = [&]() {
+        if (pj < nplanes) {
+            psrc += chan;
+            if (++pc == C) { pc = 0; ++pj; psrc += (ptrdiff_t)plane - (ptrdiff_t)C * (ptrdiff_t)chan; }
+            if (++ps == R) ps = 0;
+        }
+        __pipeline_commit();
+    };
+    auto copy_next = [&]() { copy_prep(); copy_pair(0); copy_pair(1); copy_pair(2); copy_done(); };
+#pragma unroll
+    for (int i = 0; i < R - 1; ++i) copy_next();
+
+    // thread geometry: 8 w groups x 4 h groups; a thread owns columns 8tw..8tw+7 of rows th, th+1 and reads, per input row,
+    // the vector left of them (only its last element is used), its own two vectors and the element right of them -- four
+    // loads at per-lane offsets, no shuffles and no selects (the out-of-tile neighbours of lanes 0 and 7 are the edge chunk)
+    const int tw = lane & 7, th = ((lane >> 3) & 3) * 2;
+    int c0 = th * kLmSW + 4 * lm_swz(2 * tw), c1 = th * kLmSW + 4 * lm_swz(2 * tw + 1);
+    int cl = th * kLmSW + (tw == 0 ? 64 + 24 : 4 * lm_swz(2 * tw - 1)), cr = th * kLmSW + (tw == 7 ? 64 : 4 * lm_swz(2 * tw + 2));
+    asm volatile("" : "+r"(c0), "+r"(c1), "+r"(cl), "+r"(cr));
+    int cs = 0;                                                   // consumer ring slot
+
+    float a2[2][8], a1[2][8], a0[2][8];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a2[q][i] = a1[q][i] = a0[q][i] = 0.f;
+
+    // input plane j feeds output planes d0+j-2 (kd = 2, set a2, complete afterwards), d0+j-1 (kd = 1, a1), d0+j (kd = 0, a0);
+    // MASK (bit kd) says which of the three lie inside the tile -- a compile-time constant, so a unit is one basic block
+    auto do_plane = [&](auto mask_tag, bool live) {
+        constexpr int MASK = decltype(mask_tag)::value;
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+            __pipeline_wait_prior(R - 2);
+            __syncwarp();                                         // the unit has landed for all lanes; all lanes are past the previous one
+            const float* st = lc_smem + cs * kLmPlane;
+            if (++cs == R) cs = 0;
+            if (!live) { copy_next(); continue; }                 // a plane outside the volume is all zeros: nothing to add
+            copy_prep();
+            float wr[3][3][3];
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) wr[kd][kh][kw] = c_lcw[wslot][c * 28 + (kd * 3 + kh) * 3 + kw];
+#pragma unroll
+            for (int hy = 0; hy < 4; ++hy) {
+                const float* p = st + hy * kLmSW;
+                const float4 ml = *reinterpret_cast<const float4*>(p + cl);
+                const float4 m0 = *reinterpret_cast<const float4*>(p + c0);
+                const float4 m1 = *reinterpret_cast<const float4*>(p + c1);
+                float v[10];
+                v[0] = ml.w;
+                v[1] = m0.x; v[2] = m0.y; v[3] = m0.z; v[4] = m0.w;
+                v[5] = m1.x; v[6] = m1.y; v[7] = m1.z; v[8] = m1.w;
+                v[9] = p[cr];
+                if (hy < 3) copy_pair(hy);
+                else copy_done();
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+                    const int oh = hy - kh;
+                    if (oh < 0 || oh >= 2) continue;
+#pragma unroll
+                    for (int kd = 0; kd < 3; ++kd) {
+                        if (!(MASK & (1 << kd))) continue;
+                        float (&a)[2][8] = kd == 2 ? a2 : (kd == 1 ? a1 : a0);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            a[oh][i] = __fmaf_rn(wr[kd][kh][2], v[i + 2], __fmaf_rn(wr[kd][kh][1], v[i + 1], __fmaf_rn(wr[kd][kh][0], v[i], a[oh][i])));
+                    }
+                }
+            }
+        }
+    };
+    const int n = dend - d0;
+    const int wo = w0 + 8 * tw;
+#pragma unroll 1
+    for (int j = 0; j < nplanes; ++j) {
+        const int gd = d0 - 1 + j;
+        const bool live = gd >= 0 && gd < D;
+        const int mask = (j >= 2 ? 4 : 0) | (j >= 1 && j <= n ? 2 : 0) | (j < n ? 1 : 0);
+        switch (mask) {
+            case 7: do_plane(std::integral_constant<int, 7>{}, live); break;
+            case 1: do_plane(std::integral_constant<int, 1>{}, live); break;
+            case 3: do_plane(std::integral_constant<int, 3>{}, live); break;
+            case 6: do_plane(std::integral_constant<int, 6>{}, live); break;
+            case 4: do_plane(std::integral_constant<int, 4>{}, live); break;
+            default: do_plane(std::integral_constant<int, 2>{}, live); break;
+        }
+        if (j >= 2) {                                             // output plane d0 + j - 2 is complete
+            const int d = d0 + j - 2;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int h = h0 + th + q;
+                if (h < H && wo < W) {
+                    float* o = out + (((size_t)b * D + d) * H + h) * W + wo;
+                    reinterpret_cast<float4*>(o)[0] = make_float4(a2[q][0], a2[q][1], a2[q][2], a2[q][3]);
+                    if (wo + 4 < W) reinterpret_cast<float4*>(o)[1] = make_float4(a2[q][4], a2[q][5], a2[q][6], a2[q][7]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { a2[q][i] = a1[q][i]; a1[q][i] = a0[q][i]; a0[q][i] = 0.f; }
+    }
+}
+
 int conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int D, int H, int W, cudaStream_t st) {
     if (!in || !w || !out) return fail(RAG_E_NULL, "conv3d_c1_fwd: null pointer");
     if (B <= 0 || C <= 0 || D <= 0 || H <= 0 || W <= 0) return fail(RAG_E_SHAPE, "conv3d_c1_fwd: non-positive dimension");
@@ -218,10 +413,28 @@ int conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int
         if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaEventCreate: %s", cudaGetErrorString(e));
         ring.have[wslot] = true;
     }
-    e = cudaMemcpyToSymbolAsync(c_lcw, w, (size_t)C * 27 * sizeof(float), (size_t)wslot * kLcMaxC * 27 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    void* ctab = nullptr;
+    e = cudaGetSymbolAddress(&ctab, c_lcw);
+    if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaGetSymbolAddress: %s", cudaGetErrorString(e));
+    e = cudaMemcpy2DAsync(static_cast<float*>(ctab) + (size_t)wslot * kLcMaxC * 28, 28 * sizeof(float), w, 27 * sizeof(float), 27 * sizeof(float), C,
+                          cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: weight copy: %s", cudaGetErrorString(e));
+    static const int march = getenv("RAG_LC_MARCH") ? atoi(getenv("RAG_LC_MARCH")) : 0;
+    if (march > 0) {
+        const int DT = march, n_dtm = (D + DT - 1) / DT;
+        dim3 grid((W + kLcWT - 1) / kLcWT, (H + kLcHT - 1) / kLcHT, B * n_dtm);
+        static const int mode = getenv("RAG_LC_MODE") ? atoi(getenv("RAG_LC_MODE")) : 0;
+        auto go = [&](auto kern, int r) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(r * kLmPlane * sizeof(float)));
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            kern<<<grid, 32, r * kLmPlane * sizeof(float), st>>>(in, out, C, D, H, W, DT, n_dtm, wslot);
+        };
+        if (mode == 0) go(conv3d_c1_march_kernel<3>, 3);
+        else go(conv3d_c1_march_kernel<4>, 4);
+    } else {
     dim3 grid((W + kLcWT - 1) / kLcWT, (H + kLcHT - 1) / kLcHT, B * n_dt);
     kern<<<grid, 256 / TH, smem, st>>>(in, w, out, C, D, H, W, n_dt, wslot);
+    }
     if (int rc = check_launch("conv3d_c1_fwd")) return rc;
     e = cudaEventRecord(ring.ev[wslot], st);
     if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaEventRecord: %s", cudaGetErrorString(e));
