@@ -419,21 +419,20 @@ int conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int
     e = cudaMemcpy2DAsync(static_cast<float*>(ctab) + (size_t)wslot * kLcMaxC * 28, 28 * sizeof(float), w, 27 * sizeof(float), 27 * sizeof(float), C,
                           cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: weight copy: %s", cudaGetErrorString(e));
-    static const int march = getenv("RAG_LC_MARCH") ? atoi(getenv("RAG_LC_MARCH")) : 0;
-    if (march > 0) {
-        const int DT = march, n_dtm = (D + DT - 1) / DT;
+    // The march kernel (one warp per CTA, 8 output planes each) wins wherever its grid fills the machine: 0.366 vs 0.494 ms
+    // at B=8 480x960, 0.082 vs 0.111 ms at B=4 288x576; below half a wave of warps the tile kernel's 4-warp CTAs are faster.
+    constexpr int kMarchDT = 8, kMarchRing = 3;
+    const int n_dtm = (D + kMarchDT - 1) / kMarchDT;
+    const long long warps = (long long)((W + kLcWT - 1) / kLcWT) * ((H + kLcHT - 1) / kLcHT) * B * n_dtm;
+    if (warps >= 6LL * num_sms() && (long long)B * n_dtm <= 65535) {
+        auto mk = conv3d_c1_march_kernel<kMarchRing>;
+        e = cudaFuncSetAttribute(mk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         dim3 grid((W + kLcWT - 1) / kLcWT, (H + kLcHT - 1) / kLcHT, B * n_dtm);
-        static const int mode = getenv("RAG_LC_MODE") ? atoi(getenv("RAG_LC_MODE")) : 0;
-        auto go = [&](auto kern, int r) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(r * kLmPlane * sizeof(float)));
-            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            kern<<<grid, 32, r * kLmPlane * sizeof(float), st>>>(in, out, C, D, H, W, DT, n_dtm, wslot);
-        };
-        if (mode == 0) go(conv3d_c1_march_kernel<3>, 3);
-        else go(conv3d_c1_march_kernel<4>, 4);
+        mk<<<grid, 32, kMarchRing * kLmPlane * sizeof(float), st>>>(in, out, C, D, H, W, kMarchDT, n_dtm, wslot);
     } else {
-    dim3 grid((W + kLcWT - 1) / kLcWT, (H + kLcHT - 1) / kLcHT, B * n_dt);
-    kern<<<grid, 256 / TH, smem, st>>>(in, w, out, C, D, H, W, n_dt, wslot);
+        dim3 grid((W + kLcWT - 1) / kLcWT, (H + kLcHT - 1) / kLcHT, B * n_dt);
+        kern<<<grid, 256 / TH, smem, st>>>(in, w, out, C, D, H, W, n_dt, wslot);
     }
     if (int rc = check_launch("conv3d_c1_fwd")) return rc;
     e = cudaEventRecord(ring.ev[wslot], st);
