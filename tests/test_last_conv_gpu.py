@@ -23,6 +23,7 @@ MARCH_SHAPES = [
     (8, 1, 26, 72, 256),      # a single channel (the copy ring runs ahead across planes); D % 8 == 2
     (4, 4, 56, 96, 192),      # the training crop's h x w
     (2, 12, 64, 96, 320),     # the layer's real depth and channels
+    (111, 2, 8, 64, 64),      # many pairs, ONE column of planes each: both out-of-volume planes in every column
 ]
 
 
