@@ -228,6 +228,162 @@ conv3d_c1_bwd_weight_kernel(const float* __restrict__ g, const float* __restrict
     }
 }
 
+// The march version of the weight gradient (the default).  ncu on the tile kernel above: 39 M shared-memory wavefronts in
+// 50 M SM cycles -- every thread re-reads a 3x3x6 window of g per tile (54 values for 216 FMAs; the 18 scalar loads among
+// them are 4-way bank conflicts) behind two block barriers.  Here a WARP owns a 4 (h) x 32 (w) column of 16 input planes of
+// one pair and walks it along d: the thread's g window ROLLS (three planes of 3 x 6 values in registers; one new plane = three
+// row loads per step, the oldest plane's registers are overwritten -- the step is unrolled by three so that the roles rotate
+// without moves), the neighbours' elements come by shuffle, and the g plane plus the thread's two input vectors of the step
+// arrive through a warp-private cp.async ring (no block barrier).  A g row in the ring mirrors its global 128-byte line
+// (columns w0..w0+31) and keeps the two halo vectors in a second chunk at a position that rotates with the row (the four
+// rows of a warp's edge loads fall into different banks).  Warps take items warp, warp + n_warps, ...; partial sums as above.
+constexpr int kWmDS = 16, kWmR = 4;                           // input planes per item, ring slots per warp
+constexpr int kWmRowF = 64, kWmG = 6 * kWmRowF, kWmSlot = kWmG + 2 * 32 * 4;   // floats: g rows | x vectors [2 channels][32 lanes]
+__device__ __forceinline__ int wm_edge(int row) { return 32 + 8 * (row & 3); }   // + 0: columns w0+32..35, + 4: columns w0-4..w0-1
+
+__global__ void __launch_bounds__(128, 3)
+conv3d_c1_bwd_weight_march_kernel(const float* __restrict__ g, const float* __restrict__ in, float* __restrict__ part,
+                                  int B, int C, int D, int H, int W, int n_w32, int n_h4, int n_ds) {
+    extern __shared__ __align__(128) float wm_smem[];
+    __shared__ float red[4][54];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = 2 * blockIdx.y, n_groups = gridDim.x;
+    const bool two = c0 + 1 < C;
+    const int tw = lane & 7, th = lane >> 3;
+    const size_t vol = (size_t)D * H * W;
+    const int n_items = B * n_ds * n_h4 * n_w32, stride = n_groups * 4;
+    float* ring = wm_smem + warp * (kWmR * kWmSlot);
+
+    // the lane's copies of a unit: two g vectors (k = 0: rows 0-3, eight lanes per row; k = 1: rows 4-5 on lanes 0-15, the
+    // twelve halo vectors on lanes 16-27) and its own input vector of both channels
+    const bool k1_main = lane < 16, k1_on = lane < 28;
+    const int r0 = lane >> 3, r1 = k1_main ? 4 + (lane >> 3) : (lane - 16) >> 1;
+    const int cq0 = 4 * (lane & 7), cq1 = k1_main ? 4 * (lane & 7) : ((lane & 1) ? -4 : 32);          // column offset from w0
+    const int so0 = r0 * kWmRowF + 4 * (lane & 7), so1 = r1 * kWmRowF + (k1_main ? 4 * (lane & 7) : wm_edge(r1) + ((lane & 1) ? 4 : 0));
+
+    // producer state: unit pu of item pi; a unit = g plane d0 - 1 + pu (p_gd) and the input plane d0 + pu - 2.  The three source
+    // pointers are set per item and advance by one plane per unit (they may point outside the tensors while the plane or the
+    // lane's row / column is outside: then the copy is a zero fill that reads nothing)
+    const ptrdiff_t HW = (ptrdiff_t)H * W;
+    int pi = blockIdx.x * 4 + warp, pu = 0, ps = 0, p_nu = 0, p_gd = 0;
+    const float *pg0 = g, *pg1 = g, *px = in;
+    bool v0 = false, v1 = false, vx = false;
+    auto decode = [&](int item, int& b, int& d0, int& h0, int& w0, int& nu) {
+        int t = item;
+        const int wq = t % n_w32; t /= n_w32;
+        const int hq = t % n_h4; t /= n_h4;
+        const int dq = t % n_ds; b = t / n_ds;
+        d0 = dq * kWmDS; h0 = hq * 4; w0 = wq * 32;
+        nu = min(kWmDS, D - d0) + 2;
+    };
+    auto p_begin = [&]() {
+        int b, d0, h0, w0;
+        decode(pi, b, d0, h0, w0, p_nu);
+        p_gd = d0 - 1;
+        const float* gb = g + (ptrdiff_t)b * (ptrdiff_t)vol + (ptrdiff_t)p_gd * HW;
+        const int gh0 = h0 - 1 + r0, gw0 = w0 + cq0, gh1 = h0 - 1 + r1, gw1 = w0 + cq1, h = h0 + th, w = w0 + 4 * tw;
+        pg0 = gb + (ptrdiff_t)gh0 * W + gw0;
+        pg1 = gb + (ptrdiff_t)gh1 * W + gw1;
+        v0 = gh0 >= 0 && gh0 < H && gw0 < W;                                        // gw0 >= 0; W % 4 == 0
+        v1 = k1_on && gh1 >= 0 && gh1 < H && gw1 >= 0 && gw1 < W;
+        px = in + ((ptrdiff_t)b * C + c0) * (ptrdiff_t)vol + (ptrdiff_t)(d0 - 2) * HW + (ptrdiff_t)h * W + w;
+        vx = h < H && w < W;
+    };
+    if (pi < n_items) p_begin();
+    auto copy_next = [&]() {
+        if (pi < n_items) {
+            float* slot = ring + ps * kWmSlot;
+            const bool pl = (unsigned)p_gd < (unsigned)D;
+            const bool ok0 = pl && v0, ok1 = pl && v1, okx = vx && pu >= 2, okx1 = okx && two;
+            __pipeline_memcpy_async(slot + so0, ok0 ? pg0 : g, 16, ok0 ? 0 : 16);
+            if (k1_on) __pipeline_memcpy_async(slot + so1, ok1 ? pg1 : g, 16, ok1 ? 0 : 16);
+            __pipeline_memcpy_async(slot + kWmG + lane * 4, okx ? px : in, 16, okx ? 0 : 16);
+            __pipeline_memcpy_async(slot + kWmG + 128 + lane * 4, okx1 ? px + vol : in, 16, okx1 ? 0 : 16);
+            pg0 += HW; pg1 += HW; px += HW; ++p_gd;
+            if (++ps == kWmR) ps = 0;
+            if (++pu == p_nu) {
+                pu = 0;
+                pi += stride;
+                if (pi < n_items) p_begin();
+            }
+        }
+        __pipeline_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < kWmR - 1; ++i) copy_next();
+
+    float acc[2][27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) { acc[0][k] = 0.f; acc[1][k] = 0.f; }
+    float W0[3][6], W1[3][6], W2[3][6];                         // g planes of the rolling window: [row h-1, h, h+1][column -1 .. 4]
+    int cs = 0;
+    const bool edge = tw == 0 || tw == 7;
+    // one unit: the new g plane goes into `nw`; with (old, mid, nw) = g planes d-1, d, d+1 the input plane d is accumulated
+    auto unit = [&](bool fma, float (&nw)[3][6], const float (&old)[3][6], const float (&mid)[3][6]) {
+        __pipeline_wait_prior(kWmR - 2);
+        __syncwarp();
+        copy_next();
+        const float* slot = ring + cs * kWmSlot;
+        if (++cs == kWmR) cs = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int row = th + j;
+            const float* p = slot + row * kWmRowF;
+            const float4 m = *reinterpret_cast<const float4*>(p + 4 * tw);
+            const float e = edge ? p[wm_edge(row) + (tw == 0 ? 7 : 0)] : 0.f;
+            const float l = __shfl_up_sync(0xffffffffu, m.w, 1, 8), r = __shfl_down_sync(0xffffffffu, m.x, 1, 8);
+            nw[j][0] = tw == 0 ? e : l;
+            nw[j][1] = m.x; nw[j][2] = m.y; nw[j][3] = m.z; nw[j][4] = m.w;
+            nw[j][5] = tw == 7 ? e : r;
+        }
+        if (!fma) return;
+        const float4 x0 = *reinterpret_cast<const float4*>(slot + kWmG + lane * 4);
+        const float4 x1 = *reinterpret_cast<const float4*>(slot + kWmG + 128 + lane * 4);
+        // gW[k] += in[p] g[p - k + 1]: for input column i (0..3) tap (kd,kh,kw) pairs with plane 2-kd, row 2-kh, element i + 2 - kw
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float* r = kd == 0 ? nw[2 - kh] : (kd == 1 ? mid[2 - kh] : old[2 - kh]);
+                    const int k = (kd * 3 + kh) * 3 + kw;
+                    float a0 = acc[0][k], a1 = acc[1][k];
+                    a0 = __fmaf_rn(x0.x, r[0 + 2 - kw], a0); a1 = __fmaf_rn(x1.x, r[0 + 2 - kw], a1);
+                    a0 = __fmaf_rn(x0.y, r[1 + 2 - kw], a0); a1 = __fmaf_rn(x1.y, r[1 + 2 - kw], a1);
+                    a0 = __fmaf_rn(x0.z, r[2 + 2 - kw], a0); a1 = __fmaf_rn(x1.z, r[2 + 2 - kw], a1);
+                    a0 = __fmaf_rn(x0.w, r[3 + 2 - kw], a0); a1 = __fmaf_rn(x1.w, r[3 + 2 - kw], a1);
+                    acc[0][k] = a0; acc[1][k] = a1;
+                }
+    };
+    for (int item = blockIdx.x * 4 + warp; item < n_items; item += stride) {
+        int b, d0, h0, w0, nu;
+        decode(item, b, d0, h0, w0, nu);
+        for (int u = 0; u < nu; u += 3) {                         // unit u: planes (u-2, u-1, u) = (old, mid, new)
+            unit(u >= 2, W0, W1, W2);
+            if (u + 1 < nu) unit(u + 1 >= 2, W1, W2, W0);
+            if (u + 2 < nu) unit(true, W2, W0, W1);
+        }
+    }
+    __pipeline_wait_prior(0);
+    // CTA reduction, fixed order: lanes by shuffle tree, then the 4 warps in order
+#pragma unroll
+    for (int k = 0; k < 54; ++k) {
+        float v = acc[k / 27][k % 27];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 54 && (threadIdx.x < 27 || two)) {
+        float v = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 4; ++wv) v += red[wv][threadIdx.x];
+        const int c = c0 + threadIdx.x / 27, k = threadIdx.x % 27;
+        part[((size_t)c * n_groups + blockIdx.x) * 27 + k] = v;
+    }
+}
+
 // gw[c][k] = sum over groups of part[c][grp][k], fixed order, fp64.  grid C; 27 warps (one per tap): the lanes take every
 // 32nd group, then a shuffle tree in a fixed order (the first version walked the 296 partials of a tap with ONE thread:
 // 23 us of dependent loads).
@@ -269,8 +425,16 @@ int conv3d_c1_bwd(const float* g, const float* in, const float* w, float* gin, f
         if (int rc = check_launch("conv3d_c1_bwd(data)")) return rc;
     }
     if (gw) {
+        static const bool tile_kernel = getenv("RAG_LC_WTILE") != nullptr;
+        if (tile_kernel) {
         const size_t wsmem = 2 * tile_bytes + (size_t)2 * 2 * 256 * sizeof(float4);   // two tile buffers + two input-vector buffers
         conv3d_c1_bwd_weight_kernel<<<dim3(kLbGroups, (C + 1) / 2), 256, wsmem, st>>>(g, in, workspace, B, C, D, H, W, n_wt, n_ht, n_dt);
+        } else {
+        const int n_w32 = (W + 31) / 32, n_h4 = (H + 3) / 4, n_ds = (D + kWmDS - 1) / kWmDS;
+        if ((long long)B * n_ds * n_h4 * n_w32 >= (1LL << 31)) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: too many tiles");
+        const size_t wsmem = (size_t)4 * kWmR * kWmSlot * sizeof(float);
+        conv3d_c1_bwd_weight_march_kernel<<<dim3(kLbGroups, (C + 1) / 2), 128, wsmem, st>>>(g, in, workspace, B, C, D, H, W, n_w32, n_h4, n_ds);
+        }
         if (int rc = check_launch("conv3d_c1_bwd(weight)")) return rc;
         conv3d_c1_bwd_weight_final_kernel<<<C, 27 * 32, 0, st>>>(workspace, gw, kLbGroups);
         if (int rc = check_launch("conv3d_c1_bwd(weight final)")) return rc;
