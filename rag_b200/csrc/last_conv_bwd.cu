@@ -4,8 +4,9 @@
 //     gW[0,c,kd,kh,kw]    = sum_{b,d,h,w}  in[b,c,d+kd-1,h+kh-1,w+kw-1] * g[b,0,d,h,w]            (weight gradient)
 // Both read the ONE-channel upstream gradient g through the same 3x3x6 register window per thread (4 adjacent w): the data
 // gradient re-uses the window for all C channels (1296 FMAs per window, output streamed with 128-bit stores: the C-times
-// larger tensor is written once), the weight gradient keeps 27 running sums per thread for one channel over many tiles and
-// reduces once per CTA (fixed order, fp64 final pass: deterministic).  cuDNN has no good kernel for a 1-channel side.
+// larger tensor is written once); the weight gradient walks columns of positions along d with the window ROLLING in registers
+// and keeps 2 x 27 running sums per thread, reduced once per CTA (fixed order, fp64 final pass: deterministic).  cuDNN has no
+// good kernel for a 1-channel side.
 #include <cuda_pipeline.h>
 
 #include "common.cuh"
@@ -27,19 +28,6 @@ __device__ __forceinline__ void lb_stage(float* sm, const float* __restrict__ g,
         if (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W)   // W % 4 == 0: a quad is inside or outside as a whole
             val = __ldg(reinterpret_cast<const float4*>(g + (size_t)b * vol + ((size_t)gd * H + gh) * W + gw));
         *reinterpret_cast<float4*>(sm + row * kLbSW + 4 * v) = val;
-    }
-}
-
-// the same tile through cp.async (no register staging; quads outside the volume are zero-filled copies of no source bytes)
-__device__ __forceinline__ void lb_stage_async(float* sm, const float* __restrict__ g, int b, int d0, int h0, int w0, int D, int H, int W) {
-    const size_t vol = (size_t)D * H * W;
-    for (int i = threadIdx.x; i < kLbRows * (kLbSW / 4); i += 256) {
-        const int row = i / (kLbSW / 4), v = i - row * (kLbSW / 4);
-        const int dz = row / (kLbH + 2), hy = row - dz * (kLbH + 2);
-        const int gd = d0 - 1 + dz, gh = h0 - 1 + hy, gw = w0 - 4 + 4 * v;
-        const bool in = gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W;
-        const float* src = in ? g + (size_t)b * vol + ((size_t)gd * H + gh) * W + gw : g;
-        __pipeline_memcpy_async(sm + row * kLbSW + 4 * v, src, 16, in ? 0 : 16);
     }
 }
 
@@ -105,131 +93,12 @@ conv3d_c1_bwd_data_kernel(const float* __restrict__ g, const float* __restrict__
     }
 }
 
-// grid (n_groups, ceil(C/2)); 256 threads; CTA (grp, cp) walks tiles grp, grp + n_groups, ... and accumulates the 27 sums of
-// channels 2cp and 2cp+1: one staging of the g tile and one register window feed 216 FMAs instead of 108 (the kernel is
-// bound by the instructions around the FMAs: staging, barriers, 54 shared-memory loads per window).
-// part [C][n_groups][27]
-__global__ void __launch_bounds__(256, 2)
-conv3d_c1_bwd_weight_kernel(const float* __restrict__ g, const float* __restrict__ in, float* __restrict__ part,
-                            int B, int C, int D, int H, int W, int n_wt, int n_ht, int n_dt) {
-    extern __shared__ __align__(16) float lbw_smem[];
-    __shared__ float red[8][54];
-    const int c0 = 2 * blockIdx.y, n_groups = gridDim.x;
-    const bool two = c0 + 1 < C;
-    const int tw = threadIdx.x & 7, th = (threadIdx.x >> 3) & 7, td = threadIdx.x >> 6;
-    const size_t vol = (size_t)D * H * W;
-    const int n_tiles = B * n_dt * n_ht * n_wt;
-    float acc[2][27];
-#pragma unroll
-    for (int k = 0; k < 27; ++k) { acc[0][k] = 0.f; acc[1][k] = 0.f; }
-    // The tile of g and the thread's two input vectors of tile k+1 are copied (cp.async) into the second buffer while tile k
-    // is worked on: the first version staged through registers between two barriers and loaded the inputs on demand, so every
-    // tile exposed an L2 and a DRAM round trip to 216 FMAs (15 % of the FP32 peak).
-    float* tiles = lbw_smem;                                          // [2][kLbRows * kLbSW]
-    float4* xs = reinterpret_cast<float4*>(lbw_smem + 2 * kLbRows * kLbSW);   // [2 buffers][2 channels][256 threads]
-    // No division per tile: the tile index advances by n_groups, i.e. by fixed digits in the mixed radix (n_wt, n_ht, n_dt, B),
-    // and the (up to three) quads of the g window a thread stages keep their place inside the window from tile to tile.
-    const int gq = n_groups / n_wt, inc_w = n_groups - gq * n_wt;
-    const int gq2 = gq / n_ht, inc_h = gq - gq2 * n_ht;
-    const int inc_b = gq2 / n_dt, inc_d = gq2 - inc_b * n_dt;
-    int i_wt, i_ht, i_dt, i_b;                                        // digits of the tile being ISSUED
-    {
-        const int t0 = blockIdx.x;
-        i_wt = t0 % n_wt; i_ht = (t0 / n_wt) % n_ht; i_dt = (t0 / (n_wt * n_ht)) % n_dt; i_b = t0 / (n_wt * n_ht * n_dt);
-    }
-    auto advance = [&]() {
-        i_wt += inc_w; if (i_wt >= n_wt) { i_wt -= n_wt; ++i_ht; }
-        i_ht += inc_h; if (i_ht >= n_ht) { i_ht -= n_ht; ++i_dt; }
-        i_dt += inc_d; if (i_dt >= n_dt) { i_dt -= n_dt; ++i_b; }
-        i_b += inc_b;
-    };
-    int s_dz[3], s_hy[3], s_v[3];                                     // the thread's quads of the window: (depth, row, vector)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int i = threadIdx.x + 256 * k;
-        const int row = i / (kLbSW / 4);
-        s_v[k] = i - row * (kLbSW / 4);
-        s_dz[k] = row / (kLbH + 2);
-        s_hy[k] = row - s_dz[k] * (kLbH + 2);
-    }
-    auto issue = [&](bool live, int buf) {                            // tile (i_b, i_dt, i_ht, i_wt) -> buffer buf
-        if (live) {
-            const int d0 = i_dt * kLbD, h0 = i_ht * kLbH, w0 = i_wt * kLbW;
-            float* sm = tiles + buf * kLbRows * kLbSW;
-            const float* gb = g + (size_t)i_b * vol;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (threadIdx.x + 256 * k < kLbRows * (kLbSW / 4)) {
-                    const int gd = d0 - 1 + s_dz[k], gh = h0 - 1 + s_hy[k], gw = w0 - 4 + 4 * s_v[k];
-                    const bool in_vol = gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W;   // W % 4 == 0
-                    const float* src = in_vol ? gb + ((size_t)gd * H + gh) * W + gw : g;
-                    __pipeline_memcpy_async(sm + (s_dz[k] * (kLbH + 2) + s_hy[k]) * kLbSW + 4 * s_v[k], src, 16, in_vol ? 0 : 16);
-                }
-            }
-            const int d = d0 + td, h = h0 + th, w = w0 + 4 * tw;
-            const bool on = d < D && h < H && w < W;
-            const float* ip = on ? in + ((size_t)i_b * C + c0) * vol + ((size_t)d * H + h) * W + w : in;
-            __pipeline_memcpy_async(xs + (buf * 2 + 0) * 256 + threadIdx.x, ip, 16, on ? 0 : 16);
-            __pipeline_memcpy_async(xs + (buf * 2 + 1) * 256 + threadIdx.x, (on && two) ? ip + vol : in, 16, (on && two) ? 0 : 16);
-        }
-        __pipeline_commit();
-    };
-    int c_d0 = i_dt * kLbD, c_h0 = i_ht * kLbH, c_w0 = i_wt * kLbW;  // origin of the tile being COMPUTED
-    issue(blockIdx.x < n_tiles, 0);
-    int it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += n_groups, ++it) {
-        const int buf = it & 1;
-        __syncthreads();                                              // everybody is done with the other buffer (tile k-1)
-        advance();
-        issue(t + n_groups < n_tiles, buf ^ 1);
-        const int n_d0 = i_dt * kLbD, n_h0 = i_ht * kLbH, n_w0 = i_wt * kLbW;
-        __pipeline_wait_prior(1);                                     // this thread's copies of tile k have landed ...
-        __syncthreads();                                              // ... and everybody's
-        const int d = c_d0 + td, h = c_h0 + th, w = c_w0 + 4 * tw;
-        c_d0 = n_d0; c_h0 = n_h0; c_w0 = n_w0;
-        if (d < D && h < H && w < W) {
-            float win[3][3][6];
-            lb_window(tiles + buf * kLbRows * kLbSW, td, th, tw, win);
-            const float4 x0 = xs[(buf * 2 + 0) * 256 + threadIdx.x];
-            const float4 x1 = xs[(buf * 2 + 1) * 256 + threadIdx.x];
-            // gW[k] += in[p] g[p - k + 1]: for input position i (0..3) tap (kd,kh,kw) pairs with window (2-kd, 2-kh, i + 2 - kw)
-#pragma unroll
-            for (int kd = 0; kd < 3; ++kd)
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        const float* r = win[2 - kd][2 - kh];
-                        const int k = (kd * 3 + kh) * 3 + kw;
-                        float a0 = acc[0][k], a1 = acc[1][k];
-                        a0 = __fmaf_rn(x0.x, r[0 + 2 - kw], a0); a1 = __fmaf_rn(x1.x, r[0 + 2 - kw], a1);
-                        a0 = __fmaf_rn(x0.y, r[1 + 2 - kw], a0); a1 = __fmaf_rn(x1.y, r[1 + 2 - kw], a1);
-                        a0 = __fmaf_rn(x0.z, r[2 + 2 - kw], a0); a1 = __fmaf_rn(x1.z, r[2 + 2 - kw], a1);
-                        a0 = __fmaf_rn(x0.w, r[3 + 2 - kw], a0); a1 = __fmaf_rn(x1.w, r[3 + 2 - kw], a1);
-                        acc[0][k] = a0; acc[1][k] = a1;
-                    }
-        }
-    }
-    // CTA reduction, fixed order: lanes by shuffle tree, then the 8 warps in order
-#pragma unroll
-    for (int k = 0; k < 54; ++k) {
-        float v = acc[k / 27][k % 27];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 54 && (threadIdx.x < 27 || two)) {
-        float v = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < 8; ++wv) v += red[wv][threadIdx.x];
-        const int c = c0 + threadIdx.x / 27, k = threadIdx.x % 27;
-        part[((size_t)c * n_groups + blockIdx.x) * 27 + k] = v;
-    }
-}
-
-// The march version of the weight gradient (the default).  ncu on the tile kernel above: 39 M shared-memory wavefronts in
-// 50 M SM cycles -- every thread re-reads a 3x3x6 window of g per tile (54 values for 216 FMAs; the 18 scalar loads among
+// Weight gradient: gW[c][k] = sum_p in[c][p] g[p - k + 1]; grid (n_groups, ceil(C/2)), 128 threads; a CTA accumulates the 27 sums
+// of channels 2cp and 2cp+1 (one g window feeds 216 FMAs instead of 108) over its share of the positions and writes one
+// partial per channel and tap: part [C][n_groups][27], reduced by the final kernel in a fixed order (fp64): deterministic.
+// History: a tile kernel (4 x 8 x 32 positions per CTA step, g tile double-buffered by cp.async, 0.353 -> 0.179 ms at B=4
+// 288x576 over the round) whose ncu capture showed 39 M shared-memory wavefronts in 50 M SM cycles -- every thread re-read
+// a 3x3x6 window of g per tile (54 values for 216 FMAs; the 18 scalar loads among
 // them are 4-way bank conflicts) behind two block barriers.  Here a WARP owns a 4 (h) x 32 (w) column of 16 input planes of
 // one pair and walks it along d: the thread's g window ROLLS (three planes of 3 x 6 values in registers; one new plane = three
 // row loads per step, the oldest plane's registers are overwritten -- the step is unrolled by three so that the roles rotate
@@ -237,6 +106,7 @@ conv3d_c1_bwd_weight_kernel(const float* __restrict__ g, const float* __restrict
 // arrive through a warp-private cp.async ring (no block barrier).  A g row in the ring mirrors its global 128-byte line
 // (columns w0..w0+31) and keeps the two halo vectors in a second chunk at a position that rotates with the row (the four
 // rows of a warp's edge loads fall into different banks).  Warps take items warp, warp + n_warps, ...; partial sums as above.
+constexpr int kLbGroups = 296;                                // CTAs per channel pair = partial sums per channel and tap
 constexpr int kWmDS = 16, kWmR = 4;                           // input planes per item, ring slots per warp
 constexpr int kWmRowF = 64, kWmG = 6 * kWmRowF, kWmSlot = kWmG + 2 * 32 * 4;   // floats: g rows | x vectors [2 channels][32 lanes]
 __device__ __forceinline__ int wm_edge(int row) { return 32 + 8 * (row & 3); }   // + 0: columns w0+32..35, + 4: columns w0-4..w0-1
@@ -246,7 +116,11 @@ conv3d_c1_bwd_weight_march_kernel(const float* __restrict__ g, const float* __re
                                   int B, int C, int D, int H, int W, int n_w32, int n_h4, int n_ds) {
     extern __shared__ __align__(128) float wm_smem[];
     __shared__ float red[4][54];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    // the warp index as a value the compiler knows is warp-uniform (from threadIdx.x >> 5 everything a warp decides per item looks
+    // divergent to it: every shuffle gets a convergence barrier, the bookkeeping stays out of the uniform registers)
+    const int warp = (__ballot_sync(0xffffffffu, threadIdx.x >= 32) != 0u) + (__ballot_sync(0xffffffffu, threadIdx.x >= 64) != 0u) +
+                     (__ballot_sync(0xffffffffu, threadIdx.x >= 96) != 0u);
     const int c0 = 2 * blockIdx.y, n_groups = gridDim.x;
     const bool two = c0 + 1 < C;
     const int tw = lane & 7, th = lane >> 3;
@@ -339,22 +213,23 @@ conv3d_c1_bwd_weight_march_kernel(const float* __restrict__ g, const float* __re
         if (!fma) return;
         const float4 x0 = *reinterpret_cast<const float4*>(slot + kWmG + lane * 4);
         const float4 x1 = *reinterpret_cast<const float4*>(slot + kWmG + 128 + lane * 4);
-        // gW[k] += in[p] g[p - k + 1]: for input column i (0..3) tap (kd,kh,kw) pairs with plane 2-kd, row 2-kh, element i + 2 - kw
+        // gW[k] += in[p] g[p - k + 1]: for input column i (0..3) tap (kd,kh,kw) pairs with plane 2-kd, row 2-kh, element i + 2 - kw.
+        // Column-major: 54 independent FMAs per input column (tap-major order chains four dependent FMAs per accumulator and,
+        // with three warps per scheduler, stalls on their latency)
+        const float xa[4] = {x0.x, x0.y, x0.z, x0.w}, xb[4] = {x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-        for (int kd = 0; kd < 3; ++kd)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
+            for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const float* r = kd == 0 ? nw[2 - kh] : (kd == 1 ? mid[2 - kh] : old[2 - kh]);
-                    const int k = (kd * 3 + kh) * 3 + kw;
-                    float a0 = acc[0][k], a1 = acc[1][k];
-                    a0 = __fmaf_rn(x0.x, r[0 + 2 - kw], a0); a1 = __fmaf_rn(x1.x, r[0 + 2 - kw], a1);
-                    a0 = __fmaf_rn(x0.y, r[1 + 2 - kw], a0); a1 = __fmaf_rn(x1.y, r[1 + 2 - kw], a1);
-                    a0 = __fmaf_rn(x0.z, r[2 + 2 - kw], a0); a1 = __fmaf_rn(x1.z, r[2 + 2 - kw], a1);
-                    a0 = __fmaf_rn(x0.w, r[3 + 2 - kw], a0); a1 = __fmaf_rn(x1.w, r[3 + 2 - kw], a1);
-                    acc[0][k] = a0; acc[1][k] = a1;
-                }
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float* r = kd == 0 ? nw[2 - kh] : (kd == 1 ? mid[2 - kh] : old[2 - kh]);
+                        const int k = (kd * 3 + kh) * 3 + kw;
+                        acc[0][k] = __fmaf_rn(xa[i], r[i + 2 - kw], acc[0][k]);
+                        acc[1][k] = __fmaf_rn(xb[i], r[i + 2 - kw], acc[1][k]);
+                    }
     };
     for (int item = blockIdx.x * 4 + warp; item < n_items; item += stride) {
         int b, d0, h0, w0, nu;
@@ -397,7 +272,6 @@ conv3d_c1_bwd_weight_final_kernel(const float* __restrict__ part, float* __restr
     if (lane == 0) gw[c * 27 + k] = (float)a;
 }
 
-constexpr int kLbGroups = 296;
 
 size_t conv3d_c1_bwd_workspace_bytes(int C) { return C > 0 ? (size_t)C * kLbGroups * 27 * sizeof(float) : 0; }
 
@@ -425,16 +299,10 @@ int conv3d_c1_bwd(const float* g, const float* in, const float* w, float* gin, f
         if (int rc = check_launch("conv3d_c1_bwd(data)")) return rc;
     }
     if (gw) {
-        static const bool tile_kernel = getenv("RAG_LC_WTILE") != nullptr;
-        if (tile_kernel) {
-        const size_t wsmem = 2 * tile_bytes + (size_t)2 * 2 * 256 * sizeof(float4);   // two tile buffers + two input-vector buffers
-        conv3d_c1_bwd_weight_kernel<<<dim3(kLbGroups, (C + 1) / 2), 256, wsmem, st>>>(g, in, workspace, B, C, D, H, W, n_wt, n_ht, n_dt);
-        } else {
         const int n_w32 = (W + 31) / 32, n_h4 = (H + 3) / 4, n_ds = (D + kWmDS - 1) / kWmDS;
         if ((long long)B * n_ds * n_h4 * n_w32 >= (1LL << 31)) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: too many tiles");
         const size_t wsmem = (size_t)4 * kWmR * kWmSlot * sizeof(float);
         conv3d_c1_bwd_weight_march_kernel<<<dim3(kLbGroups, (C + 1) / 2), 128, wsmem, st>>>(g, in, workspace, B, C, D, H, W, n_w32, n_h4, n_ds);
-        }
         if (int rc = check_launch("conv3d_c1_bwd(weight)")) return rc;
         conv3d_c1_bwd_weight_final_kernel<<<C, 27 * 32, 0, st>>>(workspace, gw, kLbGroups);
         if (int rc = check_launch("conv3d_c1_bwd(weight final)")) return rc;

@@ -105,7 +105,8 @@ def test_upsample_module_is_a_drop_in():
     assert Upsample(size=[8, 6, 12], mode="trilinear", align_corners=True)(x.cpu()).device.type == "cpu"
 
 
-CONV_CASES = [(1, 12, 16, 12, 24), (2, 12, 9, 5, 36), (1, 5, 3, 4, 8), (2, 12, 64, 24, 192), (1, 64, 6, 9, 40)]
+CONV_CASES = [(1, 12, 16, 12, 24), (2, 12, 9, 5, 36), (1, 5, 3, 4, 8), (2, 12, 64, 24, 192), (1, 64, 6, 9, 40),
+              (1, 3, 17, 7, 68)]     # depth tail of ONE plane behind a full 16-plane segment, ragged h / w
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=str)
