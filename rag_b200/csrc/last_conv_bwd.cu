@@ -2,96 +2,17 @@
 // input (src/models/rag_model.py:269, applied at :361-365; src/automl/operations_3d.py:31-47 with bn=False, relu=False).
 //     gin[b,c,d,h,w]      = sum_{kd,kh,kw} W[0,c,kd,kh,kw] * g[b,0,d-kd+1,h-kh+1,w-kw+1]          (data gradient)
 //     gW[0,c,kd,kh,kw]    = sum_{b,d,h,w}  in[b,c,d+kd-1,h+kh-1,w+kw-1] * g[b,0,d,h,w]            (weight gradient)
-// Both read the ONE-channel upstream gradient g through the same 3x3x6 register window per thread (4 adjacent w): the data
-// gradient re-uses the window for all C channels (1296 FMAs per window, output streamed with 128-bit stores: the C-times
-// larger tensor is written once); the weight gradient walks columns of positions along d with the window ROLLING in registers
-// and keeps 2 x 27 running sums per thread, reduced once per CTA (fixed order, fp64 final pass: deterministic).  cuDNN has no
-// good kernel for a 1-channel side.
+// Both read the ONE-channel upstream gradient g through the same 3x3x6 register window per thread (4 adjacent w) and both are
+// MARCH kernels: a warp owns a 4 (h) x 32 (w) column of 16 planes and walks it along d with the window ROLLING in registers
+// (one new plane = three row loads per step), fed by a warp-private cp.async ring, no block barrier.  The data gradient re-uses
+// the window for all C channels (1296 FMAs per step, output streamed with 128-bit stores: the C-times larger tensor is
+// written once); the weight gradient keeps 2 x 27 running sums per thread, reduced once per CTA (fixed order, fp64 final pass:
+// deterministic).  cuDNN has no good kernel for a 1-channel side.
 #include <cuda_pipeline.h>
 
 #include "common.cuh"
 
 namespace rag {
-
-constexpr int kLbD = 4, kLbH = 8, kLbW = 32;                // tile of positions per CTA: 4 x 8 x 32, thread = 4 adjacent w
-constexpr int kLbSW = kLbW + 8;                             // staged row: w0-4 .. w0+35 (16-byte aligned segments)
-constexpr int kLbRows = (kLbD + 2) * (kLbH + 2);
-
-// stage g[b, d0-1 .. d0+4, h0-1 .. h0+8, w0-4 .. w0+35] (zero outside the volume) into smem [rows][kLbSW]
-__device__ __forceinline__ void lb_stage(float* sm, const float* __restrict__ g, int b, int d0, int h0, int w0, int D, int H, int W) {
-    const size_t vol = (size_t)D * H * W;
-    for (int i = threadIdx.x; i < kLbRows * (kLbSW / 4); i += 256) {
-        const int row = i / (kLbSW / 4), v = i - row * (kLbSW / 4);
-        const int dz = row / (kLbH + 2), hy = row - dz * (kLbH + 2);
-        const int gd = d0 - 1 + dz, gh = h0 - 1 + hy, gw = w0 - 4 + 4 * v;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W)   // W % 4 == 0: a quad is inside or outside as a whole
-            val = __ldg(reinterpret_cast<const float4*>(g + (size_t)b * vol + ((size_t)gd * H + gh) * W + gw));
-        *reinterpret_cast<float4*>(sm + row * kLbSW + 4 * v) = val;
-    }
-}
-
-// the thread's window: win[kd][kh][0..5] = g at (d+kd-1, h+kh-1, w0+4tw-1 .. w0+4tw+4)
-__device__ __forceinline__ void lb_window(const float* sm, int td, int th, int tw, float (&win)[3][3][6]) {
-#pragma unroll
-    for (int kd = 0; kd < 3; ++kd)
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const float* p = sm + ((td + kd) * (kLbH + 2) + th + kh) * kLbSW + 4 * tw;   // column (w0-4) + 4tw
-            const float4 m = *reinterpret_cast<const float4*>(p + 4);
-            win[kd][kh][0] = p[3];
-            win[kd][kh][1] = m.x; win[kd][kh][2] = m.y; win[kd][kh][3] = m.z; win[kd][kh][4] = m.w;
-            win[kd][kh][5] = p[8];
-        }
-}
-
-// grid (ceil(W/32), ceil(H/8), B*ceil(D/4)); 256 threads.  smem: tile | weights [C][28]
-__global__ void __launch_bounds__(256)
-conv3d_c1_bwd_data_kernel(const float* __restrict__ g, const float* __restrict__ wgt, float* __restrict__ gin,
-                          int C, int D, int H, int W, int n_dt) {
-    extern __shared__ __align__(16) float lbd_smem[];
-    float* tile = lbd_smem;
-    float* ws = tile + kLbRows * kLbSW;
-    const int b = blockIdx.z / n_dt, d0 = (blockIdx.z - b * n_dt) * kLbD, h0 = blockIdx.y * kLbH, w0 = blockIdx.x * kLbW;
-    // weights padded to 28 per channel: the 27 taps of a channel are seven broadcast LDS.128 instead of 27 scalar loads
-    for (int i = threadIdx.x; i < C * 28; i += 256) {
-        const int c = i / 28, k = i - c * 28;
-        ws[i] = k < 27 ? __ldg(wgt + c * 27 + k) : 0.f;
-    }
-    lb_stage(tile, g, b, d0, h0, w0, D, H, W);
-    __syncthreads();
-    const int tw = threadIdx.x & 7, th = (threadIdx.x >> 3) & 7, td = threadIdx.x >> 6;
-    const int d = d0 + td, h = h0 + th, w = w0 + 4 * tw;
-    if (d >= D || h >= H || w >= W) return;
-    float win[3][3][6];
-    lb_window(tile, td, th, tw, win);
-    const size_t vol = (size_t)D * H * W;
-    float* o = gin + (size_t)b * C * vol + ((size_t)d * H + h) * W + w;
-    for (int c = 0; c < C; ++c) {
-        float wc[28];
-#pragma unroll
-        for (int q = 0; q < 7; ++q) {
-            const float4 v = *reinterpret_cast<const float4*>(ws + c * 28 + 4 * q);
-            wc[4 * q] = v.x; wc[4 * q + 1] = v.y; wc[4 * q + 2] = v.z; wc[4 * q + 3] = v.w;
-        }
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        // gin[p] = sum_k W[k] g[p - k + 1]: tap (kd,kh,kw) reads the window at (2-kd, 2-kh, i + 2 - kw) for output i
-#pragma unroll
-        for (int kd = 0; kd < 3; ++kd)
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const float wv = wc[(kd * 3 + kh) * 3 + kw];
-                    const float* r = win[2 - kd][2 - kh];
-                    acc.x = __fmaf_rn(wv, r[0 + 2 - kw], acc.x);
-                    acc.y = __fmaf_rn(wv, r[1 + 2 - kw], acc.y);
-                    acc.z = __fmaf_rn(wv, r[2 + 2 - kw], acc.z);
-                    acc.w = __fmaf_rn(wv, r[3 + 2 - kw], acc.w);
-                }
-        st_stream(reinterpret_cast<float4*>(o + (size_t)c * vol), acc);
-    }
-}
 
 // Weight gradient: gW[c][k] = sum_p in[c][p] g[p - k + 1]; grid (n_groups, ceil(C/2)), 128 threads; a CTA accumulates the 27 sums
 // of channels 2cp and 2cp+1 (one g window feeds 216 FMAs instead of 108) over its share of the positions and writes one
@@ -259,6 +180,121 @@ conv3d_c1_bwd_weight_march_kernel(const float* __restrict__ g, const float* __re
     }
 }
 
+// The data gradient (same column walk and ring as the weight gradient; an item per warp): per step the rolling window of g
+// gives, for each of the C channels, 108 FMAs against that channel's 27 weights (seven broadcast LDS.128 from the CTA's padded
+// table) and one streamed 128-bit store.  Its predecessor, a 4 x 8 x 32 tile per CTA, spent a quarter of its instructions in
+// the per-tile prologue (staging through registers, weight table, 27 window loads) for 1296 FMAs per thread: 0.088 -> 0.079 ms
+// at B=4 288x576, 0.489 -> 0.405 ms at B=8 480x960.
+// grid ceil(items / 4), 128 threads.  smem: ring [4 warps][kWmR][6 x 64] | weights [C][28]
+constexpr int kDmSlot = kWmG;
+__global__ void __launch_bounds__(128, 4)
+conv3d_c1_bwd_data_march_kernel(const float* __restrict__ g, const float* __restrict__ wgt, float* __restrict__ gin,
+                                int B, int C, int D, int H, int W, int n_w32, int n_h4, int n_ds) {
+    extern __shared__ __align__(128) float dm_smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = (__ballot_sync(0xffffffffu, threadIdx.x >= 32) != 0u) + (__ballot_sync(0xffffffffu, threadIdx.x >= 64) != 0u) +
+                     (__ballot_sync(0xffffffffu, threadIdx.x >= 96) != 0u);
+    float* ring = dm_smem + warp * (kWmR * kDmSlot);
+    float* ws = dm_smem + 4 * kWmR * kDmSlot;
+    for (int i = threadIdx.x; i < C * 28; i += 128) {
+        const int c = i / 28, k = i - c * 28;
+        ws[i] = k < 27 ? __ldg(wgt + c * 27 + k) : 0.f;
+    }
+    __syncthreads();
+    const int n_items = B * n_ds * n_h4 * n_w32;
+    const int item = blockIdx.x * 4 + warp;
+    if (item >= n_items) return;
+    const int tw = lane & 7, th = lane >> 3;
+    const size_t vol = (size_t)D * H * W;
+    const ptrdiff_t HW = (ptrdiff_t)H * W;
+    int t = item;
+    const int wq = t % n_w32; t /= n_w32;
+    const int hq = t % n_h4; t /= n_h4;
+    const int dq = t % n_ds, b = t / n_ds;
+    const int d0 = dq * kWmDS, h0 = hq * 4, w0 = wq * 32, nu = min(kWmDS, D - d0) + 2;
+
+    const bool k1_main = lane < 16, k1_on = lane < 28;
+    const int r0 = lane >> 3, r1 = k1_main ? 4 + (lane >> 3) : (lane - 16) >> 1;
+    const int cq0 = 4 * (lane & 7), cq1 = k1_main ? 4 * (lane & 7) : ((lane & 1) ? -4 : 32);
+    const int so0 = r0 * kWmRowF + 4 * (lane & 7), so1 = r1 * kWmRowF + (k1_main ? 4 * (lane & 7) : wm_edge(r1) + ((lane & 1) ? 4 : 0));
+    const int gh0 = h0 - 1 + r0, gw0 = w0 + cq0, gh1 = h0 - 1 + r1, gw1 = w0 + cq1;
+    const float* gb = g + (ptrdiff_t)b * (ptrdiff_t)vol + (ptrdiff_t)(d0 - 1) * HW;
+    const float *pg0 = gb + (ptrdiff_t)gh0 * W + gw0, *pg1 = gb + (ptrdiff_t)gh1 * W + gw1;
+    const bool v0 = gh0 >= 0 && gh0 < H && gw0 < W, v1 = k1_on && gh1 >= 0 && gh1 < H && gw1 >= 0 && gw1 < W;
+    int pu = 0, ps = 0;
+    auto copy_next = [&]() {
+        if (pu < nu) {
+            float* slot = ring + ps * kDmSlot;
+            const bool pl = (unsigned)(d0 - 1 + pu) < (unsigned)D;
+            const bool ok0 = pl && v0, ok1 = pl && v1;
+            __pipeline_memcpy_async(slot + so0, ok0 ? pg0 : g, 16, ok0 ? 0 : 16);
+            if (k1_on) __pipeline_memcpy_async(slot + so1, ok1 ? pg1 : g, 16, ok1 ? 0 : 16);
+            pg0 += HW; pg1 += HW; ++pu;
+            if (++ps == kWmR) ps = 0;
+        }
+        __pipeline_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < kWmR - 1; ++i) copy_next();
+
+    const int h = h0 + th, w = w0 + 4 * tw;
+    const bool on = h < H && w < W;
+    float* o = gin + (size_t)b * C * vol + (size_t)d0 * H * W + (size_t)(on ? h : 0) * W + (on ? w : 0);   // plane d0, channel 0
+    float W0[3][6], W1[3][6], W2[3][6];
+    int cs = 0;
+    const bool edge = tw == 0 || tw == 7;
+    auto unit = [&](bool out, float (&nw)[3][6], const float (&old)[3][6], const float (&mid)[3][6]) {
+        __pipeline_wait_prior(kWmR - 2);
+        __syncwarp();
+        copy_next();
+        const float* slot = ring + cs * kDmSlot;
+        if (++cs == kWmR) cs = 0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int row = th + j;
+            const float* p = slot + row * kWmRowF;
+            const float4 m = *reinterpret_cast<const float4*>(p + 4 * tw);
+            const float e = edge ? p[wm_edge(row) + (tw == 0 ? 7 : 0)] : 0.f;
+            const float l = __shfl_up_sync(0xffffffffu, m.w, 1, 8), r = __shfl_down_sync(0xffffffffu, m.x, 1, 8);
+            nw[j][0] = tw == 0 ? e : l;
+            nw[j][1] = m.x; nw[j][2] = m.y; nw[j][3] = m.z; nw[j][4] = m.w;
+            nw[j][5] = tw == 7 ? e : r;
+        }
+        if (!out) return;
+        // gin[p] = sum_k W[k] g[p - k + 1]: tap (kd,kh,kw) reads plane 2-kd (old / mid / nw = g at d-1 / d / d+1), row 2-kh, element i + 2 - kw
+        for (int c = 0; c < C; ++c) {
+            float wc[28];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const float4 v = *reinterpret_cast<const float4*>(ws + c * 28 + 4 * q);
+                wc[4 * q] = v.x; wc[4 * q + 1] = v.y; wc[4 * q + 2] = v.z; wc[4 * q + 3] = v.w;
+            }
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float wv = wc[(kd * 3 + kh) * 3 + kw];
+                        const float* r = kd == 0 ? nw[2 - kh] : (kd == 1 ? mid[2 - kh] : old[2 - kh]);
+                        acc.x = __fmaf_rn(wv, r[0 + 2 - kw], acc.x);
+                        acc.y = __fmaf_rn(wv, r[1 + 2 - kw], acc.y);
+                        acc.z = __fmaf_rn(wv, r[2 + 2 - kw], acc.z);
+                        acc.w = __fmaf_rn(wv, r[3 + 2 - kw], acc.w);
+                    }
+            if (on) st_stream(reinterpret_cast<float4*>(o + (size_t)c * vol), acc);
+        }
+        o += HW;
+    };
+    for (int u = 0; u < nu; u += 3) {                             // unit u: planes (u-2, u-1, u) = (old, mid, new) -> output plane d0 + u - 2
+        unit(u >= 2, W0, W1, W2);
+        if (u + 1 < nu) unit(u + 1 >= 2, W1, W2, W0);
+        if (u + 2 < nu) unit(true, W2, W0, W1);
+    }
+    __pipeline_wait_prior(0);
+}
+
 // gw[c][k] = sum over groups of part[c][grp][k], fixed order, fp64.  grid C; 27 warps (one per tap): the lanes take every
 // 32nd group, then a shuffle tree in a fixed order (the first version walked the 296 partials of a tap with ONE thread:
 // 23 us of dependent loads).
@@ -285,22 +321,17 @@ int conv3d_c1_bwd(const float* g, const float* in, const float* w, float* gin, f
     if (W % 4 != 0) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: W=%d must be a multiple of 4", W);
     if ((size_t)D * H * W >= ((size_t)1 << 31) || C > 1024) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: D*H*W must be < 2^31 and C <= 1024");
     if (!aligned(g, 16) || (gin && !aligned(gin, 16)) || (in && !aligned(in, 16))) return fail(RAG_E_ALIGN, "conv3d_c1_bwd: g, in, gin must be 16-byte aligned");
-    const int n_wt = (W + kLbW - 1) / kLbW, n_ht = (H + kLbH - 1) / kLbH, n_dt = (D + kLbD - 1) / kLbD;
-    if ((long long)B * n_dt > 65535 || n_ht > 65535 || (long long)B * n_dt * n_ht * n_wt >= (1LL << 31))
-        return fail(RAG_E_SHAPE, "conv3d_c1_bwd: B*ceil(D/4) and ceil(H/8) must be <= 65535");
-    const size_t tile_bytes = (size_t)kLbRows * kLbSW * sizeof(float);
+    const int n_w32 = (W + 31) / 32, n_h4 = (H + 3) / 4, n_ds = (D + kWmDS - 1) / kWmDS;
+    const long long items = (long long)B * n_ds * n_h4 * n_w32;               // 4 (h) x 32 (w) columns of 16 planes
+    if (items >= (1LL << 31)) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: too many tiles");
     if (gin) {
-        const size_t smem = tile_bytes + (size_t)C * 28 * sizeof(float);
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(conv3d_c1_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return fail((int)e, "conv3d_c1_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        }
-        conv3d_c1_bwd_data_kernel<<<dim3(n_wt, n_ht, B * n_dt), 256, smem, st>>>(g, w, gin, C, D, H, W, n_dt);
+        const size_t dsmem = ((size_t)4 * kWmR * kDmSlot + (size_t)C * 28) * sizeof(float);
+        cudaError_t e = cudaFuncSetAttribute(conv3d_c1_bwd_data_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
+        if (e != cudaSuccess) return fail((int)e, "conv3d_c1_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        conv3d_c1_bwd_data_march_kernel<<<(unsigned)((items + 3) / 4), 128, dsmem, st>>>(g, w, gin, B, C, D, H, W, n_w32, n_h4, n_ds);
         if (int rc = check_launch("conv3d_c1_bwd(data)")) return rc;
     }
     if (gw) {
-        const int n_w32 = (W + 31) / 32, n_h4 = (H + 3) / 4, n_ds = (D + kWmDS - 1) / kWmDS;
-        if ((long long)B * n_ds * n_h4 * n_w32 >= (1LL << 31)) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: too many tiles");
         const size_t wsmem = (size_t)4 * kWmR * kWmSlot * sizeof(float);
         conv3d_c1_bwd_weight_march_kernel<<<dim3(kLbGroups, (C + 1) / 2), 128, wsmem, st>>>(g, in, workspace, B, C, D, H, W, n_w32, n_h4, n_ds);
         if (int rc = check_launch("conv3d_c1_bwd(weight)")) return rc;
