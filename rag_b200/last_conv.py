@@ -74,7 +74,7 @@ def _layer_ok(conv: nn.Module, x: torch.Tensor) -> bool:
     if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
             and x.shape[1] == conv.in_channels and x.numel() > 0 and x.shape[-1] % 4 == 0
             and x.shape[2] * x.shape[3] * x.shape[4] < 2 ** 31 and x.shape[0] * ((x.shape[2] + 15) // 16) <= 65535
-            and x.shape[0] * ((x.shape[2] + 3) // 4) <= 65535):
+            and x.shape[0] * ((x.shape[2] + 15) // 16) * ((x.shape[3] + 3) // 4) * ((x.shape[4] + 31) // 32) < 2 ** 31):   # conv3d_c1_bwd
         return False
     if x.is_contiguous() and x.data_ptr() % 16:
         return False
