@@ -420,11 +420,12 @@ int conv3d_c1_fwd(const float* in, const float* w, float* out, int B, int C, int
                           cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: weight copy: %s", cudaGetErrorString(e));
     // The march kernel (one warp per CTA, 8 output planes each) wins wherever its grid fills the machine: 0.366 vs 0.494 ms
-    // at B=8 480x960, 0.082 vs 0.111 ms at B=4 288x576; below half a wave of warps the tile kernel's 4-warp CTAs are faster.
+    // at B=8 480x960, 0.082 vs 0.111 ms at B=4 288x576; the crossover is at 600-800 warps (one pair at 480x960, 800 warps: 0.081 vs
+    // 0.085 ms; two pairs at 288x576, 576 warps: 0.064 vs 0.062 ms), below it the tile kernel's 4-warp CTAs are faster.
     constexpr int kMarchDT = 8, kMarchRing = 3;
     const int n_dtm = (D + kMarchDT - 1) / kMarchDT;
     const long long warps = (long long)((W + kLcWT - 1) / kLcWT) * ((H + kLcHT - 1) / kLcHT) * B * n_dtm;
-    if (warps >= 6LL * num_sms() && (long long)B * n_dtm <= 65535) {
+    if (warps >= 5LL * num_sms() && (long long)B * n_dtm <= 65535) {
         auto mk = conv3d_c1_march_kernel<kMarchRing>;
         e = cudaFuncSetAttribute(mk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return fail((int)e, "conv3d_c1_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -17,7 +17,7 @@ SHAPES = [
 ]
 
 # Shapes whose grid is deep enough for the march kernel (one warp per 8 x 8 x 64 column; conv3d_c1_fwd picks it from
-# six warps per SM up): ragged h / w tiles, depth tails of one and two planes, one channel, the real channel count
+# five warps per SM up): ragged h / w tiles, depth tails of one and two planes, one channel, the real channel count
 MARCH_SHAPES = [
     (6, 3, 17, 100, 200),     # D % 8 == 1: the last column holds ONE output plane; H % 8 != 0, W % 64 != 0
     (8, 1, 26, 72, 256),      # a single channel (the copy ring runs ahead across planes); D % 8 == 2
@@ -38,7 +38,7 @@ def test_conv3d_c1_matches_fp32_reference(shape):
 
     b, c, d, h, w = shape
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    assert (_march_warps(shape) >= 6 * sms) == (shape in MARCH_SHAPES), "the case no longer exercises the kernel it was written for"
+    assert (_march_warps(shape) >= 5 * sms) == (shape in MARCH_SHAPES), "the case no longer exercises the kernel it was written for"
     g = gen(sum(shape))
     x = randn((b, c, d, h, w), g)
     wt = randn((1, c, 3, 3, 3), g) * 0.1
