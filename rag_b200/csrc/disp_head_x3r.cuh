@@ -117,7 +117,9 @@ head_fwd_x3r_kernel(const float* __restrict__ cost, float* __restrict__ disp, fl
     float* tile = x3r_smem;
     float2* tot = reinterpret_cast<float2*>(x3r_smem + STAGES * kStageFloats);   // [18][128]
     float2* kap = tot + 18 * NT;                                                   // [Dl][2]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int tid = threadIdx.x;
+    asm volatile("" : "+r"(tid));     // one read: the compiler otherwise re-reads SR_TID (27 S2R per chunk of bins) wherever it needs a thread index
+    const int lane = tid & 31, warp = tid >> 5;
     // kappa_q(j) = 3 ln2 (lambda_fp32(3j+1+q) - q/3), q = 1, 2: the 3 converts du (z/3 domain) to dz.
     // lambda - fl(q/3) is exact in fp32 (Sterbenz); fl(1/3) - 1/3 = 2^-25/3, fl(2/3) - 2/3 = 2^-24/3.
     // Once per CTA; published by the first chunk barrier of the first tile.
