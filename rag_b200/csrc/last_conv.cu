@@ -199,6 +199,21 @@ conv3d_c1_kernel(const float* __restrict__ in, const float* __restrict__ w, floa
 // row, which own columns 8tw..8tw+7, hit eight different bank groups with each of their LDS.128.
 constexpr int kLmSW = 96, kLmPlane = kLcSH * kLmSW;           // row stride (floats), floats per staged plane
 __host__ __device__ constexpr int lm_swz(int v) { return v < 8 || v > 15 ? v : v ^ 1; }
+// the layout's bank claim, checked at compile time: the eight lanes of a row (tw = 0..7) read three vectors each -- left
+// neighbour (the edge chunk's vector 6 for lane 0), own first, own second -- and every one of the three warp-wide loads must
+// touch eight different 16-byte bank groups
+constexpr int lm_vec_left(int tw) { return tw == 0 ? 16 + 6 : lm_swz(2 * tw - 1); }
+constexpr bool lm_groups_distinct(int which) {
+    int seen = 0;
+    for (int tw = 0; tw < 8; ++tw) {
+        const int v = which == 0 ? lm_vec_left(tw) : (which == 1 ? lm_swz(2 * tw) : lm_swz(2 * tw + 1));
+        const int grp = v & 7;
+        if (seen & (1 << grp)) return false;
+        seen |= 1 << grp;
+    }
+    return true;
+}
+static_assert(lm_groups_distinct(0) && lm_groups_distinct(1) && lm_groups_distinct(2), "march kernel: LDS.128 bank conflict in the row layout");
 __device__ __forceinline__ void lm_cp16(float* smem, const float* g) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(g) : "memory");
 }
