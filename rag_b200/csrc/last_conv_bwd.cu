@@ -20,7 +20,7 @@ namespace rag {
 // History: a tile kernel (4 x 8 x 32 positions per CTA step, g tile double-buffered by cp.async, 0.353 -> 0.179 ms at B=4
 // 288x576 over the round) whose ncu capture showed 39 M shared-memory wavefronts in 50 M SM cycles -- every thread re-read
 // a 3x3x6 window of g per tile (54 values for 216 FMAs; the 18 scalar loads among
-// them are 4-way bank conflicts) behind two block barriers.  Here a WARP owns a 4 (h) x 32 (w) column of 16 input planes of
+// them are 4-way bank conflicts) behind two block barriers.  Here a WARP owns a 4 (h) x 32 (w) column of 32 input planes of
 // one pair and walks it along d: the thread's g window ROLLS (three planes of 3 x 6 values in registers; one new plane = three
 // row loads per step, the oldest plane's registers are overwritten -- the step is unrolled by three so that the roles rotate
 // without moves), the neighbours' elements come by shuffle, and the g plane plus the thread's two input vectors of the step
@@ -28,7 +28,7 @@ namespace rag {
 // (columns w0..w0+31) and keeps the two halo vectors in a second chunk at a position that rotates with the row (the four
 // rows of a warp's edge loads fall into different banks).  Warps take items warp, warp + n_warps, ...; partial sums as above.
 constexpr int kLbGroups = 296;                                // CTAs per channel pair = partial sums per channel and tap
-constexpr int kWmDS = 16, kWmR = 4;                           // input planes per item, ring slots per warp
+constexpr int kWmDS = 32, kWmR = 4;                           // input planes per item (16: 0.121 ms, 32: 0.115 ms), ring slots per warp
 constexpr int kWmRowF = 64, kWmG = 6 * kWmRowF, kWmSlot = kWmG + 2 * 32 * 4;   // floats: g rows | x vectors [2 channels][32 lanes]
 __device__ __forceinline__ int wm_edge(int row) { return 32 + 8 * (row & 3); }   // + 0: columns w0+32..35, + 4: columns w0-4..w0-1
 
@@ -186,7 +186,7 @@ conv3d_c1_bwd_weight_march_kernel(const float* __restrict__ g, const float* __re
 // the per-tile prologue (staging through registers, weight table, 27 window loads) for 1296 FMAs per thread: 0.088 -> 0.079 ms
 // at B=4 288x576, 0.489 -> 0.405 ms at B=8 480x960.
 // grid ceil(items / 4), 128 threads.  smem: ring [4 warps][kWmR][6 x 64] | weights [C][28]
-constexpr int kDmSlot = kWmG;
+constexpr int kDmSlot = kWmG, kDmDS = 16;                  // 16 planes per item here: twice the warps (0.079 vs 0.090 ms with 32)
 __global__ void __launch_bounds__(128, 4)
 conv3d_c1_bwd_data_march_kernel(const float* __restrict__ g, const float* __restrict__ wgt, float* __restrict__ gin,
                                 int B, int C, int D, int H, int W, int n_w32, int n_h4, int n_ds) {
@@ -211,7 +211,7 @@ conv3d_c1_bwd_data_march_kernel(const float* __restrict__ g, const float* __rest
     const int wq = t % n_w32; t /= n_w32;
     const int hq = t % n_h4; t /= n_h4;
     const int dq = t % n_ds, b = t / n_ds;
-    const int d0 = dq * kWmDS, h0 = hq * 4, w0 = wq * 32, nu = min(kWmDS, D - d0) + 2;
+    const int d0 = dq * kDmDS, h0 = hq * 4, w0 = wq * 32, nu = min(kDmDS, D - d0) + 2;
 
     const bool k1_main = lane < 16, k1_on = lane < 28;
     const int r0 = lane >> 3, r1 = k1_main ? 4 + (lane >> 3) : (lane - 16) >> 1;
@@ -321,14 +321,14 @@ int conv3d_c1_bwd(const float* g, const float* in, const float* w, float* gin, f
     if (W % 4 != 0) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: W=%d must be a multiple of 4", W);
     if ((size_t)D * H * W >= ((size_t)1 << 31) || C > 1024) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: D*H*W must be < 2^31 and C <= 1024");
     if (!aligned(g, 16) || (gin && !aligned(gin, 16)) || (in && !aligned(in, 16))) return fail(RAG_E_ALIGN, "conv3d_c1_bwd: g, in, gin must be 16-byte aligned");
-    const int n_w32 = (W + 31) / 32, n_h4 = (H + 3) / 4, n_ds = (D + kWmDS - 1) / kWmDS;
-    const long long items = (long long)B * n_ds * n_h4 * n_w32;               // 4 (h) x 32 (w) columns of 16 planes
+    const int n_w32 = (W + 31) / 32, n_h4 = (H + 3) / 4, n_ds = (D + kWmDS - 1) / kWmDS, n_dsd = (D + kDmDS - 1) / kDmDS;
+    const long long items = (long long)B * n_dsd * n_h4 * n_w32;              // data gradient: 4 (h) x 32 (w) columns of 16 planes
     if (items >= (1LL << 31)) return fail(RAG_E_SHAPE, "conv3d_c1_bwd: too many tiles");
     if (gin) {
         const size_t dsmem = ((size_t)4 * kWmR * kDmSlot + (size_t)C * 28) * sizeof(float);
         cudaError_t e = cudaFuncSetAttribute(conv3d_c1_bwd_data_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
         if (e != cudaSuccess) return fail((int)e, "conv3d_c1_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        conv3d_c1_bwd_data_march_kernel<<<(unsigned)((items + 3) / 4), 128, dsmem, st>>>(g, w, gin, B, C, D, H, W, n_w32, n_h4, n_ds);
+        conv3d_c1_bwd_data_march_kernel<<<(unsigned)((items + 3) / 4), 128, dsmem, st>>>(g, w, gin, B, C, D, H, W, n_w32, n_h4, n_dsd);
         if (int rc = check_launch("conv3d_c1_bwd(data)")) return rc;
     }
     if (gw) {

@@ -106,7 +106,8 @@ def test_upsample_module_is_a_drop_in():
 
 
 CONV_CASES = [(1, 12, 16, 12, 24), (2, 12, 9, 5, 36), (1, 5, 3, 4, 8), (2, 12, 64, 24, 192), (1, 64, 6, 9, 40),
-              (1, 3, 17, 7, 68)]     # depth tail of ONE plane behind a full 16-plane segment, ragged h / w
+              (1, 3, 17, 7, 68),     # depth tail of ONE plane behind a full 16-plane segment (data gradient), ragged h / w
+              (1, 2, 33, 5, 36)]     # the same behind a 32-plane segment (weight gradient)
 
 
 @pytest.mark.parametrize("case", CONV_CASES, ids=str)
