@@ -1,5 +1,5 @@
 """Time rag_conv3d_c1_fwd (last_3_3d forward) and check it against an fp64 convolution on a sub-block.
-Usage: python tools/conv_time.py   (RAG_LC_PAIR=1 selects the pair kernel while it is under evaluation)"""
+Usage: python tools/conv_time.py"""
 import json, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rag_b200 import _cabi
