@@ -162,13 +162,25 @@ conv3d_c1_bwd_weight_march_kernel(const float* __restrict__ g, const float* __re
         }
     }
     __pipeline_wait_prior(0);
-    // CTA reduction, fixed order: lanes by shuffle tree, then the 4 warps in order
+    // CTA reduction, fixed order: a value-halving butterfly over the lanes (at every stage a lane hands half of its values to its
+    // partner and adds the half it receives: 62 shuffles for 54 values instead of 270; lane L ends with the sums of values 2L
+    // and 2L+1), then the 4 warps in order
+    {
+        float v[64];
 #pragma unroll
-    for (int k = 0; k < 54; ++k) {
-        float v = acc[k / 27][k % 27];
+        for (int k = 0; k < 64; ++k) v[k] = k < 54 ? acc[k / 27][k % 27] : 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) red[warp][k] = v;
+        for (int st = 0; st < 5; ++st) {
+            const int m = 16 >> st, n = 32 >> st;                 // partner distance, values kept after this stage
+            const bool up = (lane & m) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const float keep = up ? v[i + n] : v[i], send = up ? v[i] : v[i + n];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+            }
+        }
+        if (2 * lane < 54) red[warp][2 * lane] = v[0];
+        if (2 * lane + 1 < 54) red[warp][2 * lane + 1] = v[1];
     }
     __syncthreads();
     if (threadIdx.x < 54 && (threadIdx.x < 27 || two)) {
